@@ -1,0 +1,454 @@
+// patch_cnn: conv1 -> (+res, ReLU, 2x2 avg-pool) -> conv2 -> (+res, ReLU, 2x2 avg-pool)
+// for every pixel's w x w window of the conv0 map (tools/models.py:133-140 applied to the
+// patch hyper_tools.py:226-243 would have materialised).  sm_100a only: tcgen05.mma
+// (kind::f16, fp16 operands = TF32's 11-bit significand, fp32 accumulate in TMEM).
+//
+// Persistent kernel, one CTA per SM, warp-specialised:
+//   warps 0-3  epilogue  (TMEM -> registers: bias + residual + ReLU + pool -> next stage)
+//   warps 4-7  loaders   (window of F0pad -> shared memory, zero-padded parity planes)
+//   warp  8    MMA issuer (one thread) + TMEM allocator
+//
+// Implicit GEMM without im2col: activations live in shared memory in the UMMA "no swizzle,
+// K-major" canonical layout with SBO = 128 B, i.e. for every 16-byte K-chunk (8 channels) a
+// *linear* array of positions, 16 B apart.  A 3x3 tap is then nothing but a different start
+// address of the A descriptor (row-major positions with a zero-padded border), so the nine
+// taps x four K-steps of a tile are 36 back-to-back tcgen05.mma (M=128, N=64, K=16) on the
+// same buffer.  Rows are split by parity into two planes (even rows / odd rows) so that the
+// two rows of every 2x2 pooling window land in the SAME TMEM lane of two accumulator tiles
+// and the two columns in adjacent lanes: pooling is one add + one shfl_xor in the epilogue.
+#include "common.cuh"
+
+namespace cmlpl {
+
+template <int W>
+struct PatchCfg {
+  static_assert(W % 4 == 0, "two 2x2 pools need w % 4 == 0");
+  // ---- conv1 input: W x W, parity planes of (W/2+1) rows x (W+2) padded columns
+  static constexpr int H1 = W;
+  static constexpr int PW1 = W + 2;
+  static constexpr int PR1 = W / 2 + 1;
+  static constexpr int ENT1 = 1 + PR1 * PW1;        // +1 leading zero entry (x = -1 of row 0)
+  static constexpr int CH1 = ENT1 * 16;             // bytes between 16-B K-chunks (= LBO)
+  static constexpr int PLANE1 = 8 * CH1;
+  static constexpr int M1 = (W / 2) * PW1;          // outputs per parity
+  static constexpr int NT1 = (M1 + 127) / 128;      // 128-row tiles per parity
+  // ---- conv2 input: W/2 x W/2
+  static constexpr int H2 = W / 2;
+  static constexpr int PW2 = H2 + 2;
+  static constexpr int PR2 = H2 / 2 + 1;
+  static constexpr int ENT2 = 1 + PR2 * PW2;
+  static constexpr int CH2 = ENT2 * 16;
+  static constexpr int PLANE2 = 8 * CH2;
+  static constexpr int M2 = (H2 / 2) * PW2;
+  static_assert(M2 <= 128, "conv2 parity plane must fit one tile");
+  static constexpr int P = (W / 4) * (W / 4);       // pooled positions written per pixel
+  // ---- TMEM columns (fp32 accumulators, 64 per tile)
+  static constexpr int TM_C1 = 0;                   // (half h, parity q) -> (h*2+q)*64
+  static constexpr int TM_C2 = NT1 * 2 * 64;        // parity q -> TM_C2 + q*64
+  static constexpr int TM_COLS = 512;
+  static_assert(TM_C2 + 128 <= TM_COLS, "TMEM budget");
+  // ---- shared memory map (bytes)
+  static constexpr int WBYTES = 9 * 8 * 64 * 8 * 2;  // one conv's weights, 73 728 B
+  static constexpr int S_W1 = 0;
+  static constexpr int S_W2 = S_W1 + WBYTES;
+  static constexpr int S_A2 = S_W2 + WBYTES;
+  static constexpr int S_A1 = S_A2 + 2 * PLANE2;
+  static constexpr int S_BIAS = S_A1 + 2 * PLANE1;   // b1[64] b2[64] f32
+  static constexpr int S_BAR = S_BIAS + 512;         // 16 mbarriers
+  static constexpr int S_TMEM = S_BAR + 128;         // tmem base address
+  // the last 128-row tile reads up to entry 128*NT1-1 + PW1+1 (+1 leading) of a chunk plane;
+  // whatever lies beyond ENT1 only feeds discarded output rows but must be mapped memory.
+  static constexpr int OVER1 = (128 * NT1 + PW1 + 2 - ENT1) * 16;
+  static constexpr int S_END0 = S_TMEM + 16;
+  static constexpr int S_END = (S_A1 + 2 * PLANE1 + (OVER1 > 0 ? OVER1 : 0)) > S_END0
+                                   ? (S_A1 + 2 * PLANE1 + (OVER1 > 0 ? OVER1 : 0)) : S_END0;
+  static constexpr int SMEM = (S_END + 127) / 128 * 128;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap (kernel error), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  printf("patch_cnn: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, M=128 N=64 K=16, fp16 in / fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major (cute/arch/mma_sm100_desc.hpp):
+//   [0,14) start>>4 | [16,30) LBO>>4 (stride between the two 16-B K-chunks of one MMA)
+//   [32,46) SBO>>4 (stride between 8-row groups) | [46,48) version=1 | [61,64) layout=0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) |
+         (uint64_t(1) << 46);
+}
+// instruction descriptor kind::f16: c=f32 (bit4), a=b=f16 (0), K-major both, N>>3 @17, M>>4 @24
+constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(64 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+
+// which parity plane / row offset feeds tap row dy of an output row of parity q:
+//   even outputs (y=2i): dy=0 -> odd plane row i (row 0 of the odd plane is the zero row y=-1),
+//                        dy=1 -> even plane row i, dy=2 -> odd plane row i+1
+//   odd outputs (y=2i+1): dy=0 -> even plane row i, dy=1 -> odd plane row i+1, dy=2 -> even plane row i+1
+__device__ __forceinline__ void tap_src(int q, int dy, int& plane, int& roff) {
+  if (q == 0) { plane = (dy == 1) ? 0 : 1; roff = (dy == 2) ? 1 : 0; }
+  else        { plane = (dy == 1) ? 1 : 0; roff = (dy == 0) ? 0 : 1; }
+}
+
+enum { BAR_A1_FULL = 0, BAR_A1_EMPTY, BAR_C1_FULL0, BAR_C1_FULL1, BAR_C1_EMPTY0, BAR_C1_EMPTY1,
+       BAR_A2_FULL, BAR_C2_FULL, BAR_C2_EMPTY, BAR_COUNT };
+
+constexpr int kEpiThreads = 128, kLoadThreads = 128, kThreads = kEpiThreads + kLoadThreads + 32;
+
+template <int W>
+__global__ void __launch_bounds__(kThreads, 1)
+patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
+                 const unsigned char* __restrict__ packed_w1, const unsigned char* __restrict__ packed_w2,
+                 const float* __restrict__ b1g, const float* __restrict__ b2g, __half* __restrict__ p2out) {
+  using Cfg = PatchCfg<W>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + Cfg::S_BAR;
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::S_BIAS);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::S_TMEM);
+
+  const int64_t npix = int64_t(band_rows) * cols;
+  const int64_t per = (npix + gridDim.x - 1) / gridDim.x;
+  const int64_t p_begin = blockIdx.x * per;
+  const int64_t p_end = (p_begin + per < npix) ? p_begin + per : npix;
+  const int pitch = cols + W - 1;   // padded map width in pixels
+
+  // ---------------------------------------------------------------- one-time setup
+  {  // weights -> smem (already in UMMA layout), zero the activation planes, biases
+    const uint4* g1 = reinterpret_cast<const uint4*>(packed_w1);
+    const uint4* g2 = reinterpret_cast<const uint4*>(packed_w2);
+    uint4* s1 = reinterpret_cast<uint4*>(smem + Cfg::S_W1);
+    uint4* s2 = reinterpret_cast<uint4*>(smem + Cfg::S_W2);
+    for (int i = tid; i < Cfg::WBYTES / 16; i += kThreads) { s1[i] = __ldg(g1 + i); s2[i] = __ldg(g2 + i); }
+    uint4* z = reinterpret_cast<uint4*>(smem + Cfg::S_A2);
+    const int zn = (Cfg::SMEM - Cfg::S_A2) / 16;
+    for (int i = tid; i < zn; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  if (tid < 64) { sbias[tid] = b1g[tid]; sbias[64 + tid] = b2g[tid]; }
+  if (tid == 0) {
+    mbar_init(bars + 8 * BAR_A1_FULL, kLoadThreads);
+    mbar_init(bars + 8 * BAR_A1_EMPTY, 1);
+    mbar_init(bars + 8 * BAR_C1_FULL0, 1);
+    mbar_init(bars + 8 * BAR_C1_FULL1, 1);
+    mbar_init(bars + 8 * BAR_C1_EMPTY0, kEpiThreads);
+    mbar_init(bars + 8 * BAR_C1_EMPTY1, kEpiThreads);
+    mbar_init(bars + 8 * BAR_A2_FULL, kEpiThreads);
+    mbar_init(bars + 8 * BAR_C2_FULL, 1);
+    mbar_init(bars + 8 * BAR_C2_EMPTY, kEpiThreads);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(sbase + Cfg::S_TMEM, Cfg::TM_COLS);
+  fence_proxy_async();   // weights / zeros written through the generic proxy, read by the MMA (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ================================================================ LOADERS
+    const int lt = tid - kEpiThreads;                        // 0..127
+    constexpr int ITEMS = W * W * 8;                         // 16-byte items per patch
+    constexpr int PER = (ITEMS + kLoadThreads - 1) / kLoadThreads;
+    uint32_t ph = 0;
+    for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
+      const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
+      const __half* src0 = f0pad + (int64_t(rb) * pitch + c) * 64;
+      mbar_wait(bars + 8 * BAR_A1_EMPTY, ph ^ 1, 1);         // conv1 of the previous patch has read A1
+      uint4 v[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int it = lt + j * kLoadThreads;
+        if (it < ITEMS) {
+          const int pix = it >> 3, ch = it & 7;
+          const int y = pix / W, x = pix - y * W;
+          v[j] = __ldg(reinterpret_cast<const uint4*>(src0 + (int64_t(y) * pitch + x) * 64) + ch);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int it = lt + j * kLoadThreads;
+        if (it < ITEMS) {
+          const int pix = it >> 3, ch = it & 7;
+          const int y = pix / W, x = pix - y * W;
+          const int q = y & 1, prow = (y + q) >> 1;          // even plane: y/2 ; odd plane: (y+1)/2
+          const int ent = 1 + prow * Cfg::PW1 + x;
+          *reinterpret_cast<uint4*>(smem + Cfg::S_A1 + q * Cfg::PLANE1 + ch * Cfg::CH1 + ent * 16) = v[j];
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + 8 * BAR_A1_FULL);
+    }
+  } else if (warp == 8) {
+    // ================================================================ MMA ISSUER
+    if (lane == 0) {
+      uint32_t ph = 0;
+      for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
+        mbar_wait(bars + 8 * BAR_A1_FULL, ph, 2);
+        tc_fence_after();
+        // ---- conv1: NT1 halves x 2 parities, 9 taps x 4 K-steps each
+#pragma unroll 1
+        for (int h = 0; h < Cfg::NT1; ++h) {
+          mbar_wait(bars + 8 * (BAR_C1_EMPTY0 + h), ph ^ 1, 3);   // epilogue drained this half (prev patch)
+          tc_fence_after();
+#pragma unroll 1
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t d = tmem + Cfg::TM_C1 + (h * 2 + q) * 64;
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              int plane, roff;
+              tap_src(q, dy, plane, roff);
+              const uint32_t a0 = sbase + Cfg::S_A1 + plane * Cfg::PLANE1 +
+                                  (1 + roff * Cfg::PW1 + (dx - 1) + h * 128) * 16;
+              const uint32_t b0 = sbase + Cfg::S_W1 + tap * 8192;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_f16(d, make_desc(a0 + ks * 2 * Cfg::CH1, Cfg::CH1, 128),
+                         make_desc(b0 + ks * 2048, 1024, 128), kIdesc, acc);
+                acc = 1;
+              }
+            }
+          }
+          umma_commit(bars + 8 * (BAR_C1_FULL0 + h));
+        }
+        umma_commit(bars + 8 * BAR_A1_EMPTY);                 // every conv1 read of A1 has completed
+        // ---- conv2: 2 parities, one 128-row tile each
+        mbar_wait(bars + 8 * BAR_A2_FULL, ph, 4);
+        tc_fence_after();
+        mbar_wait(bars + 8 * BAR_C2_EMPTY, ph ^ 1, 5);
+        tc_fence_after();
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t d = tmem + Cfg::TM_C2 + q * 64;
+          uint32_t acc = 0;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            int plane, roff;
+            tap_src(q, dy, plane, roff);
+            const uint32_t a0 = sbase + Cfg::S_A2 + plane * Cfg::PLANE2 + (1 + roff * Cfg::PW2 + (dx - 1)) * 16;
+            const uint32_t b0 = sbase + Cfg::S_W2 + tap * 8192;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_f16(d, make_desc(a0 + ks * 2 * Cfg::CH2, Cfg::CH2, 128),
+                       make_desc(b0 + ks * 2048, 1024, 128), kIdesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(bars + 8 * BAR_C2_FULL);
+      }
+    }
+  } else {
+    // ================================================================ EPILOGUE (warps 0-3)
+    const int L = tid;                                       // TMEM lane == row of the tile
+    const uint32_t lane_addr = tmem + (uint32_t(warp * 32) << 16);
+    uint32_t ph = 0;
+    for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
+      const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
+      const __half* win = f0pad + (int64_t(rb) * pitch + c) * 64;
+      // ------------------------------------------------ conv1 epilogue -> A2 (pooled, fp16)
+#pragma unroll 1
+      for (int h = 0; h < Cfg::NT1; ++h) {
+        const int m = h * 128 + L;
+        const int i = m / Cfg::PW1, x = m - i * Cfg::PW1;
+        const bool valid = (m < Cfg::M1) && (x < W);
+        const bool writer = valid && ((x & 1) == 0);
+        // residual = conv0 output at the same position (models.py:133,135), rows 2i and 2i+1
+        const uint4* resE = reinterpret_cast<const uint4*>(win + (int64_t(2 * i) * pitch + x) * 64);
+        const uint4* resO = reinterpret_cast<const uint4*>(win + (int64_t(2 * i + 1) * pitch + x) * 64);
+        // destination in the conv2 planes: pooled pixel (py=i, px=x/2)
+        const int q2 = i & 1, prow2 = (i + q2) >> 1;
+        unsigned char* dst = smem + Cfg::S_A2 + q2 * Cfg::PLANE2 + (1 + prow2 * Cfg::PW2 + (x >> 1)) * 16;
+        mbar_wait(bars + 8 * (BAR_C1_FULL0 + h), ph, 6);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          float e[16], o[16];
+          tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64 + cc * 16, e);
+          tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64 + cc * 16, o);
+          uint4 re[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          uint4 ro[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (valid) {
+            re[0] = __ldg(resE + cc * 2); re[1] = __ldg(resE + cc * 2 + 1);
+            ro[0] = __ldg(resO + cc * 2); ro[1] = __ldg(resO + cc * 2 + 1);
+          }
+          tmem_ld_wait();
+          const __half2* he = reinterpret_cast<const __half2*>(re);
+          const __half2* ho = reinterpret_cast<const __half2*>(ro);
+          float pooled[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 fe = __half22float2(he[j]), fo = __half22float2(ho[j]);
+            const float b0 = sbias[cc * 16 + 2 * j], b1 = sbias[cc * 16 + 2 * j + 1];
+            const float v0 = fmaxf(e[2 * j] + b0 + fe.x, 0.f) + fmaxf(o[2 * j] + b0 + fo.x, 0.f);
+            const float v1 = fmaxf(e[2 * j + 1] + b1 + fe.y, 0.f) + fmaxf(o[2 * j + 1] + b1 + fo.y, 0.f);
+            pooled[2 * j] = v0; pooled[2 * j + 1] = v1;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pooled[j] = (pooled[j] + __shfl_xor_sync(0xffffffffu, pooled[j], 1)) * 0.25f;
+          if (writer) {
+            __half2 hv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hv[j] = __floats2half2_rn(pooled[2 * j], pooled[2 * j + 1]);
+            *reinterpret_cast<uint4*>(dst + (cc * 2) * Cfg::CH2) = *reinterpret_cast<uint4*>(&hv[0]);
+            *reinterpret_cast<uint4*>(dst + (cc * 2 + 1) * Cfg::CH2) = *reinterpret_cast<uint4*>(&hv[4]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (BAR_C1_EMPTY0 + h));
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + 8 * BAR_A2_FULL);
+      mbar_wait(bars + 8 * BAR_A2_FULL, ph, 7);              // every epilogue thread's A2 writes are visible
+      // ------------------------------------------------ conv2 epilogue -> P2 (global, fp16)
+      {
+        const int m = L;
+        const int i = m / Cfg::PW2, x = m - i * Cfg::PW2;
+        const bool valid = (m < Cfg::M2) && (x < Cfg::H2);
+        const bool writer = valid && ((x & 1) == 0);
+        // residual = pooled conv1 output (models.py:137,139) at rows 2i (even plane row i) and 2i+1 (odd plane row i+1)
+        const unsigned char* rE = smem + Cfg::S_A2 + 0 * Cfg::PLANE2 + (1 + i * Cfg::PW2 + x) * 16;
+        const unsigned char* rO = smem + Cfg::S_A2 + 1 * Cfg::PLANE2 + (1 + (i + 1) * Cfg::PW2 + x) * 16;
+        __half* dst = p2out + (p * Cfg::P + (i * (Cfg::H2 / 2) + (x >> 1))) * 64;
+        mbar_wait(bars + 8 * BAR_C2_FULL, ph, 8);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          float e[16], o[16];
+          tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64 + cc * 16, e);
+          tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64 + cc * 16, o);
+          uint4 re[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          uint4 ro[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (valid) {
+            re[0] = *reinterpret_cast<const uint4*>(rE + (cc * 2) * Cfg::CH2);
+            re[1] = *reinterpret_cast<const uint4*>(rE + (cc * 2 + 1) * Cfg::CH2);
+            ro[0] = *reinterpret_cast<const uint4*>(rO + (cc * 2) * Cfg::CH2);
+            ro[1] = *reinterpret_cast<const uint4*>(rO + (cc * 2 + 1) * Cfg::CH2);
+          }
+          tmem_ld_wait();
+          const __half2* he = reinterpret_cast<const __half2*>(re);
+          const __half2* ho = reinterpret_cast<const __half2*>(ro);
+          float pooled[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 fe = __half22float2(he[j]), fo = __half22float2(ho[j]);
+            const float b0 = sbias[64 + cc * 16 + 2 * j], b1 = sbias[64 + cc * 16 + 2 * j + 1];
+            const float v0 = fmaxf(e[2 * j] + b0 + fe.x, 0.f) + fmaxf(o[2 * j] + b0 + fo.x, 0.f);
+            const float v1 = fmaxf(e[2 * j + 1] + b1 + fe.y, 0.f) + fmaxf(o[2 * j + 1] + b1 + fo.y, 0.f);
+            pooled[2 * j] = v0; pooled[2 * j + 1] = v1;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pooled[j] = (pooled[j] + __shfl_xor_sync(0xffffffffu, pooled[j], 1)) * 0.25f;
+          if (writer) {
+            __half2 hv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hv[j] = __floats2half2_rn(pooled[2 * j], pooled[2 * j + 1]);
+            uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 16);
+            __stcs(d4, *reinterpret_cast<uint4*>(&hv[0]));
+            __stcs(d4 + 1, *reinterpret_cast<uint4*>(&hv[4]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bars + 8 * BAR_C2_EMPTY);
+      }
+      // A2 is rewritten by the next patch's conv1 epilogue: all residual reads must be done
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::TM_COLS);
+  }
+}
+
+}  // namespace cmlpl
+
+using namespace cmlpl;
+
+extern "C" int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
+                                   cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(f0pad && packed && p2, "patch_cnn: null pointer");
+  CMLPL_CHECK_ARG(w == 20, "patch_cnn: w=%d unsupported (BaseNet2's classifier fixes w=20, tools/models.py:127)", w);
+  CMLPL_CHECK_ARG(cols > 0 && band_rows > 0, "patch_cnn: bad dims");
+  CMLPL_CHECK_ARG(reinterpret_cast<uintptr_t>(f0pad) % 16 == 0 && reinterpret_cast<uintptr_t>(p2) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(packed) % 16 == 0, "patch_cnn: buffers must be 16-byte aligned");
+  using Cfg = PatchCfg<20>;
+  const PackedLayout L = packed_layout(1, 1, w);   // conv offsets do not depend on B, C
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  auto kern = patch_cnn_kernel<20>;
+  CMLPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  const int64_t npix = int64_t(band_rows) * cols;
+  int64_t grid = sm_count();
+  if (grid > npix) grid = npix;
+  kern<<<int(grid), kThreads, Cfg::SMEM, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(f0pad), cols, band_rows, pk + L.w1, pk + L.w2,
+      reinterpret_cast<const float*>(pk + L.b1), reinterpret_cast<const float*>(pk + L.b2),
+      static_cast<__half*>(p2));
+  CMLPL_CHECK_LAUNCH("patch_cnn");
+  return CMLPL_OK;
+}

@@ -1,0 +1,117 @@
+// Materialising patch gather.
+//   tools/hyper_tools.py:35-55   MirrowCut            (symmetric mirror padding)
+//   tools/hyper_tools.py:226-243 ExtractPatches       (even w, window r-w/2 .. r+w/2-1)
+//   tools/hyper_tools.py:300-317 ExtractPatches_for_base (odd w, window r-(w-1)/2 .. r+(w-1)/2)
+//   train.py:157                 x + randn*noise      (optional fused noise add)
+//
+// HBM-bound: 4*F*w*w bytes written per pixel (96 000 B at F=60, w=20); the 400-fold
+// overlapping window reads are served by L2.  One CTA stages one pixel's window
+// (channels-last in the cube) into shared memory with coalesced float4 reads, then
+// streams it out channel-major ([F][w][w]) with coalesced float4 stores -- the
+// transposition happens in shared memory (row stride w*w+1 words to spread banks).
+#include "common.cuh"
+
+namespace cmlpl {
+
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2)
+patch_gather_kernel(const float* __restrict__ cube, int scene_rows, int cols, int feat,
+                    int slab_row0, int w, const int64_t* __restrict__ idx, int64_t first,
+                    int64_t n, const float* __restrict__ noise, float noise_scale,
+                    float* __restrict__ out) {
+  extern __shared__ float tile[];  // [feat][w*w + 1]
+  const int ww = w * w;
+  const int stride = ww + 1;
+  const int lo = window_lo(w);
+  const int tid = threadIdx.x;
+
+  for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
+    const int64_t pix = idx ? idx[p] : first + p;
+    const int r = int(pix / cols), c = int(pix % cols);
+
+    if (VEC) {
+      const int f4n = feat >> 2;
+      const int total = ww * f4n;
+      for (int i = tid; i < total; i += blockDim.x) {
+        const int pos = i / f4n, f4 = i - pos * f4n;
+        const int y = pos / w, x = pos - y * w;
+        const int sr = mirror_index(r + lo + y, scene_rows) - slab_row0;
+        const int sc = mirror_index(c + lo + x, cols);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(cube + (int64_t(sr) * cols + sc) * feat) + f4);
+        float* t = tile + (f4 * 4) * stride + pos;
+        t[0] = v.x; t[stride] = v.y; t[2 * stride] = v.z; t[3 * stride] = v.w;
+      }
+      __syncthreads();
+      float4* o4 = reinterpret_cast<float4*>(out + p * int64_t(feat) * ww);
+      const float4* n4 = noise ? reinterpret_cast<const float4*>(noise + p * int64_t(feat) * ww) : nullptr;
+      const int total4 = (feat * ww) >> 2;
+      for (int i = tid; i < total4; i += blockDim.x) {
+        const int e = i << 2;
+        const int f = e / ww, q = e - f * ww;
+        const float* t = tile + f * stride + q;
+        float4 v = make_float4(t[0], t[1], t[2], t[3]);
+        if (n4) {
+          const float4 z = __ldcs(n4 + i);
+          // mul then add, two roundings like torch's `x + randn*noise` (never an FMA)
+          v.x = __fadd_rn(v.x, __fmul_rn(z.x, noise_scale)); v.y = __fadd_rn(v.y, __fmul_rn(z.y, noise_scale));
+          v.z = __fadd_rn(v.z, __fmul_rn(z.z, noise_scale)); v.w = __fadd_rn(v.w, __fmul_rn(z.w, noise_scale));
+        }
+        __stcs(o4 + i, v);
+      }
+    } else {
+      const int total = ww * feat;
+      for (int i = tid; i < total; i += blockDim.x) {
+        const int pos = i / feat, f = i - pos * feat;
+        const int y = pos / w, x = pos - y * w;
+        const int sr = mirror_index(r + lo + y, scene_rows) - slab_row0;
+        const int sc = mirror_index(c + lo + x, cols);
+        tile[f * stride + pos] = __ldg(cube + (int64_t(sr) * cols + sc) * feat + f);
+      }
+      __syncthreads();
+      float* o = out + p * int64_t(feat) * ww;
+      const float* nz = noise ? noise + p * int64_t(feat) * ww : nullptr;
+      for (int i = tid; i < total; i += blockDim.x) {
+        const int f = i / ww, q = i - f * ww;
+        float v = tile[f * stride + q];
+        if (nz) v = __fadd_rn(v, __fmul_rn(__ldcs(nz + i), noise_scale));
+        __stcs(o + i, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace cmlpl
+
+extern "C" int cmlpl_patch_gather_f32(const float* cube, int scene_rows, int cols, int feat,
+                                      int slab_row0, int slab_rows, int w, int odd_mode,
+                                      const int64_t* idx, int64_t first, int64_t n,
+                                      const float* noise, float noise_scale, float* out,
+                                      cmlpl_stream_t stream) {
+  using namespace cmlpl;
+  CMLPL_CHECK_ARG(cube && out, "patch_gather: null pointer");
+  CMLPL_CHECK_ARG(scene_rows > 0 && cols > 0 && feat > 0 && w > 0, "patch_gather: bad dims");
+  // the reference raises ValueError for the wrong parity (hyper_tools.py:240 shape mismatch)
+  CMLPL_CHECK_ARG(odd_mode ? (w % 2 == 1) : (w % 2 == 0),
+                  "patch_gather: w=%d has the wrong parity for %s", w,
+                  odd_mode ? "ExtractPatches_for_base" : "ExtractPatches");
+  CMLPL_CHECK_ARG(w / 2 <= scene_rows && w / 2 <= cols, "patch_gather: window larger than the scene");
+  CMLPL_CHECK_ARG(slab_row0 >= 0 && slab_rows > 0 && slab_row0 + slab_rows <= scene_rows,
+                  "patch_gather: slab [%d,%d) outside the scene", slab_row0, slab_row0 + slab_rows);
+  if (n <= 0) return CMLPL_OK;
+  const size_t smem = size_t(feat) * (w * w + 1) * sizeof(float);
+  CMLPL_CHECK_ARG(smem <= 227 * 1024, "patch_gather: window of %zu bytes does not fit shared memory", smem);
+  const bool vec = (feat % 4 == 0) && ((w * w) % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(cube) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                   (!noise || reinterpret_cast<uintptr_t>(noise) % 16 == 0);
+  auto kern = vec ? patch_gather_kernel<true> : patch_gather_kernel<false>;
+  CMLPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int ctas_per_sm = smem * 2 <= 227 * 1024 ? 2 : 1;
+  int64_t grid = int64_t(sm_count()) * ctas_per_sm * 4;
+  if (grid > n) grid = n;
+  kern<<<int(grid), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      cube, scene_rows, cols, feat, slab_row0, w, idx, first, n, noise, noise_scale, out);
+  CMLPL_CHECK_LAUNCH("patch_gather");
+  return CMLPL_OK;
+}

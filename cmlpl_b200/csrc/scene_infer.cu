@@ -1,0 +1,267 @@
+// Full-scene inference (tools/hyper_tools.py:416-437 test_whole) without materialised
+// patches.  Stages (one launch each, all on the caller's stream):
+//   1. conv0_map     conv0 (1x1, models.py:102,132) once per scene pixel -> mirrored,
+//                    halo-padded fp16 map F0pad[(rows+w-1),(cols+w-1),64]; a pixel's patch
+//                    is then a plain w x w window of this map (hyper_tools.py:35-55,226-243)
+//   2. spectral_head relu(feat_spe(x)) (models.py:142-143) and its classifier columns
+//   3. patch_cnn     conv1/conv2 + residual + ReLU + avg-pool per pixel (patch_cnn_sm100.cu,
+//                    tcgen05) -> pooled features P2[n,(w/4)^2,64] fp16
+//   4. classify      classifier (models.py:150) over [P2 | spectral] + argmax
+//                    (hyper_tools.py:426, first index wins ties)
+#include "common.cuh"
+#include "gemm_core.cuh"
+
+namespace cmlpl {
+
+// ------------------------------------------------------------------ conv0 map
+// thread = (padded pixel, 8 output channels); weights [ci][n] in shared memory.
+__global__ void __launch_bounds__(256)
+conv0_map_kernel(const float* __restrict__ cube, int scene_rows, int cols, int slab_row0,
+                 int w, int band_row0, int prow_n, int pcol_n,
+                 const float* __restrict__ w0t, const float* __restrict__ b0, __half* __restrict__ f0pad) {
+  __shared__ __align__(16) float ws[60 * 64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 60 * 64; i += blockDim.x) ws[i] = w0t[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = b0[threadIdx.x];
+  __syncthreads();
+  const int lo = window_lo(w);
+  const int64_t total = int64_t(prow_n) * pcol_n * 8;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int g = int(t & 7);
+    const int64_t pp = t >> 3;
+    const int pr = int(pp / pcol_n), pc = int(pp - int64_t(pr) * pcol_n);
+    const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0;
+    const int sc = mirror_index(pc + lo, cols);
+    const float4* src = reinterpret_cast<const float4*>(cube + (int64_t(sr) * cols + sc) * 60);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
+#pragma unroll 5
+    for (int c4 = 0; c4 < 15; ++c4) {
+      const float4 v = __ldg(src + c4);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 wa = *reinterpret_cast<const float4*>(&ws[(c4 * 4 + e) * 64 + g * 8]);
+        const float4 wb = *reinterpret_cast<const float4*>(&ws[(c4 * 4 + e) * 64 + g * 8 + 4]);
+        acc[0] = fmaf(xv[e], wa.x, acc[0]); acc[1] = fmaf(xv[e], wa.y, acc[1]);
+        acc[2] = fmaf(xv[e], wa.z, acc[2]); acc[3] = fmaf(xv[e], wa.w, acc[3]);
+        acc[4] = fmaf(xv[e], wb.x, acc[4]); acc[5] = fmaf(xv[e], wb.y, acc[5]);
+        acc[6] = fmaf(xv[e], wb.z, acc[6]); acc[7] = fmaf(xv[e], wb.w, acc[7]);
+      }
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(f0pad + pp * 64 + g * 8) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+// ------------------------------------------------------------------ classifier + argmax
+// one warp per pixel; lanes stride over the K = P*64 pooled features in 8-half chunks.
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+classify_kernel(const __half* __restrict__ p2, const float* __restrict__ spe, int64_t n, int K, int C,
+                const float* __restrict__ wc, const float* __restrict__ bc,
+                uint8_t* __restrict__ labels, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = int64_t(gridDim.x) * (blockDim.x >> 5);
+  const int chunks = K >> 3;
+  for (int64_t p = warp; p < n; p += nwarps) {
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+    const uint4* src = reinterpret_cast<const uint4*>(p2 + p * K);
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const uint4 raw = __ldcs(src + ch);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          const float4 wa = __ldg(reinterpret_cast<const float4*>(wc + int64_t(c) * K + ch * 8));
+          const float4 wb = __ldg(reinterpret_cast<const float4*>(wc + int64_t(c) * K + ch * 8 + 4));
+          float s = acc[c];
+          s = fmaf(x[0], wa.x, s); s = fmaf(x[1], wa.y, s); s = fmaf(x[2], wa.z, s); s = fmaf(x[3], wa.w, s);
+          s = fmaf(x[4], wb.x, s); s = fmaf(x[5], wb.y, s); s = fmaf(x[6], wb.z, s); s = fmaf(x[7], wb.w, s);
+          acc[c] = s;
+        }
+      }
+    }
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        float v = warp_sum(acc[c]);
+        v += (spe ? spe[p * C + c] : 0.f) + bc[c];
+        if (logits && lane == 0) logits[p * C + c] = v;
+        if (v > best) { best = v; arg = c; }   // strict '>' : first index wins ties
+      }
+    }
+    if (lane == 0) labels[p] = uint8_t(arg);
+  }
+}
+
+// argmax over dense fp32 logits (batch-mode test_whole path, hyper_tools.py:426)
+__global__ void argmax_kernel(const float* __restrict__ logits, int64_t n, int C, uint8_t* __restrict__ labels) {
+  for (int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; p < n; p += int64_t(gridDim.x) * blockDim.x) {
+    float best = -INFINITY; int arg = 0;
+    for (int c = 0; c < C; ++c) { const float v = logits[p * C + c]; if (v > best) { best = v; arg = c; } }
+    labels[p] = uint8_t(arg);
+  }
+}
+
+struct SceneWs {
+  size_t f0pad, p2, spe, hidden, total;
+  int64_t chunk;
+};
+static SceneWs scene_ws(int band_rows, int cols, int C, int w) {
+  SceneWs s;
+  const int64_t n = int64_t(band_rows) * cols;
+  const int P = ((w / 2) / 2) * ((w / 2) / 2);
+  size_t o = 0;
+  s.f0pad = o; o = align256(o + size_t(band_rows + w - 1) * (cols + w - 1) * 64 * 2);
+  s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);
+  s.spe = o; o = align256(o + size_t(n) * C * 4);
+  s.chunk = n < 16384 ? n : 16384;
+  s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);
+  s.total = o;
+  return s;
+}
+
+}  // namespace cmlpl
+
+using namespace cmlpl;
+
+extern "C" size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w) {
+  (void)num_features;
+  if (band_rows <= 0 || cols <= 0 || num_classes <= 0 || w < 4) return 0;
+  return scene_ws(band_rows, cols, num_classes, w).total;
+}
+
+extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows, int w,
+                                   int band_row0, int band_rows, const void* packed, void* f0pad,
+                                   cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(cube && packed && f0pad, "conv0_map: null pointer");
+  CMLPL_CHECK_ARG(scene_rows > 0 && cols > 0 && w >= 2 && band_rows > 0, "conv0_map: bad dims");
+  CMLPL_CHECK_ARG(w / 2 <= scene_rows && w / 2 <= cols, "conv0_map: window larger than the scene");
+  CMLPL_CHECK_ARG(band_row0 >= 0 && band_row0 + band_rows <= scene_rows, "conv0_map: band outside the scene");
+  CMLPL_CHECK_ARG(reinterpret_cast<uintptr_t>(cube) % 16 == 0, "conv0_map: cube must be 16-byte aligned");
+  // the slab must hold every (mirrored) source row of the band's halo
+  const int lo = window_lo(w);
+  int rmin = scene_rows, rmax = -1;
+  const int cand[4] = {band_row0 + lo, band_row0, band_row0 + band_rows - 1, band_row0 + band_rows - 1 + lo + w - 1};
+  for (int i = 0; i < 4; ++i) {
+    const int m = mirror_index(cand[i], scene_rows);
+    rmin = m < rmin ? m : rmin; rmax = m > rmax ? m : rmax;
+  }
+  CMLPL_CHECK_ARG(rmin >= slab_row0 && rmax < slab_row0 + slab_rows,
+                  "conv0_map: slab rows [%d,%d) do not cover the band's halo [%d,%d]", slab_row0,
+                  slab_row0 + slab_rows, rmin, rmax);
+  const PackedLayout L = packed_layout(1, 1, w);  // w0/b0 offsets do not depend on B, C
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  const int prow_n = band_rows + w - 1, pcol_n = cols + w - 1;
+  const int64_t total = int64_t(prow_n) * pcol_n * 8;
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  conv0_map_kernel<<<int(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cube, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n,
+      reinterpret_cast<const float*>(pk + L.w0), reinterpret_cast<const float*>(pk + L.b0),
+      static_cast<__half*>(f0pad));
+  CMLPL_CHECK_LAUNCH("conv0_map");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_features, int num_classes, int w,
+                                       const void* packed, float* hidden, int64_t chunk, float* spe_logits,
+                                       cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(spectra && packed && hidden && spe_logits, "spectral_head: null pointer");
+  CMLPL_CHECK_ARG(n >= 0 && chunk > 0 && num_features > 0 && num_classes > 0, "spectral_head: bad dims");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  const PackedLayout L = packed_layout(num_features, num_classes, w);
+  const float* wspe = reinterpret_cast<const float*>(pk + L.wspe);
+  const float* bspe = reinterpret_cast<const float*>(pk + L.bspe);
+  const float* wc_spe = reinterpret_cast<const float*>(pk + L.wc_spe);
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const int m = int((n - s0) < chunk ? (n - s0) : chunk);
+    // hidden = relu(X . Wspe^T + bspe)         (models.py:142-143)
+    int rc = launch_gemm(m, 1024, num_features, 1,
+                         StridedA{spectra + s0 * num_features, num_features, 1},
+                         StridedB{wspe, 1, num_features},
+                         StridedC{hidden, 1024, 1, bspe, 1.f, 0.f, 1}, s, "spectral_hidden");
+    if (rc != CMLPL_OK) return rc;
+    // spe_logits = hidden . Wc_spe^T           (spectral columns of models.py:150)
+    rc = launch_gemm(m, num_classes, 1024, 1, StridedA{hidden, 1024, 1}, StridedB{wc_spe, 1, 1024},
+                     StridedC{spe_logits + s0 * num_classes, num_classes, 1, nullptr, 1.f, 0.f, 0}, s,
+                     "spectral_logits");
+    if (rc != CMLPL_OK) return rc;
+  }
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_classify_f16(const void* p2, const float* spe_logits, int64_t n, int num_features,
+                                  int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
+                                  cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(p2 && packed && labels, "classify: null pointer");
+  CMLPL_CHECK_ARG(n >= 0 && num_classes > 0 && num_classes <= 32 && w >= 4, "classify: bad dims (C=%d w=%d)",
+                  num_classes, w);
+  if (n == 0) return CMLPL_OK;
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  const PackedLayout L = packed_layout(num_features, num_classes, w);
+  const int K = L.conv_pos * 64;
+  const float* wc = reinterpret_cast<const float*>(pk + L.wc_conv);
+  const float* bc = reinterpret_cast<const float*>(pk + L.bc);
+  int64_t grid = (n + 7) / 8;
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (num_classes <= 16)
+    classify_kernel<16><<<int(grid), 256, 0, s>>>(static_cast<const __half*>(p2), spe_logits, n, K, num_classes, wc, bc, labels, logits);
+  else
+    classify_kernel<32><<<int(grid), 256, 0, s>>>(static_cast<const __half*>(p2), spe_logits, n, K, num_classes, wc, bc, labels, logits);
+  CMLPL_CHECK_LAUNCH("classify");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_argmax_u8(const float* logits, int64_t n, int num_classes, uint8_t* labels, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(logits && labels && n >= 0 && num_classes > 0 && num_classes <= 255, "argmax: bad args");
+  if (n == 0) return CMLPL_OK;
+  int64_t grid = (n + 255) / 256;
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  argmax_kernel<<<int(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, n, num_classes, labels);
+  CMLPL_CHECK_LAUNCH("argmax");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows,
+                                 const float* spectra, int num_features, int num_classes, int w, int band_row0,
+                                 int band_rows, const void* packed, void* workspace, size_t workspace_bytes,
+                                 uint8_t* labels, float* logits, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(cube && spectra && packed && workspace && labels, "scene_infer: null pointer");
+  CMLPL_CHECK_ARG(w == 20, "scene_infer: w=%d unsupported (the reference classifier is hard-wired to 2624 inputs, "
+                  "tools/models.py:127, i.e. w=20)", w);
+  CMLPL_CHECK_ARG(band_rows > 0 && cols > 0 && num_classes > 0 && num_classes <= 32, "scene_infer: bad dims");
+  const SceneWs ws = scene_ws(band_rows, cols, num_classes, w);
+  CMLPL_CHECK_ARG(workspace_bytes >= ws.total, "scene_infer: workspace %zu < required %zu", workspace_bytes, ws.total);
+  CMLPL_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "scene_infer: workspace must be 256-byte aligned");
+  unsigned char* wsb = static_cast<unsigned char*>(workspace);
+  const int64_t n = int64_t(band_rows) * cols;
+  int rc = cmlpl_conv0_map_f16(cube, scene_rows, cols, slab_row0, slab_rows, w, band_row0, band_rows, packed,
+                               wsb + ws.f0pad, stream);
+  if (rc != CMLPL_OK) return rc;
+  rc = cmlpl_spectral_head_f32(spectra, n, num_features, num_classes, w, packed,
+                               reinterpret_cast<float*>(wsb + ws.hidden), ws.chunk,
+                               reinterpret_cast<float*>(wsb + ws.spe), stream);
+  if (rc != CMLPL_OK) return rc;
+  rc = cmlpl_patch_cnn_f16(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.p2, stream);
+  if (rc != CMLPL_OK) return rc;
+  return cmlpl_classify_f16(wsb + ws.p2, reinterpret_cast<const float*>(wsb + ws.spe), n, num_features, num_classes,
+                            w, packed, labels, logits, stream);
+}

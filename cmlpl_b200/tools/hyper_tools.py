@@ -1,0 +1,181 @@
+"""Prep / eval utilities of the reference's tools/hyper_tools.py on the B200 kernels.
+
+Kept names and return conventions: MirrowCut, ExtractPatches, ExtractPatches_for_base,
+featureNormalize, PCANorm, SampleGen, test_whole, CalAccuracy.  Patch extraction, scene
+inference and the confusion matrix run in libcmlpl_sm100.so; PCA / z-scoring stay float64
+numpy exactly like the reference (one-off preprocessing before the hot path).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+
+DATASETS = {1: ("PaviaU", 9, 103), 2: ("Salinas", 16, 204), 3: ("Houston", 15, 144), 4: ("Indian_pines", 16, 200)}
+_MAT = {1: ("PaviaU.mat", "paviaU", "PaviaU_gt.mat", "paviaU_gt"),
+        2: ("salinas.mat", "HSI_original", "salinas_gt.mat", "Data_gt"),
+        3: ("Houston.mat", "Houston", "Houston_gt.mat", "Houston_gt"),
+        4: ("indian_pines_corrected.mat", "indian_pines_corrected", "indian_pines_gt.mat", "indian_pines_gt")}
+
+
+def _device():
+    _lib.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------ preprocessing (host, float64)
+def featureNormalize(X, type):
+    """hyper_tools.py:8-22."""
+    if type == 1:
+        centred = X - np.mean(X, 0)
+        return centred / np.std(centred, 0)
+    if type == 2:
+        lo, hi = np.min(X, 0), np.max(X, 0)
+        return (X - lo) / (hi - lo)
+    raise ValueError(f"featureNormalize: unknown type {type}")
+
+
+def PCANorm(X, num_PC):
+    """hyper_tools.py:25-32: project the centred data on the leading left-singular vectors of its covariance."""
+    centred = X - np.mean(X, 0)
+    basis = np.linalg.svd(np.cov(centred.T))[0][:, :num_PC]
+    return centred @ basis
+
+
+# ------------------------------------------------------------------ patches (device)
+def _to_cube(X) -> torch.Tensor:
+    if isinstance(X, torch.Tensor):
+        return X.to(device=_device(), dtype=torch.float32).contiguous()
+    # the reference assigns float64 windows into a float32 array (hyper_tools.py:233,240): the
+    # cast commutes with the gather, so cast the cube once
+    return torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(_device())
+
+
+def MirrowCut(X, hw):
+    """hyper_tools.py:35-55 (== symmetric padding by hw).  Returned as float64 numpy like the reference.
+    Implemented as a w=1 gather of the padded coordinate grid through the same device index map."""
+    cube = _to_cube(X)
+    R, C, F = cube.shape
+    if hw > R or hw > C:
+        raise ValueError("MirrowCut: hw larger than the image")
+    rr = torch.arange(-hw, R + hw, device=cube.device)
+    cc = torch.arange(-hw, C + hw, device=cube.device)
+    mr = torch.where(rr < 0, -rr - 1, torch.where(rr >= R, 2 * R - 1 - rr, rr))
+    mc = torch.where(cc < 0, -cc - 1, torch.where(cc >= C, 2 * C - 1 - cc, cc))
+    idx = (mr[:, None] * C + mc[None, :]).reshape(-1).contiguous()
+    out = ops.patch_gather(cube, 1, idx=idx, odd_mode=True)          # [n, F, 1, 1]
+    out = out.view(R + 2 * hw, C + 2 * hw, F)
+    if isinstance(X, np.ndarray) and X.dtype == np.float64:
+        # exact for float32-representable inputs; otherwise re-gather on host to keep float64 bits
+        res = np.asarray(X)[mr.cpu().numpy()[:, None], mc.cpu().numpy()[None, :], :]
+        return res.astype(np.float64)
+    return out.cpu().numpy().astype(np.float64)
+
+
+def ExtractPatches(X, w, idx=None, as_numpy=True):
+    """hyper_tools.py:226-243: every pixel's w x w window (even w) -> f32 [K, F, w, w].
+    ``idx`` (raster indices) restricts the gather; ``as_numpy=False`` keeps the CUDA tensor."""
+    if w % 2:
+        raise ValueError("ExtractPatches: could not broadcast an odd window (the reference raises too); "
+                         "use ExtractPatches_for_base for odd w")
+    return _extract(X, w, idx, False, as_numpy)
+
+
+def ExtractPatches_for_base(X, w, idx=None, as_numpy=True):
+    """hyper_tools.py:300-317: odd-w centred variant."""
+    if w % 2 == 0:
+        raise ValueError("ExtractPatches_for_base: w must be odd")
+    return _extract(X, w, idx, True, as_numpy)
+
+
+def _extract(X, w, idx, odd, as_numpy):
+    cube = _to_cube(X)
+    if idx is not None:
+        idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64).to(cube.device).contiguous()
+    out = ops.patch_gather(cube, w, idx=idx, odd_mode=odd)
+    return out.cpu().numpy() if as_numpy else out
+
+
+def SampleGen(dataID=1, w=16, n_PC=3, root="./dataset/", as_numpy=True):
+    """hyper_tools.py:246-297: load the .mat scene, PCA + z-score -> (XP, X, Y)."""
+    import scipy.io as sio
+
+    fx, kx, fy, ky = _MAT[dataID]
+    X = sio.loadmat(root + fx)[kx]
+    Y = sio.loadmat(root + fy)[ky]
+    row, col, n_feature = X.shape
+    X = X.reshape(row * col, n_feature)
+    X_PCA = featureNormalize(PCANorm(X, n_PC), 1).reshape(row, col, n_PC)
+    X = featureNormalize(X, 1)
+    XP = ExtractPatches(X_PCA, w, as_numpy=as_numpy)
+    return XP, X, Y.reshape(row * col, )
+
+
+# ------------------------------------------------------------------ inference + metrics
+def test_whole(model, data_loader, print_per_batches=10):
+    """hyper_tools.py:416-437: predicted label of every sample the loader yields, int64 numpy.
+
+    When the loader wraps a cube-backed ``HSIDataSet('wholeset')`` the whole scene goes through
+    the fused scene-inference kernels (patches never materialised); any other loader is consumed
+    batch by batch through ``model(XP, X)`` on device like the reference."""
+    model.eval()
+    ds = getattr(data_loader, "dataset", None)
+    if ds is not None and getattr(ds, "scene_ready", False) and ds.setindex == "wholeset":
+        labels = scene_labels(model, ds.cube_device(), ds.spectra_device(), ds.w)
+        return labels.cpu().numpy().astype(np.int64)
+    outs = []
+    num_batches = len(data_loader)
+    dev = _device()
+    with torch.no_grad():
+        for batch_idx, data in enumerate(data_loader):
+            XP, X = data[0], data[1]
+            logits, _ = model(XP.to(dev, torch.float32), X.to(dev, torch.float32))
+            outs.append(ops.argmax_u8(logits.contiguous()))
+            if (batch_idx + 1) % print_per_batches == 0:
+                print('---------------------Testing the whole set-[%d/%d]---------------------' % (
+                    batch_idx + 1, num_batches))
+    return torch.cat(outs).cpu().numpy().astype(np.int64)
+
+
+def scene_labels(model, cube, spectra, w=20, band=None, scene_rows=None, slab_row0=0, want_logits=False):
+    """Labels (uint8 CUDA tensor) of the scene rows ``band=(r0, r1)`` (default: all)."""
+    R = cube.shape[0] if scene_rows is None else scene_rows
+    r0, r1 = (0, R) if band is None else band
+    packed = model.packed_weights(w)
+    return ops.scene_infer(cube, spectra, packed, model.num_classes, w, band_row0=r0, band_rows=r1 - r0,
+                           scene_rows=R, slab_row0=slab_row0, want_logits=want_logits)
+
+
+def confusion_matrix(predict, label, num_classes):
+    """int64 [C, C] counts cm[label, predict] computed on device."""
+    dev = _device()
+    p = torch.as_tensor(np.asarray(predict)).to(dev)
+    if p.dtype != torch.uint8:
+        if p.numel() and (int(p.min()) < 0 or int(p.max()) > 255):
+            raise ValueError("predictions must lie in [0, 255]")
+        p = p.to(torch.uint8)
+    l = torch.as_tensor(np.asarray(label)).to(dev).to(torch.int64)
+    return ops.confusion(p.contiguous(), l.contiguous(), num_classes).cpu().numpy()
+
+
+def CalAccuracy(predict, label):
+    """hyper_tools.py:208-223 -> (OA, Kappa, producerA[C]) with C = max(label)+1.
+
+    Counts come from the device confusion matrix (sized to also hold predictions above
+    max(label), which the reference counts in ``reali`` but in no per-class hit); the ratios are
+    formed in float64 on the host in the reference's order of operations."""
+    label = np.asarray(label)
+    predict = np.asarray(predict)
+    n = label.shape[0]
+    C = int(label.max()) + 1
+    full = max(C, int(predict.max()) + 1)
+    cm = confusion_matrix(predict, label, full).astype(np.float64)
+    correct_sum = np.diag(cm)[:C].copy()
+    reali = cm.sum(1)[:C]
+    predicti = cm.sum(0)[:C]
+    OA = np.trace(cm) * 1.0 / n
+    with np.errstate(divide="ignore", invalid="ignore"):
+        producerA = correct_sum / reali
+    Kappa = (n * np.sum(correct_sum) - np.sum(reali * predicti)) * 1.0 / (n * n - np.sum(reali * predicti))
+    return OA, Kappa, producerA

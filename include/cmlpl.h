@@ -1,0 +1,160 @@
+/*
+ * cmlpl.h -- C ABI of libcmlpl_sm100.so: the B200 (sm_100a) kernels behind the CMLPL
+ * hot path (patch gather -> BaseNet2 -> losses -> full-scene inference -> OA/AA/kappa).
+ *
+ * The reference (liuli33/CMLPL) has no FFI: its "API" is Python names.  Each entry
+ * point below names the reference code it replaces (file:line under the reference
+ * root); cmlpl_b200/ binds them with ctypes and re-exposes the reference's Python
+ * names on top (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer; the library allocates nothing persistent;
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, <0 = error; cmlpl_last_error() gives the message
+ *     (thread-local);
+ *   - tensors are dense row-major with the shapes written in the comments.
+ */
+#ifndef CMLPL_H_
+#define CMLPL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMLPL_OK 0
+#define CMLPL_ERR_ARG (-1)
+#define CMLPL_ERR_CUDA (-2)
+#define CMLPL_ERR_UNSUPPORTED (-3)
+
+typedef void* cmlpl_stream_t;
+
+int cmlpl_version(void);
+const char* cmlpl_last_error(void);
+/* 1 if the device the current context runs on is sm_100 (B200), else 0 (or <0). */
+int cmlpl_device_ok(void);
+
+/* ------------------------------------------------------------------ patches --
+ * tools/hyper_tools.py:35-55 (MirrowCut), :226-243 (ExtractPatches, even w) and
+ * :300-317 (ExtractPatches_for_base, odd w; odd_mode=1).
+ * cube   f32 [slab_rows, cols, feat]   channels-last slab = scene rows
+ *                                       [slab_row0, slab_row0+slab_rows) of a scene with
+ *                                       scene_rows rows (band sharding; mirror padding is
+ *                                       applied at true scene edges only)
+ * idx    i64 [n] raster pixel indices r*cols+c, or NULL for first, first+1, ...
+ * noise  f32 [n, feat, w, w] or NULL;  out = patch + noise*noise_scale (train.py:157)
+ * out    f32 [n, feat, w, w]
+ */
+int cmlpl_patch_gather_f32(const float* cube, int scene_rows, int cols, int feat,
+                           int slab_row0, int slab_rows, int w, int odd_mode,
+                           const int64_t* idx, int64_t first, int64_t n,
+                           const float* noise, float noise_scale,
+                           float* out, cmlpl_stream_t stream);
+
+/* ------------------------------------------------------------ fp32 building --
+ * Dense fp32 building blocks of BaseNet2 (tools/models.py:97-152) in batch mode,
+ * NCHW like the reference; used by training forward/backward (a5, a12).
+ */
+
+/* C[M,N] = act( alpha * op(A)[M,K] . op(B)[K,N] + bias[N] + beta*C ) with arbitrary
+ * element strides (so any transpose is a stride choice).  act: 0 none, 1 relu.
+ * nn.Linear forward / dgrad / wgrad (models.py:142,150). */
+int cmlpl_sgemm_f32(int M, int N, int K, float alpha,
+                    const float* A, int64_t a_rs, int64_t a_cs,
+                    const float* B, int64_t b_rs, int64_t b_cs,
+                    const float* bias, float beta,
+                    float* C, int64_t c_rs, int64_t c_cs, int act,
+                    cmlpl_stream_t stream);
+
+/* y[b,co,h,w] = act( conv_kxk(x, wgt, pad=k/2) + bias + (res ? res : 0) ), k in {1,3}.
+ * models.py:132-135,138-139.   x f32 [b,ci,h,w], wgt f32 [co,ci,k,k], res/y f32 [b,co,h,w].
+ * transpose_w=1 computes the data gradient: uses wgt[ci_out... ] flipped/transposed, i.e.
+ * y = conv(x, flip(wgt)^T) with x = dL/dy [b,co,h,w] -> y = dL/dx [b,ci,h,w]. */
+int cmlpl_conv2d_f32(const float* x, const float* wgt, const float* bias, const float* res,
+                     float* y, int b, int ci, int co, int h, int w, int k, int act,
+                     int transpose_w, cmlpl_stream_t stream);
+
+/* dW[co,ci,k,k] = sum_{b,y,x} dy[b,co,y,x] * x[b,ci,y+ky-p,x+kx-p];  db[co] = sum dy. */
+int cmlpl_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* db,
+                           int b, int ci, int co, int h, int w, int k, cmlpl_stream_t stream);
+
+/* 2x2/2 average pool forward / backward (models.py:136,140), NCHW. */
+int cmlpl_avgpool2_f32(const float* x, float* y, int64_t planes, int h, int w, cmlpl_stream_t stream);
+int cmlpl_avgpool2_bwd_f32(const float* dy, float* dx, int64_t planes, int h, int w, cmlpl_stream_t stream);
+
+/* relu backward with optional residual fan-out: dx = dy * (y > 0). */
+int cmlpl_relu_bwd_f32(const float* y, const float* dy, float* dx, int64_t n, cmlpl_stream_t stream);
+/* column sums: out[n] = sum_m x[m,n] (bias gradients of nn.Linear). */
+int cmlpl_colsum_f32(const float* x, float* out, int64_t m, int64_t n, cmlpl_stream_t stream);
+
+/* models.py:87-90 Normalize: y = x / sqrt(sum x^2) per row (no epsilon), and its backward
+ * dx = (dy - y * sum(dy*y)) / norm. */
+int cmlpl_l2norm_f32(const float* x, float* y, float* norm, int64_t rows, int64_t cols, cmlpl_stream_t stream);
+int cmlpl_l2norm_bwd_f32(const float* y, const float* norm, const float* dy, float* dx,
+                         int64_t rows, int64_t cols, cmlpl_stream_t stream);
+
+/* ------------------------------------------------------------ scene inference --
+ * tools/hyper_tools.py:416-437 (test_whole) over a whole scene / row band without ever
+ * materialising patches: conv0 is evaluated once per scene pixel into a mirrored,
+ * halo-padded fp16 map; a persistent tcgen05 kernel runs conv1/conv2 (+residual, ReLU,
+ * 2x2 avg-pool) per pixel with the patch window staged in shared memory; the classifier
+ * (+ spectral branch) and argmax finish in a head kernel.
+ *
+ * Packed weights: cmlpl_pack_basenet2() converts the reference state_dict tensors
+ * (models.py:102-127: conv0/1/2.{weight,bias}, feat_spe.*, classifier.*) into the
+ * kernel layouts inside a caller-owned buffer of cmlpl_packed_bytes() bytes.
+ */
+size_t cmlpl_packed_bytes(int num_features, int num_classes, int w);
+int cmlpl_pack_basenet2(const float* conv0_w, const float* conv0_b,
+                        const float* conv1_w, const float* conv1_b,
+                        const float* conv2_w, const float* conv2_b,
+                        const float* spe_w, const float* spe_b,
+                        const float* cls_w, const float* cls_b,
+                        int num_features, int num_classes, int w,
+                        void* packed, cmlpl_stream_t stream);
+
+/* Workspace needed to infer `band_rows` rows of a scene with `cols` columns. */
+size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w);
+
+/* cube     f32 [slab_rows, cols, 60]  PCA cube slab (rows slab_row0.. of the scene)
+ * spectra  f32 [band_rows*cols, num_features]   rows of X for the band's pixels
+ * labels   u8  [band_rows*cols]  argmax (first index on ties, hyper_tools.py:426)
+ * logits   f32 [band_rows*cols, num_classes] or NULL
+ * Band = scene rows [band_row0, band_row0+band_rows). */
+int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows,
+                      const float* spectra, int num_features, int num_classes, int w,
+                      int band_row0, int band_rows, const void* packed,
+                      void* workspace, size_t workspace_bytes,
+                      uint8_t* labels, float* logits, cmlpl_stream_t stream);
+
+/* Individual stages of cmlpl_scene_infer (exposed for tests / profiling). */
+int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows,
+                        int w, int band_row0, int band_rows, const void* packed,
+                        void* f0pad /* f16 [band_rows+w-1, cols+w-1, 64] */, cmlpl_stream_t stream);
+int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                        void* p2 /* f16 [band_rows*cols, (w/4)^2, 64] */, cmlpl_stream_t stream);
+int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_features, int num_classes, int w,
+                            const void* packed, float* hidden /* f32 [chunk,1024] scratch */,
+                            int64_t chunk, float* spe_logits /* f32 [n, C] */, cmlpl_stream_t stream);
+int cmlpl_classify_f16(const void* p2, const float* spe_logits /* may be NULL */, int64_t n,
+                       int num_features, int num_classes, int w, const void* packed,
+                       uint8_t* labels, float* logits /* may be NULL */, cmlpl_stream_t stream);
+/* hyper_tools.py:426 torch.max(outputs, 1): first index on ties.  logits f32 [n, C] -> u8 [n]. */
+int cmlpl_argmax_u8(const float* logits, int64_t n, int num_classes, uint8_t* labels,
+                    cmlpl_stream_t stream);
+
+/* ------------------------------------------------------------------ metrics --
+ * tools/hyper_tools.py:208-223 (CalAccuracy): integer confusion matrix
+ * cm[label, pred] += 1 for pairs with both in [0, C).  pred u8 [n], label i64 [n],
+ * cm i64 [C, C] (accumulated into; zero it first).  OA/AA/kappa are float64 host
+ * arithmetic on these counts. */
+int cmlpl_confusion_i64(const uint8_t* pred, const int64_t* label, int64_t n, int num_classes,
+                        int64_t* cm, cmlpl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMLPL_H_ */
