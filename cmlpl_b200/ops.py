@@ -50,6 +50,8 @@ def patch_gather(cube: torch.Tensor, w: int, idx: torch.Tensor | None = None, fi
         _chk(out, name="out")
     if noise is not None:
         _chk(noise, name="noise")
+    if n == 0:
+        return out
     _lib.call("cmlpl_patch_gather_f32", cube.data_ptr(), scene_rows, cols, feat, slab_row0, slab_rows,
               w, int(odd_mode), _p(idx), first, n, _p(noise), float(noise_scale), out.data_ptr(), _stream())
     return out
