@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: pixels/sec of full-scene inference on a PaviaU-shaped synthetic scene
+(610 x 340 x 103, 9 classes; BASELINE.json metric / configs[0]) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One "step" = one pass of the hot path over the whole scene: conv0 map -> spectral branch ->
+tcgen05 per-pixel CNN -> classifier + argmax (+ label-map all-gather and confusion all-reduce
+when N > 1).  `value` is device-resident throughput; `e2e` goes through the public call with
+pinned HOST buffers (H2D of the cube + spectra and D2H of the label map inside the timed region).
+Multi-GPU: row bands, weak scaling -- the scene grows to (610*N) x 340 and every rank infers a
+610-row band (+ read-only halo); no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R0, C0, B0, K0, W0 = 610, 340, 103, 9, 20
+FLOP_PER_PX_CNN = 2 * (14_745_600 + 3_686_400)          # conv1 + conv2 MACs per pixel
+FLOP_PER_PX_ALL = 2 * (1_536_000 + 14_745_600 + 3_686_400 + 1024 * B0 + 2624 * K0)   # 40.19 MFLOP (8d)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return {"hbm": z["hbm_gbs"], "tf_burst": z["bf16_tflops"], "tf_sustained": z["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[1]) for r in rows if len(r) >= 8]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows if len(r) >= 8 for i in range(4) if r[4 + i].strip() == "Active"})
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(r[3]) for r in rows if len(r) >= 8)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port of the reference path)
+def cpu_reference_pass(cube_pca, spectra, sd, rows, threads):
+    """The reference's test_whole path on host cores for scene rows [rows[0], rows[1]):
+    per-pixel window copy out of the mirror-padded cube (hyper_tools.py:231-243), batches of 512
+    through BaseNet2 in fp32 (models.py:130-152), argmax (hyper_tools.py:426).  Returns seconds."""
+    from oracle import cmlpl_oracle as O          # CPU baseline leg only
+
+    torch.set_num_threads(threads)
+    R, C, F = cube_pca.shape
+    w, hw = W0, W0 // 2
+    Xm = O.mirrow_cut(cube_pca, hw)               # one-off for the scene: not timed (amortised over all pixels)
+    r0, r1 = rows
+    n = (r1 - r0) * C
+    t0 = time.perf_counter()
+    XP = np.zeros((n, w, w, F), dtype=np.float32)
+    k = 0
+    for r in range(r0, r1):
+        for c in range(C):
+            XP[k] = Xm[r:r + 2 * hw, c:c + 2 * hw, :]
+            k += 1
+    XP = np.moveaxis(XP, 3, 1).astype(np.float32)
+    Xs = spectra[r0 * C:r1 * C]
+    out = []
+    with torch.no_grad():
+        for s in range(0, n, 512):
+            xp = torch.from_numpy(XP[s:s + 512].astype("float32").copy())
+            xs = torch.from_numpy(Xs[s:s + 512].astype("float32").copy())
+            lo, _ = O.basenet2_forward(sd, xp, xs)
+            out.append(torch.max(lo, 1)[1].numpy())
+    np.concatenate(out)
+    return time.perf_counter() - t0, n
+
+
+def run_reference_arm(args, scene):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cmlpl_oracle as O
+    cube_pca, spectra, _ = scene
+    torch.manual_seed(1088)
+    sd = O.basenet2_init(B0, K0)
+    threads = os.cpu_count() or 1
+    rows_per_step = 6
+    times, npx = [], 0
+    for i in range(args.warmup + args.steps):
+        r0 = (37 + i * rows_per_step) % (R0 - rows_per_step)
+        dt, npx = cpu_reference_pass(cube_pca, spectra, sd, (r0, r0 + rows_per_step), threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = npx / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "pixels/sec full-scene inference", "value": val, "unit": "pixels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, note="CPU arm: one step = a 6-row band (2040 px) of the same scene"),
+        "cpu_baseline": {"value": val, "unit": "pixels/s", "cores": threads, "kind": "port",
+                         "sample": f"{rows_per_step} rows x {C0} cols = {npx} px per step through the oracle port of "
+                                   "ExtractPatches loop + BaseNet2 fp32 (bs 512) + argmax"},
+        "e2e": {"value": val, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, note=None):
+    cfg = {"workload": f"PaviaU-shaped synthetic scene {R0}x{C0}x{B0}, {K0} classes, w={W0}, n_PC=60 "
+                       "(BASELINE.json configs[0], the configuration the metric is quoted on); "
+                       "random-init BaseNet2 (seed 1088), synthetic cube seed 1088",
+           "scene_rows": R0 * n_gpus, "scene_cols": C0, "bands": B0, "classes": K0, "patch": W0,
+           "pixels_per_step": R0 * C0 * n_gpus,
+           "parallelism": f"row bands x{n_gpus} (weak: {R0} rows + halo per GPU, scene = {R0 * n_gpus} rows)",
+           "l2_policy": "per-step working set (cube 50 MB + spectra 85 MB + conv0 map 29 MB + pooled features "
+                        "664 MB) exceeds the 126 MB L2; no explicit flush"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cmlpl_b200", choices=["cmlpl_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    from cmlpl_b200 import synth
+    t_data = time.time()
+    scene = synth.preprocessed_scene(R0, C0, B0, K0, 60, 1088)
+    t_data = time.time() - t_data
+    if args.impl == "reference":
+        return run_reference_arm(args, scene)
+
+    import torch.distributed as dist
+    from cmlpl_b200 import _lib, ops, parallel
+    from cmlpl_b200.tools.models import BaseNet2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    cube_pca, spectra, gt = scene
+
+    # ---- weak scaling: the scene is the base scene stacked `world` times; this rank's band = copy `rank`
+    scene_rows = R0 * world
+    r0, r1 = parallel.band_of(rank, world, scene_rows)
+    s0, s1 = parallel.slab_of(r0, r1, scene_rows, W0)
+    slab_host = torch.from_numpy(np.ascontiguousarray(cube_pca[np.arange(s0, s1) % R0])).pin_memory()
+    spec_host = torch.from_numpy(np.ascontiguousarray(spectra)).pin_memory()      # band rows == base scene rows
+    truth = torch.from_numpy(gt.reshape(-1).astype(np.int64) - 1).to(dev)       # -1 = unlabelled (ignored)
+    n_band = (r1 - r0) * C0
+
+    torch.manual_seed(1088)
+    net = BaseNet2(num_features=B0, dropout=0, num_classes=K0).to(dev).eval()
+    packed = net.packed_weights(W0)
+    slab = slab_host.to(dev)
+    spec = spec_host.to(dev)
+    ws = ops.scene_workspace(r1 - r0, C0, B0, K0, W0, dev)
+    labels = torch.empty(n_band, dtype=torch.uint8, device=dev)
+    labels_host = torch.empty(n_band, dtype=torch.uint8).pin_memory()
+    cm = torch.zeros(K0, K0, dtype=torch.int64, device=dev)
+
+    def step_device():
+        ops.scene_infer(slab, spec, packed, K0, W0, band_row0=r0, band_rows=r1 - r0, scene_rows=scene_rows,
+                        slab_row0=s0, workspace=ws, labels=labels)
+        if world > 1:
+            parallel.gather_label_map(labels, scene_rows, C0)
+            cm.zero_()
+            parallel.reduce_confusion(ops.confusion(labels, truth, K0, cm))
+
+    def step_e2e():
+        d_slab = slab_host.to(dev, non_blocking=True)
+        d_spec = spec_host.to(dev, non_blocking=True)
+        ops.scene_infer(d_slab, d_spec, packed, K0, W0, band_row0=r0, band_rows=r1 - r0, scene_rows=scene_rows,
+                        slab_row0=s0, workspace=ws, labels=labels)
+        if world > 1:
+            parallel.gather_label_map(labels, scene_rows, C0)
+        labels_host.copy_(labels, non_blocking=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    # ---- per-kernel durations of the same step, CUDA events on the launching stream
+    L = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    wsz = {k: None for k in ()}
+    nb = r1 - r0
+    f0_bytes = (nb + W0 - 1) * (C0 + W0 - 1) * 64 * 2
+    al = lambda x: (x + 255) // 256 * 256
+    off_f0, off_p2 = 0, al(f0_bytes)
+    off_spe = off_p2 + al(n_band * 25 * 64 * 2)
+    off_hid = off_spe + al(n_band * K0 * 4)
+    base = ws.data_ptr()
+    chunk = min(n_band, 16384)
+    names = ["conv0_map", "spectral_head", "patch_cnn", "classify"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    for it in range(args.warmup + args.steps):
+        e = ev[it - args.warmup] if it >= args.warmup else [None] * 5
+        if e[0]: e[0].record()
+        _lib.call("cmlpl_conv0_map_f16", slab.data_ptr(), scene_rows, C0, s0, s1 - s0, W0, r0, nb, packed.data_ptr(),
+                  base + off_f0, st)
+        if e[1]: e[1].record()
+        _lib.call("cmlpl_spectral_head_f32", spec.data_ptr(), n_band, B0, K0, W0, packed.data_ptr(), base + off_hid,
+                  chunk, base + off_spe, st)
+        if e[2]: e[2].record()
+        _lib.call("cmlpl_patch_cnn_f16", base + off_f0, C0, W0, nb, packed.data_ptr(), base + off_p2, st)
+        if e[3]: e[3].record()
+        _lib.call("cmlpl_classify_f16", base + off_p2, base + off_spe, n_band, B0, K0, W0, packed.data_ptr(),
+                  labels.data_ptr(), None, st)
+        if e[4]: e[4].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    stage_ms = {names[i]: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in ev])) for i in range(4)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    px_step = R0 * C0 * world
+    value = px_step / (ms_dev / 1e3)
+    e2e_val = px_step / (ms_e2e / 1e3)
+    cnn_ms = stage_ms["patch_cnn"]
+    achieved = n_band * FLOP_PER_PX_CNN / (cnn_ms / 1e3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("patch_cnn_dram_bytes_per_launch")
+    n_spec_launch = 2 * ((n_band + chunk - 1) // chunk)
+    launches_per_step = 1 + n_spec_launch + 1 + 1 + (1 if world > 1 else 0)
+    line = {
+        "metric": "pixels/sec full-scene inference", "value": value, "unit": "pixels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16; same 11-bit significand as the TF32 the "
+                 "reference's torch 1.8 GPU path used); fp32 elsewhere",
+        "data": "synthetic", "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "pixels/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(slab_host.numel() * 4 + spec_host.numel() * 4) * world,
+                "d2h_bytes_per_step": int(n_band) * world},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {"kernel": "patch_cnn_kernel<20> (tcgen05 conv1+conv2 per pixel)", "bound": "tensor",
+                     "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+                     "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside the step loop)",
+                     "algorithmic_flop_per_pixel": FLOP_PER_PX_CNN, "pixels_per_launch": n_band,
+                     "kernel_ms": cnn_ms, "stage_ms": stage_ms,
+                     "whole_step_algorithmic_tflops": px_step / world * FLOP_PER_PX_ALL / (ms_dev / 1e3) / 1e12},
+        "host_prep_s": t_data,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cmlpl_oracle as O      # cpu_baseline leg: the oracle port is the thing timed here
+        torch.manual_seed(1088)
+        sd = O.basenet2_init(B0, K0)
+        threads = os.cpu_count() or 1
+        tot_t, tot_n, rows = 0.0, 0, 6
+        rr = 100
+        while tot_t < 12.0 and rr + rows < R0:
+            dt, n = cpu_reference_pass(cube_pca, spectra, sd, (rr, rr + rows), threads)
+            tot_t += dt; tot_n += n; rr += rows
+        line["cpu_baseline"] = {"value": tot_n / tot_t, "unit": "pixels/s", "cores": threads, "kind": "port",
+                                "sample": f"{tot_n} px (rows 100..{rr} of the same scene) in {tot_t:.1f} s: oracle port "
+                                          "of the reference test_whole path (per-pixel patch loop + BaseNet2 fp32 bs 512 "
+                                          "+ argmax), torch threads = all host cores"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

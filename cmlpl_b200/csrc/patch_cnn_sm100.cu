@@ -4,9 +4,10 @@
 // (kind::f16, fp16 operands = TF32's 11-bit significand, fp32 accumulate in TMEM).
 //
 // Persistent kernel, one CTA per SM, warp-specialised:
-//   warps 0-3  epilogue  (TMEM -> registers: bias + residual + ReLU + pool -> next stage)
-//   warps 4-7  loaders   (window of F0pad -> shared memory, zero-padded parity planes)
-//   warp  8    MMA issuer (one thread) + TMEM allocator
+//   warps 0-7   epilogue  (TMEM -> registers: bias + residual + ReLU + pool -> next stage);
+//               warp w reads TMEM lane quadrant w%4 and the 32 output channels of half w/4
+//   warps 8-11  loaders   (window of F0pad -> shared memory, zero-padded parity planes)
+//   warp  12    MMA issuer (one thread) + TMEM allocator
 //
 // Implicit GEMM without im2col: activations live in shared memory in the UMMA "no swizzle,
 // K-major" canonical layout with SBO = 128 B, i.e. for every 16-byte K-chunk (8 channels) a
@@ -138,19 +139,48 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor kind::f16: c=f32 (bit4), a=b=f16 (0), K-major both, N>>3 @17, M>>4 @24
 constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(64 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
 
-// which parity plane / row offset feeds tap row dy of an output row of parity q:
-//   even outputs (y=2i): dy=0 -> odd plane row i (row 0 of the odd plane is the zero row y=-1),
-//                        dy=1 -> even plane row i, dy=2 -> odd plane row i+1
-//   odd outputs (y=2i+1): dy=0 -> even plane row i, dy=1 -> odd plane row i+1, dy=2 -> even plane row i+1
-__device__ __forceinline__ void tap_src(int q, int dy, int& plane, int& roff) {
-  if (q == 0) { plane = (dy == 1) ? 0 : 1; roff = (dy == 2) ? 1 : 0; }
-  else        { plane = (dy == 1) ? 1 : 0; roff = (dy == 0) ? 0 : 1; }
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// One 128-row accumulator tile of a 3x3 convolution: 9 taps x 4 K-steps = 36 tcgen05.mma with
+// compile-time descriptor offsets (everything but the two base words is an immediate, so the
+// operands stay in uniform registers and the single issuing lane runs back-to-back UTCHMMA).
+//   Q      parity of the output rows of this tile
+//   PWX    padded row width (entries), CHX bytes between K-chunks, PLANEX bytes per parity plane
+//   a_lo   low descriptor word of (even plane, entry 1 + first output row of the tile)
+//   b_lo   low descriptor word of the weights (tap 0, K-step 0)
+template <int Q, int PWX, int CHX, int PLANEX>
+__device__ __forceinline__ void issue_conv_tile(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo) {
+  constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;   // SBO = 128 B, version 1
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap % 3;
+    // even outputs (y=2i): dy=0 -> odd plane row i, dy=1 -> even plane row i, dy=2 -> odd plane row i+1
+    // odd outputs (y=2i+1): dy=0 -> even plane row i, dy=1 -> odd plane row i+1, dy=2 -> even plane row i+1
+    const int plane = (Q == 0) ? (dy == 1 ? 0 : 1) : (dy == 1 ? 1 : 0);
+    const int roff = (Q == 0) ? (dy == 2 ? 1 : 0) : (dy == 0 ? 0 : 1);
+    const int a_off = plane * PLANEX + (roff * PWX + dx - 1) * 16;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t da = kHi | uint64_t(a_lo + uint32_t((a_off + ks * 2 * CHX) / 16));
+      const uint64_t db = kHi | uint64_t(b_lo + uint32_t((tap * 8192 + ks * 2048) / 16));
+      umma_f16(d_tmem, da, db, kIdesc, (tap | ks) != 0 ? 1u : 0u);
+    }
+  }
 }
 
 enum { BAR_A1_FULL = 0, BAR_A1_EMPTY, BAR_C1_FULL0, BAR_C1_FULL1, BAR_C1_EMPTY0, BAR_C1_EMPTY1,
        BAR_A2_FULL, BAR_C2_FULL, BAR_C2_EMPTY, BAR_COUNT };
 
-constexpr int kEpiThreads = 128, kLoadThreads = 128, kThreads = kEpiThreads + kLoadThreads + 32;
+constexpr int kEpiThreads = 256, kLoadThreads = 96, kThreads = kEpiThreads + kLoadThreads + 32;
+constexpr int kEpiWarps = kEpiThreads / 32, kLoadWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + kLoadThreads / 32;
 
 template <int W>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -196,117 +226,120 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
     mbar_init(bars + 8 * BAR_C2_EMPTY, kEpiThreads);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(sbase + Cfg::S_TMEM, Cfg::TM_COLS);
+  if (warp == kMmaWarp) tmem_alloc(sbase + Cfg::S_TMEM, Cfg::TM_COLS);
   fence_proxy_async();   // weights / zeros written through the generic proxy, read by the MMA (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= kLoadWarp0 && warp < kMmaWarp) {
     // ================================================================ LOADERS
     const int lt = tid - kEpiThreads;                        // 0..127
     constexpr int ITEMS = W * W * 8;                         // 16-byte items per patch
     constexpr int PER = (ITEMS + kLoadThreads - 1) / kLoadThreads;
+    constexpr int HALF = (PER + 1) / 2;
     uint32_t ph = 0;
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
       const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
       const __half* src0 = f0pad + (int64_t(rb) * pitch + c) * 64;
       mbar_wait(bars + 8 * BAR_A1_EMPTY, ph ^ 1, 1);         // conv1 of the previous patch has read A1
-      uint4 v[PER];
+      // two batches: all loads of a batch in flight (L2 latency overlapped), then its stores
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint4 v[HALF];
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const int it = lt + j * kLoadThreads;
-        if (it < ITEMS) {
-          const int pix = it >> 3, ch = it & 7;
-          const int y = pix / W, x = pix - y * W;
-          v[j] = __ldg(reinterpret_cast<const uint4*>(src0 + (int64_t(y) * pitch + x) * 64) + ch);
+        for (int j = 0; j < HALF; ++j) {
+          const int it = lt + (half * HALF + j) * kLoadThreads;
+          if (it < ITEMS) {
+            const int pix = it >> 3, ch = it & 7;
+            const int y = pix / W, x = pix - y * W;
+            v[j] = __ldg(reinterpret_cast<const uint4*>(src0 + (int64_t(y) * pitch + x) * 64) + ch);
+          }
         }
-      }
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const int it = lt + j * kLoadThreads;
-        if (it < ITEMS) {
-          const int pix = it >> 3, ch = it & 7;
-          const int y = pix / W, x = pix - y * W;
-          const int q = y & 1, prow = (y + q) >> 1;          // even plane: y/2 ; odd plane: (y+1)/2
-          const int ent = 1 + prow * Cfg::PW1 + x;
-          *reinterpret_cast<uint4*>(smem + Cfg::S_A1 + q * Cfg::PLANE1 + ch * Cfg::CH1 + ent * 16) = v[j];
+        for (int j = 0; j < HALF; ++j) {
+          const int it = lt + (half * HALF + j) * kLoadThreads;
+          if (it < ITEMS) {
+            const int pix = it >> 3, ch = it & 7;
+            const int y = pix / W, x = pix - y * W;
+            const int q = y & 1, prow = (y + q) >> 1;        // even plane: y/2 ; odd plane: (y+1)/2
+            const int ent = 1 + prow * Cfg::PW1 + x;
+            *reinterpret_cast<uint4*>(smem + Cfg::S_A1 + q * Cfg::PLANE1 + ch * Cfg::CH1 + ent * 16) = v[j];
+          }
         }
       }
       fence_proxy_async();
       mbar_arrive(bars + 8 * BAR_A1_FULL);
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ================================================================ MMA ISSUER
-    if (lane == 0) {
-      uint32_t ph = 0;
-      for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
-        mbar_wait(bars + 8 * BAR_A1_FULL, ph, 2);
-        tc_fence_after();
-        // ---- conv1: NT1 halves x 2 parities, 9 taps x 4 K-steps each
-#pragma unroll 1
-        for (int h = 0; h < Cfg::NT1; ++h) {
-          mbar_wait(bars + 8 * (BAR_C1_EMPTY0 + h), ph ^ 1, 3);   // epilogue drained this half (prev patch)
-          tc_fence_after();
-#pragma unroll 1
-          for (int q = 0; q < 2; ++q) {
-            const uint32_t d = tmem + Cfg::TM_C1 + (h * 2 + q) * 64;
-            uint32_t acc = 0;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              int plane, roff;
-              tap_src(q, dy, plane, roff);
-              const uint32_t a0 = sbase + Cfg::S_A1 + plane * Cfg::PLANE1 +
-                                  (1 + roff * Cfg::PW1 + (dx - 1) + h * 128) * 16;
-              const uint32_t b0 = sbase + Cfg::S_W1 + tap * 8192;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                umma_f16(d, make_desc(a0 + ks * 2 * Cfg::CH1, Cfg::CH1, 128),
-                         make_desc(b0 + ks * 2048, 1024, 128), kIdesc, acc);
-                acc = 1;
-              }
-            }
-          }
-          umma_commit(bars + 8 * (BAR_C1_FULL0 + h));
-        }
-        umma_commit(bars + 8 * BAR_A1_EMPTY);                 // every conv1 read of A1 has completed
-        // ---- conv2: 2 parities, one 128-row tile each
-        mbar_wait(bars + 8 * BAR_A2_FULL, ph, 4);
-        tc_fence_after();
-        mbar_wait(bars + 8 * BAR_C2_EMPTY, ph ^ 1, 5);
-        tc_fence_after();
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          const uint32_t d = tmem + Cfg::TM_C2 + q * 64;
-          uint32_t acc = 0;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            int plane, roff;
-            tap_src(q, dy, plane, roff);
-            const uint32_t a0 = sbase + Cfg::S_A2 + plane * Cfg::PLANE2 + (1 + roff * Cfg::PW2 + (dx - 1)) * 16;
-            const uint32_t b0 = sbase + Cfg::S_W2 + tap * 8192;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_f16(d, make_desc(a0 + ks * 2 * Cfg::CH2, Cfg::CH2, 128),
-                       make_desc(b0 + ks * 2048, 1024, 128), kIdesc, acc);
-              acc = 1;
-            }
-          }
-        }
-        umma_commit(bars + 8 * BAR_C2_FULL);
-      }
-    }
-  } else {
-    // ================================================================ EPILOGUE (warps 0-3)
-    const int L = tid;                                       // TMEM lane == row of the tile
-    const uint32_t lane_addr = tmem + (uint32_t(warp * 32) << 16);
+    // The whole warp walks the protocol (so every address stays warp-uniform); one elected lane
+    // issues the MMAs and the commits.  A 512-column allocation necessarily starts at column 0.
+    if (tmem != 0) { printf("patch_cnn: unexpected TMEM base %u\n", tmem); __trap(); }
+    const uint32_t a1_lo = ((sbase + Cfg::S_A1 + 16) >> 4) | (uint32_t(Cfg::CH1 >> 4) << 16);
+    const uint32_t a2_lo = ((sbase + Cfg::S_A2 + 16) >> 4) | (uint32_t(Cfg::CH2 >> 4) << 16);
+    const uint32_t w1_lo = ((sbase + Cfg::S_W1) >> 4) | (uint32_t(1024 >> 4) << 16);
+    const uint32_t w2_lo = ((sbase + Cfg::S_W2) >> 4) | (uint32_t(1024 >> 4) << 16);
     uint32_t ph = 0;
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
+      mbar_wait(bars + 8 * BAR_A1_FULL, ph, 2);
+      // ---- conv1: NT1 halves x 2 parities
+#pragma unroll
+      for (int h = 0; h < Cfg::NT1; ++h) {
+        mbar_wait(bars + 8 * (BAR_C1_EMPTY0 + h), ph ^ 1, 3);     // epilogue drained this half (prev patch)
+        tc_fence_after();
+        if (elect_one_sync()) {
+          issue_conv_tile<0, Cfg::PW1, Cfg::CH1, Cfg::PLANE1>(Cfg::TM_C1 + (h * 2 + 0) * 64, a1_lo + h * 128, w1_lo);
+          issue_conv_tile<1, Cfg::PW1, Cfg::CH1, Cfg::PLANE1>(Cfg::TM_C1 + (h * 2 + 1) * 64, a1_lo + h * 128, w1_lo);
+          umma_commit(bars + 8 * (BAR_C1_FULL0 + h));
+          if (h == Cfg::NT1 - 1) umma_commit(bars + 8 * BAR_A1_EMPTY);   // every conv1 read of A1 has completed
+        }
+        __syncwarp();
+      }
+      // ---- conv2: 2 parities, one 128-row tile each
+      mbar_wait(bars + 8 * BAR_A2_FULL, ph, 4);
+      mbar_wait(bars + 8 * BAR_C2_EMPTY, ph ^ 1, 5);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        issue_conv_tile<0, Cfg::PW2, Cfg::CH2, Cfg::PLANE2>(Cfg::TM_C2, a2_lo, w2_lo);
+        issue_conv_tile<1, Cfg::PW2, Cfg::CH2, Cfg::PLANE2>(Cfg::TM_C2 + 64, a2_lo, w2_lo);
+        umma_commit(bars + 8 * BAR_C2_FULL);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================ EPILOGUE (warps 0-7)
+    const int L = (warp & 3) * 32 + lane;                    // TMEM lane == row of the tile
+    const int chalf = warp >> 2;                             // which 32 output channels this warp handles
+    const uint32_t lane_addr = tmem + (uint32_t((warp & 3) * 32) << 16) + chalf * 32;
+    const float* bias1 = sbias + chalf * 32;
+    const float* bias2 = sbias + 64 + chalf * 32;
+    uint32_t ph = 0;
+    // bias + residual + ReLU on both rows of the pooling window, sum, add the horizontal neighbour
+    auto pool16 = [&](const float* e, const float* o, const uint4* re, const uint4* ro, const float* bias,
+                      uint4& out_lo, uint4& out_hi) {
+      const __half2* he = reinterpret_cast<const __half2*>(re);
+      const __half2* ho = reinterpret_cast<const __half2*>(ro);
+      float pooled[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 fe = __half22float2(he[j]), fo = __half22float2(ho[j]);
+        const float b0 = bias[2 * j], b1 = bias[2 * j + 1];
+        pooled[2 * j] = fmaxf(e[2 * j] + b0 + fe.x, 0.f) + fmaxf(o[2 * j] + b0 + fo.x, 0.f);
+        pooled[2 * j + 1] = fmaxf(e[2 * j + 1] + b1 + fe.y, 0.f) + fmaxf(o[2 * j + 1] + b1 + fo.y, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pooled[j] = (pooled[j] + __shfl_xor_sync(0xffffffffu, pooled[j], 1)) * 0.25f;
+      __half2 hv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hv[j] = __floats2half2_rn(pooled[2 * j], pooled[2 * j + 1]);
+      out_lo = *reinterpret_cast<uint4*>(&hv[0]);
+      out_hi = *reinterpret_cast<uint4*>(&hv[4]);
+    };
+    for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
       const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
-      const __half* win = f0pad + (int64_t(rb) * pitch + c) * 64;
+      const __half* win = f0pad + (int64_t(rb) * pitch + c) * 64 + chalf * 32;
       // ------------------------------------------------ conv1 epilogue -> A2 (pooled, fp16)
 #pragma unroll 1
       for (int h = 0; h < Cfg::NT1; ++h) {
@@ -314,49 +347,40 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         const int i = m / Cfg::PW1, x = m - i * Cfg::PW1;
         const bool valid = (m < Cfg::M1) && (x < W);
         const bool writer = valid && ((x & 1) == 0);
-        // residual = conv0 output at the same position (models.py:133,135), rows 2i and 2i+1
-        const uint4* resE = reinterpret_cast<const uint4*>(win + (int64_t(2 * i) * pitch + x) * 64);
-        const uint4* resO = reinterpret_cast<const uint4*>(win + (int64_t(2 * i + 1) * pitch + x) * 64);
-        // destination in the conv2 planes: pooled pixel (py=i, px=x/2)
+        // residual = conv0 output at the same position (models.py:133,135), rows 2i and 2i+1;
+        // it does not depend on the MMA, so fetch it (L2) before waiting for the accumulators
+        uint4 re[4], ro[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { re[k] = make_uint4(0, 0, 0, 0); ro[k] = make_uint4(0, 0, 0, 0); }
+        if (valid) {
+          const uint4* resE = reinterpret_cast<const uint4*>(win + (int64_t(2 * i) * pitch + x) * 64);
+          const uint4* resO = reinterpret_cast<const uint4*>(win + (int64_t(2 * i + 1) * pitch + x) * 64);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { re[k] = __ldg(resE + k); ro[k] = __ldg(resO + k); }
+        }
+        // destination in the conv2 planes: pooled pixel (py=i, px=x/2), chunks chalf*4 .. chalf*4+3
         const int q2 = i & 1, prow2 = (i + q2) >> 1;
-        unsigned char* dst = smem + Cfg::S_A2 + q2 * Cfg::PLANE2 + (1 + prow2 * Cfg::PW2 + (x >> 1)) * 16;
+        unsigned char* dst = smem + Cfg::S_A2 + q2 * Cfg::PLANE2 + (chalf * 4) * Cfg::CH2 +
+                             (1 + prow2 * Cfg::PW2 + (x >> 1)) * 16;
         mbar_wait(bars + 8 * (BAR_C1_FULL0 + h), ph, 6);
         tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          float e[16], o[16];
-          tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64 + cc * 16, e);
-          tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64 + cc * 16, o);
-          uint4 re[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          uint4 ro[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (valid) {
-            re[0] = __ldg(resE + cc * 2); re[1] = __ldg(resE + cc * 2 + 1);
-            ro[0] = __ldg(resO + cc * 2); ro[1] = __ldg(resO + cc * 2 + 1);
-          }
-          tmem_ld_wait();
-          const __half2* he = reinterpret_cast<const __half2*>(re);
-          const __half2* ho = reinterpret_cast<const __half2*>(ro);
-          float pooled[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 fe = __half22float2(he[j]), fo = __half22float2(ho[j]);
-            const float b0 = sbias[cc * 16 + 2 * j], b1 = sbias[cc * 16 + 2 * j + 1];
-            const float v0 = fmaxf(e[2 * j] + b0 + fe.x, 0.f) + fmaxf(o[2 * j] + b0 + fo.x, 0.f);
-            const float v1 = fmaxf(e[2 * j + 1] + b1 + fe.y, 0.f) + fmaxf(o[2 * j + 1] + b1 + fo.y, 0.f);
-            pooled[2 * j] = v0; pooled[2 * j + 1] = v1;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pooled[j] = (pooled[j] + __shfl_xor_sync(0xffffffffu, pooled[j], 1)) * 0.25f;
-          if (writer) {
-            __half2 hv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hv[j] = __floats2half2_rn(pooled[2 * j], pooled[2 * j + 1]);
-            *reinterpret_cast<uint4*>(dst + (cc * 2) * Cfg::CH2) = *reinterpret_cast<uint4*>(&hv[0]);
-            *reinterpret_cast<uint4*>(dst + (cc * 2 + 1) * Cfg::CH2) = *reinterpret_cast<uint4*>(&hv[4]);
-          }
-        }
+        float e0[16], o0[16], e1[16], o1[16];
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64, e0);
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64, o0);
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64 + 16, e1);
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64 + 16, o1);
+        tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bars + 8 * (BAR_C1_EMPTY0 + h));
+        mbar_arrive(bars + 8 * (BAR_C1_EMPTY0 + h));         // accumulators are in registers: free the tiles
+        uint4 w0, w1, w2, w3;
+        pool16(e0, o0, &re[0], &ro[0], bias1, w0, w1);
+        pool16(e1, o1, &re[2], &ro[2], bias1 + 16, w2, w3);
+        if (writer) {
+          *reinterpret_cast<uint4*>(dst) = w0;
+          *reinterpret_cast<uint4*>(dst + Cfg::CH2) = w1;
+          *reinterpret_cast<uint4*>(dst + 2 * Cfg::CH2) = w2;
+          *reinterpret_cast<uint4*>(dst + 3 * Cfg::CH2) = w3;
+        }
       }
       fence_proxy_async();
       mbar_arrive(bars + 8 * BAR_A2_FULL);
@@ -367,50 +391,38 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         const int i = m / Cfg::PW2, x = m - i * Cfg::PW2;
         const bool valid = (m < Cfg::M2) && (x < Cfg::H2);
         const bool writer = valid && ((x & 1) == 0);
-        // residual = pooled conv1 output (models.py:137,139) at rows 2i (even plane row i) and 2i+1 (odd plane row i+1)
-        const unsigned char* rE = smem + Cfg::S_A2 + 0 * Cfg::PLANE2 + (1 + i * Cfg::PW2 + x) * 16;
-        const unsigned char* rO = smem + Cfg::S_A2 + 1 * Cfg::PLANE2 + (1 + (i + 1) * Cfg::PW2 + x) * 16;
-        __half* dst = p2out + (p * Cfg::P + (i * (Cfg::H2 / 2) + (x >> 1))) * 64;
-        mbar_wait(bars + 8 * BAR_C2_FULL, ph, 8);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          float e[16], o[16];
-          tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64 + cc * 16, e);
-          tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64 + cc * 16, o);
-          uint4 re[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          uint4 ro[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (valid) {
-            re[0] = *reinterpret_cast<const uint4*>(rE + (cc * 2) * Cfg::CH2);
-            re[1] = *reinterpret_cast<const uint4*>(rE + (cc * 2 + 1) * Cfg::CH2);
-            ro[0] = *reinterpret_cast<const uint4*>(rO + (cc * 2) * Cfg::CH2);
-            ro[1] = *reinterpret_cast<const uint4*>(rO + (cc * 2 + 1) * Cfg::CH2);
-          }
-          tmem_ld_wait();
-          const __half2* he = reinterpret_cast<const __half2*>(re);
-          const __half2* ho = reinterpret_cast<const __half2*>(ro);
-          float pooled[16];
+        // residual = pooled conv1 output (models.py:137,139): rows 2i (even plane row i), 2i+1 (odd plane row i+1)
+        uint4 re[4], ro[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 fe = __half22float2(he[j]), fo = __half22float2(ho[j]);
-            const float b0 = sbias[64 + cc * 16 + 2 * j], b1 = sbias[64 + cc * 16 + 2 * j + 1];
-            const float v0 = fmaxf(e[2 * j] + b0 + fe.x, 0.f) + fmaxf(o[2 * j] + b0 + fo.x, 0.f);
-            const float v1 = fmaxf(e[2 * j + 1] + b1 + fe.y, 0.f) + fmaxf(o[2 * j + 1] + b1 + fo.y, 0.f);
-            pooled[2 * j] = v0; pooled[2 * j + 1] = v1;
-          }
+        for (int k = 0; k < 4; ++k) { re[k] = make_uint4(0, 0, 0, 0); ro[k] = make_uint4(0, 0, 0, 0); }
+        if (valid) {
+          const unsigned char* rE = smem + Cfg::S_A2 + (chalf * 4) * Cfg::CH2 + (1 + i * Cfg::PW2 + x) * 16;
+          const unsigned char* rO = smem + Cfg::S_A2 + Cfg::PLANE2 + (chalf * 4) * Cfg::CH2 +
+                                    (1 + (i + 1) * Cfg::PW2 + x) * 16;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pooled[j] = (pooled[j] + __shfl_xor_sync(0xffffffffu, pooled[j], 1)) * 0.25f;
-          if (writer) {
-            __half2 hv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hv[j] = __floats2half2_rn(pooled[2 * j], pooled[2 * j + 1]);
-            uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 16);
-            __stcs(d4, *reinterpret_cast<uint4*>(&hv[0]));
-            __stcs(d4 + 1, *reinterpret_cast<uint4*>(&hv[4]));
+          for (int k = 0; k < 4; ++k) {
+            re[k] = *reinterpret_cast<const uint4*>(rE + k * Cfg::CH2);
+            ro[k] = *reinterpret_cast<const uint4*>(rO + k * Cfg::CH2);
           }
         }
+        __half* dst = p2out + (p * Cfg::P + (i * (Cfg::H2 / 2) + (x >> 1))) * 64 + chalf * 32;
+        mbar_wait(bars + 8 * BAR_C2_FULL, ph, 8);
+        tc_fence_after();
+        float e0[16], o0[16], e1[16], o1[16];
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64, e0);
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64, o0);
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64 + 16, e1);
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64 + 16, o1);
+        tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bars + 8 * BAR_C2_EMPTY);
+        uint4 w0, w1, w2, w3;
+        pool16(e0, o0, &re[0], &ro[0], bias2, w0, w1);
+        pool16(e1, o1, &re[2], &ro[2], bias2 + 16, w2, w3);
+        if (writer) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          __stcs(d4, w0); __stcs(d4 + 1, w1); __stcs(d4 + 2, w2); __stcs(d4 + 3, w3);
+        }
       }
       // A2 is rewritten by the next patch's conv1 epilogue: all residual reads must be done
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
@@ -420,7 +432,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, Cfg::TM_COLS);
   }

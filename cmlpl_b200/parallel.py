@@ -1,0 +1,65 @@
+"""Row-band sharding of full-scene inference across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo for the CPU tests of this host
+logic).  Pixels are independent, so there is no data-path collective: rank g owns scene rows
+[r0, r1) and needs cube rows [r0-hw, r1+w-hw-1) mirrored at true scene edges only -- read from
+its own slab.  The only exchanges are at the end: all-gather of the uint8 label map and
+all-reduce(sum) of the int64 confusion matrix behind OA/AA/kappa.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def band_of(rank: int, world: int, scene_rows: int):
+    """Contiguous row band of ``rank``: ceil(R/world) rows each, last ranks may be short/empty."""
+    per = -(-scene_rows // world)
+    r0 = min(rank * per, scene_rows)
+    return r0, min(r0 + per, scene_rows)
+
+
+def _mirror(o, n):
+    return -o - 1 if o < 0 else (2 * n - 1 - o if o >= n else o)
+
+
+def slab_of(r0: int, r1: int, scene_rows: int, w: int):
+    """Cube rows [s0, s1) the band [r0, r1) reads (window rows r-w//2 .. r-w//2+w-1, mirrored)."""
+    if r1 <= r0:
+        return r0, r0
+    lo = -(w // 2)
+    cand = [_mirror(r0 + lo, scene_rows), r0, r1 - 1, _mirror(r1 - 1 + lo + w - 1, scene_rows)]
+    return min(cand), max(cand) + 1
+
+
+def gather_label_map(local_labels: torch.Tensor, scene_rows: int, cols: int, group=None) -> torch.Tensor:
+    """all-gather the per-band uint8 labels into the raster-ordered label map [scene_rows*cols].
+    Bands are padded to the common band height so one fixed-size all_gather suffices."""
+    world = dist.get_world_size(group)
+    per = -(-scene_rows // world)
+    buf = torch.zeros(per * cols, dtype=torch.uint8, device=local_labels.device)
+    buf[: local_labels.numel()] = local_labels
+    out = torch.empty(world * per * cols, dtype=torch.uint8, device=local_labels.device)
+    dist.all_gather_into_tensor(out, buf, group=group) if out.is_cuda else \
+        dist.all_gather(list(out.view(world, -1).unbind(0)), buf, group=group)
+    return out[: scene_rows * cols]
+
+
+def reduce_confusion(cm: torch.Tensor, group=None) -> torch.Tensor:
+    """all-reduce(sum) of the int64 [C,C] confusion matrix (exact integer counts)."""
+    dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=group)
+    return cm
+
+
+def sharded_scene_labels(infer_band, scene_rows: int, cols: int, labels_true: torch.Tensor | None = None,
+                         num_classes: int = 0, confusion_fn=None, group=None):
+    """Run ``infer_band(r0, r1) -> uint8 labels [(r1-r0)*cols]`` on this rank's band, then exchange.
+    Returns (label map of the whole scene, confusion matrix or None)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    r0, r1 = band_of(rank, world, scene_rows)
+    local = infer_band(r0, r1)
+    cm = None
+    if labels_true is not None and confusion_fn is not None:
+        cm = reduce_confusion(confusion_fn(local, labels_true[r0 * cols:r1 * cols], num_classes), group)
+    return gather_label_map(local, scene_rows, cols, group), cm
