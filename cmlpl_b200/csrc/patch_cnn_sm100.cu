@@ -6,8 +6,10 @@
 // Persistent kernel, one CTA per SM, warp-specialised:
 //   warps 0-7   epilogue  (TMEM -> registers: bias + residual + ReLU + pool -> next stage);
 //               warp w reads TMEM lane quadrant w%4 and the 32 output channels of half w/4
-//   warps 8-11  loaders   (window of F0pad -> shared memory, zero-padded parity planes)
-//   warp  12    MMA issuer (one thread) + TMEM allocator
+//   warps 8-9   loaders   (cp.async 16 B straight into the zero-padded parity planes: 8 pixels x 8
+//               channel chunks per step; the (row, column) pattern repeats every two window rows,
+//               so per-thread offsets are computed once)
+//   warp  10    MMA issuer (one elected lane) + TMEM allocator
 //
 // Implicit GEMM without im2col: activations live in shared memory in the UMMA "no swizzle,
 // K-major" canonical layout with SBO = 128 B, i.e. for every 16-byte K-chunk (8 channels) a
@@ -92,6 +94,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     if (mbar_try_wait(bar, parity)) return;
   printf("patch_cnn: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
   __trap();
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (UBLKCP); completes `bytes` transaction bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -179,14 +195,22 @@ __device__ __forceinline__ void issue_conv_tile(uint32_t d_tmem, uint32_t a_lo, 
 enum { BAR_A1_FULL = 0, BAR_A1_EMPTY, BAR_C1_FULL0, BAR_C1_FULL1, BAR_C1_EMPTY0, BAR_C1_EMPTY1,
        BAR_A2_FULL, BAR_C2_FULL, BAR_C2_EMPTY, BAR_COUNT };
 
-constexpr int kEpiThreads = 256, kLoadThreads = 96, kThreads = kEpiThreads + kLoadThreads + 32;
+constexpr int kEpiThreads = 256, kLoadThreads = 64, kThreads = kEpiThreads + kLoadThreads + 32;
 constexpr int kEpiWarps = kEpiThreads / 32, kLoadWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + kLoadThreads / 32;
 
-template <int W>
+// TRACE: CTA 0 records clock64() at the protocol points of its first 64 patches into
+// trace[patch][16] (diagnostics only; see cmlpl_debug_patch_cnn_trace).
+#define CMLPL_TRACE(slot)                                                                  \
+  do {                                                                                     \
+    if (TRACE && blockIdx.x == 0 && (p - p_begin) < 64) trace[(p - p_begin) * 16 + (slot)] = clock64(); \
+  } while (0)
+
+template <int W, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
                  const unsigned char* __restrict__ packed_w1, const unsigned char* __restrict__ packed_w2,
-                 const float* __restrict__ b1g, const float* __restrict__ b2g, __half* __restrict__ p2out) {
+                 const float* __restrict__ b1g, const float* __restrict__ b2g, __half* __restrict__ p2out,
+                 long long* __restrict__ trace) {
   using Cfg = PatchCfg<W>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,6 +224,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
   const int64_t p_begin = blockIdx.x * per;
   const int64_t p_end = (p_begin + per < npix) ? p_begin + per : npix;
   const int pitch = cols + W - 1;   // padded map width in pixels
+  const int plane_rows = band_rows + W - 1;   // padded map height (rows per chunk plane)
 
   // ---------------------------------------------------------------- one-time setup
   {  // weights -> smem (already in UMMA layout), zero the activation planes, biases
@@ -216,7 +241,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
   if (tid < 64) { sbias[tid] = b1g[tid]; sbias[64 + tid] = b2g[tid]; }
   if (tid == 0) {
     mbar_init(bars + 8 * BAR_A1_FULL, kLoadThreads);
-    mbar_init(bars + 8 * BAR_A1_EMPTY, 1);
+    mbar_init(bars + 8 * BAR_A1_EMPTY, 1 + kEpiThreads);   // conv1 MMAs done + residuals read
     mbar_init(bars + 8 * BAR_C1_FULL0, 1);
     mbar_init(bars + 8 * BAR_C1_FULL1, 1);
     mbar_init(bars + 8 * BAR_C1_EMPTY0, kEpiThreads);
@@ -235,41 +260,41 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
 
   if (warp >= kLoadWarp0 && warp < kMmaWarp) {
     // ================================================================ LOADERS
-    const int lt = tid - kEpiThreads;                        // 0..127
-    constexpr int ITEMS = W * W * 8;                         // 16-byte items per patch
-    constexpr int PER = (ITEMS + kLoadThreads - 1) / kLoadThreads;
-    constexpr int HALF = (PER + 1) / 2;
+    // F0 is chunk-planar in HBM ([8 chunks][rows][cols][8 halves]).  64 threads = 8 chunks x 8 pixels per
+    // step; 5 steps cover two window rows (40 pixels) and the pattern repeats for each of the W/2 row
+    // pairs: global += 2 rows, both planes += one plane row.  Per-thread offsets are computed once.
+    static_assert(W % 2 == 0 && (2 * W) % 8 == 0, "row-pair pattern needs 2W divisible by 8");
+    constexpr int STEPS = 2 * W / 8;
+    const int lt = tid - kEpiThreads;                        // 0..63
+    const int lch = lt >> 3, lpx = lt & 7;
+    int64_t goff[STEPS];                                     // halves, relative to the window origin of chunk 0
+    uint32_t soff[STEPS];                                    // smem byte address for row pair 0
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+      const int pix = st * 8 + lpx;                          // 0 .. 2W-1 within the row pair
+      const int y = pix / W, x = pix - y * W;                // y in {0,1}
+      goff[st] = ((int64_t(lch) * plane_rows + y) * pitch + x) * 8;
+      // even plane: row g ; odd plane: row g+1  (g = row pair)
+      soff[st] = sbase + Cfg::S_A1 + y * Cfg::PLANE1 + lch * Cfg::CH1 + (1 + y * Cfg::PW1 + x) * 16;
+    }
     uint32_t ph = 0;
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
       const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
-      const __half* src0 = f0pad + (int64_t(rb) * pitch + c) * 64;
-      mbar_wait(bars + 8 * BAR_A1_EMPTY, ph ^ 1, 1);         // conv1 of the previous patch has read A1
-      // two batches: all loads of a batch in flight (L2 latency overlapped), then its stores
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint4 v[HALF];
+      const __half* src = f0pad + (int64_t(rb) * pitch + c) * 8;
+      mbar_wait(bars + 8 * BAR_A1_EMPTY, ph ^ 1, 1);         // conv1 MMAs + residual reads of the previous patch done
+      // hold the copies back until the previous patch's conv1 epilogue has finished: the LSU queue is
+      // shared with the epilogue's shared-memory traffic, and the load still hides under conv2
+      if (p > p_begin) mbar_wait(bars + 8 * BAR_A2_FULL, ph ^ 1, 10);
+      if (lt == 0) CMLPL_TRACE(0);
 #pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-          const int it = lt + (half * HALF + j) * kLoadThreads;
-          if (it < ITEMS) {
-            const int pix = it >> 3, ch = it & 7;
-            const int y = pix / W, x = pix - y * W;
-            v[j] = __ldg(reinterpret_cast<const uint4*>(src0 + (int64_t(y) * pitch + x) * 64) + ch);
-          }
-        }
+      for (int g = 0; g < W / 2; ++g) {
 #pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-          const int it = lt + (half * HALF + j) * kLoadThreads;
-          if (it < ITEMS) {
-            const int pix = it >> 3, ch = it & 7;
-            const int y = pix / W, x = pix - y * W;
-            const int q = y & 1, prow = (y + q) >> 1;        // even plane: y/2 ; odd plane: (y+1)/2
-            const int ent = 1 + prow * Cfg::PW1 + x;
-            *reinterpret_cast<uint4*>(smem + Cfg::S_A1 + q * Cfg::PLANE1 + ch * Cfg::CH1 + ent * 16) = v[j];
-          }
-        }
+        for (int st = 0; st < STEPS; ++st)
+          cp_async16(soff[st] + g * Cfg::PW1 * 16, src + goff[st] + int64_t(2 * g) * pitch * 8);
       }
-      fence_proxy_async();
+      cp_async_wait_all();
+      fence_proxy_async();                                   // generic-proxy writes -> visible to the MMA
+      if (lt == 0) CMLPL_TRACE(1);
       mbar_arrive(bars + 8 * BAR_A1_FULL);
     }
   } else if (warp == kMmaWarp) {
@@ -284,6 +309,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
     uint32_t ph = 0;
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
       mbar_wait(bars + 8 * BAR_A1_FULL, ph, 2);
+      if (lane == 0) CMLPL_TRACE(2);
       // ---- conv1: NT1 halves x 2 parities
 #pragma unroll
       for (int h = 0; h < Cfg::NT1; ++h) {
@@ -297,16 +323,19 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         }
         __syncwarp();
       }
+      if (lane == 0) CMLPL_TRACE(3);
       // ---- conv2: 2 parities, one 128-row tile each
       mbar_wait(bars + 8 * BAR_A2_FULL, ph, 4);
       mbar_wait(bars + 8 * BAR_C2_EMPTY, ph ^ 1, 5);
       tc_fence_after();
+      if (lane == 0) CMLPL_TRACE(4);
       if (elect_one_sync()) {
         issue_conv_tile<0, Cfg::PW2, Cfg::CH2, Cfg::PLANE2>(Cfg::TM_C2, a2_lo, w2_lo);
         issue_conv_tile<1, Cfg::PW2, Cfg::CH2, Cfg::PLANE2>(Cfg::TM_C2 + 64, a2_lo, w2_lo);
         umma_commit(bars + 8 * BAR_C2_FULL);
       }
       __syncwarp();
+      if (lane == 0) CMLPL_TRACE(5);
     }
   } else {
     // ================================================================ EPILOGUE (warps 0-7)
@@ -338,8 +367,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
       out_hi = *reinterpret_cast<uint4*>(&hv[4]);
     };
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
-      const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
-      const __half* win = f0pad + (int64_t(rb) * pitch + c) * 64 + chalf * 32;
+      mbar_wait(bars + 8 * BAR_A1_FULL, ph, 9);             // the residuals are read back from A1
       // ------------------------------------------------ conv1 epilogue -> A2 (pooled, fp16)
 #pragma unroll 1
       for (int h = 0; h < Cfg::NT1; ++h) {
@@ -347,40 +375,63 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         const int i = m / Cfg::PW1, x = m - i * Cfg::PW1;
         const bool valid = (m < Cfg::M1) && (x < W);
         const bool writer = valid && ((x & 1) == 0);
-        // residual = conv0 output at the same position (models.py:133,135), rows 2i and 2i+1;
-        // it does not depend on the MMA, so fetch it (L2) before waiting for the accumulators
+        // residual = conv0 output at the same position (models.py:133,135), rows 2i and 2i+1: read it
+        // back from the A1 planes (same fp16 values the MMA consumes) before waiting for the
+        // accumulators.  A1 is stable until the loader is released, and the loader's release needs
+        // this thread's arrival below (after the last half's residual is in registers).
         uint4 re[4], ro[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { re[k] = make_uint4(0, 0, 0, 0); ro[k] = make_uint4(0, 0, 0, 0); }
         if (valid) {
-          const uint4* resE = reinterpret_cast<const uint4*>(win + (int64_t(2 * i) * pitch + x) * 64);
-          const uint4* resO = reinterpret_cast<const uint4*>(win + (int64_t(2 * i + 1) * pitch + x) * 64);
+          const unsigned char* rE = smem + Cfg::S_A1 + (chalf * 4) * Cfg::CH1 + (1 + i * Cfg::PW1 + x) * 16;
+          const unsigned char* rO = smem + Cfg::S_A1 + Cfg::PLANE1 + (chalf * 4) * Cfg::CH1 +
+                                    (1 + (i + 1) * Cfg::PW1 + x) * 16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { re[k] = __ldg(resE + k); ro[k] = __ldg(resO + k); }
+          for (int k = 0; k < 4; ++k) {
+            re[k] = *reinterpret_cast<const uint4*>(rE + k * Cfg::CH1);
+            ro[k] = *reinterpret_cast<const uint4*>(rO + k * Cfg::CH1);
+          }
+        }
+        if (h == Cfg::NT1 - 1) {
+          // make sure the loads have landed (consume them) before telling the loader A1 may be rewritten
+          uint32_t sink = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sink |= re[k].x ^ ro[k].w;
+          asm volatile("" ::"r"(sink) : "memory");
+          mbar_arrive(bars + 8 * BAR_A1_EMPTY);
         }
         // destination in the conv2 planes: pooled pixel (py=i, px=x/2), chunks chalf*4 .. chalf*4+3
         const int q2 = i & 1, prow2 = (i + q2) >> 1;
         unsigned char* dst = smem + Cfg::S_A2 + q2 * Cfg::PLANE2 + (chalf * 4) * Cfg::CH2 +
                              (1 + prow2 * Cfg::PW2 + (x >> 1)) * 16;
         mbar_wait(bars + 8 * (BAR_C1_FULL0 + h), ph, 6);
+        if (tid == 0) CMLPL_TRACE(6 + 2 * h);
         tc_fence_after();
-        float e0[16], o0[16], e1[16], o1[16];
-        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64, e0);
-        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64, o0);
-        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64 + 16, e1);
-        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64 + 16, o1);
+        // two 16-channel groups one after the other keeps only 32 accumulators live
+        float e[16], o[16];
+        uint4 w0, w1;
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64, e);
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64, o);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bars + 8 * (BAR_C1_EMPTY0 + h));         // accumulators are in registers: free the tiles
-        uint4 w0, w1, w2, w3;
-        pool16(e0, o0, &re[0], &ro[0], bias1, w0, w1);
-        pool16(e1, o1, &re[2], &ro[2], bias1 + 16, w2, w3);
+        if (tid == 0 && h == 0) CMLPL_TRACE(13);
+        pool16(e, o, &re[0], &ro[0], bias1, w0, w1);
+        if (tid == 0 && h == 0) CMLPL_TRACE(14);
         if (writer) {
           *reinterpret_cast<uint4*>(dst) = w0;
           *reinterpret_cast<uint4*>(dst + Cfg::CH2) = w1;
-          *reinterpret_cast<uint4*>(dst + 2 * Cfg::CH2) = w2;
-          *reinterpret_cast<uint4*>(dst + 3 * Cfg::CH2) = w3;
         }
+        if (tid == 0 && h == 0) CMLPL_TRACE(15);
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64 + 16, e);
+        tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64 + 16, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (BAR_C1_EMPTY0 + h));         // accumulators are in registers: free the tiles
+        pool16(e, o, &re[2], &ro[2], bias1 + 16, w0, w1);
+        if (writer) {
+          *reinterpret_cast<uint4*>(dst + 2 * Cfg::CH2) = w0;
+          *reinterpret_cast<uint4*>(dst + 3 * Cfg::CH2) = w1;
+        }
+        if (tid == 0) CMLPL_TRACE(7 + 2 * h);
       }
       fence_proxy_async();
       mbar_arrive(bars + 8 * BAR_A2_FULL);
@@ -406,24 +457,27 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
           }
         }
         __half* dst = p2out + (p * Cfg::P + (i * (Cfg::H2 / 2) + (x >> 1))) * 64 + chalf * 32;
+        if (tid == 0) CMLPL_TRACE(10);
         mbar_wait(bars + 8 * BAR_C2_FULL, ph, 8);
+        if (tid == 0) CMLPL_TRACE(11);
         tc_fence_after();
-        float e0[16], o0[16], e1[16], o1[16];
-        tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64, e0);
-        tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64, o0);
-        tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64 + 16, e1);
-        tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64 + 16, o1);
+        float e[16], o[16];
+        uint4 w0, w1;
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64, e);
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64, o);
+        tmem_ld_wait();
+        pool16(e, o, &re[0], &ro[0], bias2, w0, w1);
+        if (writer) { __stcs(d4, w0); __stcs(d4 + 1, w1); }
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64 + 16, e);
+        tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64 + 16, o);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bars + 8 * BAR_C2_EMPTY);
-        uint4 w0, w1, w2, w3;
-        pool16(e0, o0, &re[0], &ro[0], bias2, w0, w1);
-        pool16(e1, o1, &re[2], &ro[2], bias2 + 16, w2, w3);
-        if (writer) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
-          __stcs(d4, w0); __stcs(d4 + 1, w1); __stcs(d4 + 2, w2); __stcs(d4 + 3, w3);
-        }
+        pool16(e, o, &re[2], &ro[2], bias2 + 16, w0, w1);
+        if (writer) { __stcs(d4 + 2, w0); __stcs(d4 + 3, w1); }
       }
+      if (tid == 0) CMLPL_TRACE(12);
       // A2 is rewritten by the next patch's conv1 epilogue: all residual reads must be done
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
@@ -442,8 +496,8 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
 
 using namespace cmlpl;
 
-extern "C" int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
-                                   cmlpl_stream_t stream) {
+static int launch_patch_cnn(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
+                            long long* trace, int grid_override, cudaStream_t stream) {
   CMLPL_CHECK_ARG(f0pad && packed && p2, "patch_cnn: null pointer");
   CMLPL_CHECK_ARG(w == 20, "patch_cnn: w=%d unsupported (BaseNet2's classifier fixes w=20, tools/models.py:127)", w);
   CMLPL_CHECK_ARG(cols > 0 && band_rows > 0, "patch_cnn: bad dims");
@@ -452,15 +506,27 @@ extern "C" int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_
   using Cfg = PatchCfg<20>;
   const PackedLayout L = packed_layout(1, 1, w);   // conv offsets do not depend on B, C
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  auto kern = patch_cnn_kernel<20>;
+  auto kern = trace ? patch_cnn_kernel<20, true> : patch_cnn_kernel<20, false>;
   CMLPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   const int64_t npix = int64_t(band_rows) * cols;
-  int64_t grid = sm_count();
+  int64_t grid = grid_override > 0 ? grid_override : sm_count();
   if (grid > npix) grid = npix;
-  kern<<<int(grid), kThreads, Cfg::SMEM, static_cast<cudaStream_t>(stream)>>>(
+  kern<<<int(grid), kThreads, Cfg::SMEM, stream>>>(
       static_cast<const __half*>(f0pad), cols, band_rows, pk + L.w1, pk + L.w2,
       reinterpret_cast<const float*>(pk + L.b1), reinterpret_cast<const float*>(pk + L.b2),
-      static_cast<__half*>(p2));
+      static_cast<__half*>(p2), trace);
   CMLPL_CHECK_LAUNCH("patch_cnn");
   return CMLPL_OK;
+}
+
+extern "C" int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
+                                   cmlpl_stream_t stream) {
+  return launch_patch_cnn(f0pad, cols, w, band_rows, packed, p2, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+// Diagnostics: same kernel, CTA 0 writes clock64() stamps of its first 64 patches to trace[64][16].
+extern "C" int cmlpl_debug_patch_cnn_trace(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                                           void* p2, long long* trace, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(trace, "patch_cnn_trace: null trace buffer");
+  return launch_patch_cnn(f0pad, cols, w, band_rows, packed, p2, trace, 0, static_cast<cudaStream_t>(stream));
 }

@@ -1,7 +1,7 @@
 // Full-scene inference (tools/hyper_tools.py:416-437 test_whole) without materialised
 // patches.  Stages (one launch each, all on the caller's stream):
 //   1. conv0_map     conv0 (1x1, models.py:102,132) once per scene pixel -> mirrored,
-//                    halo-padded fp16 map F0pad[(rows+w-1),(cols+w-1),64]; a pixel's patch
+//                    halo-padded fp16 map F0pad[8 chunks][(rows+w-1)][(cols+w-1)][8 channels]; a pixel's patch
 //                    is then a plain w x w window of this map (hyper_tools.py:35-55,226-243)
 //   2. spectral_head relu(feat_spe(x)) (models.py:142-143) and its classifier columns
 //   3. patch_cnn     conv1/conv2 + residual + ReLU + avg-pool per pixel (patch_cnn_sm100.cu,
@@ -26,9 +26,12 @@ conv0_map_kernel(const float* __restrict__ cube, int scene_rows, int cols, int s
   __syncthreads();
   const int lo = window_lo(w);
   const int64_t total = int64_t(prow_n) * pcol_n * 8;
+  const int64_t plane = int64_t(prow_n) * pcol_n;
   for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int g = int(t & 7);
-    const int64_t pp = t >> 3;
+    // consecutive threads -> consecutive pixels of the same 8-channel group (coalesced 16-B stores
+    // into the chunk-planar map [8][prow_n][pcol_n][8])
+    const int g = int(t / plane);
+    const int64_t pp = t - int64_t(g) * plane;
     const int pr = int(pp / pcol_n), pc = int(pp - int64_t(pr) * pcol_n);
     const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0;
     const int sc = mirror_index(pc + lo, cols);
@@ -53,7 +56,7 @@ conv0_map_kernel(const float* __restrict__ cube, int scene_rows, int cols, int s
     __half2 h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-    *reinterpret_cast<uint4*>(f0pad + pp * 64 + g * 8) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(f0pad + (int64_t(g) * plane + pp) * 8) = *reinterpret_cast<uint4*>(h);
   }
 }
 

@@ -133,7 +133,7 @@ int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, int slab_row0
 /* Individual stages of cmlpl_scene_infer (exposed for tests / profiling). */
 int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows,
                         int w, int band_row0, int band_rows, const void* packed,
-                        void* f0pad /* f16 [band_rows+w-1, cols+w-1, 64] */, cmlpl_stream_t stream);
+                        void* f0pad /* f16 [8, band_rows+w-1, cols+w-1, 8]: chunk-planar (8 channels per 16-B chunk) */, cmlpl_stream_t stream);
 int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed,
                         void* p2 /* f16 [band_rows*cols, (w/4)^2, 64] */, cmlpl_stream_t stream);
 int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_features, int num_classes, int w,
@@ -142,6 +142,10 @@ int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_features, i
 int cmlpl_classify_f16(const void* p2, const float* spe_logits /* may be NULL */, int64_t n,
                        int num_features, int num_classes, int w, const void* packed,
                        uint8_t* labels, float* logits /* may be NULL */, cmlpl_stream_t stream);
+/* Diagnostics: cmlpl_patch_cnn_f16 with CTA 0 writing clock64() stamps of its first 64 patches
+ * (16 slots each: loader / MMA issuer / epilogue protocol points) to trace i64 [64,16]. */
+int cmlpl_debug_patch_cnn_trace(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                                void* p2, long long* trace, cmlpl_stream_t stream);
 /* hyper_tools.py:426 torch.max(outputs, 1): first index on ties.  logits f32 [n, C] -> u8 [n]. */
 int cmlpl_argmax_u8(const float* logits, int64_t n, int num_classes, uint8_t* labels,
                     cmlpl_stream_t stream);

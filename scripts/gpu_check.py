@@ -34,13 +34,14 @@ def main():
 
     # ---- stage 1: conv0 map
     cube_d = torch.from_numpy(cube).to(dev)
-    f0 = torch.empty((R + w - 1, C + w - 1, 64), dtype=torch.float16, device=dev)
+    f0 = torch.empty((8, R + w - 1, C + w - 1, 8), dtype=torch.float16, device=dev)
     _lib.call("cmlpl_conv0_map_f16", cube_d.data_ptr(), R, C, 0, R, w, 0, R, packed.data_ptr(), f0.data_ptr(),
               torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     pad = np.pad(cube, ((10, 9), (10, 9), (0, 0)), mode="symmetric")
     ref0 = torch.einsum("rcf,of->rco", torch.from_numpy(pad), sd["conv0.weight"][:, :, 0, 0]) + sd["conv0.bias"]
-    print("conv0_map rel err", rel(f0.float().cpu().numpy(), ref0.numpy()))
+    f0n = f0.permute(1, 2, 0, 3).reshape(R + w - 1, C + w - 1, 64)
+    print("conv0_map rel err", rel(f0n.float().cpu().numpy(), ref0.numpy()))
 
     # ---- stage 3: patch_cnn on the device's own f0 (fp16) vs torch on the same fp16 values
     n = R * C
@@ -50,7 +51,7 @@ def main():
               torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     print("patch_cnn ran in %.3f s" % (time.time() - t0))
-    f0c = f0.float().cpu()
+    f0c = f0n.float().cpu()
     w1 = sd["conv1.weight"].half().float(); w2 = sd["conv2.weight"].half().float()
     import torch.nn.functional as F
     idx = [0, 1, C - 1, C, n // 2, n - 1, 5 * C + 7]
