@@ -221,3 +221,80 @@ def confusion(pred_u8, label_i64, num_classes: int, cm: torch.Tensor | None = No
     _lib.call("cmlpl_confusion_i64", pred_u8.data_ptr(), label_i64.data_ptr(), pred_u8.numel(), num_classes,
               cm.data_ptr(), _stream())
     return cm
+
+
+# ------------------------------------------------------------------ losses / optimizer
+def ce_fwd_bwd(logits, labels=None, probs=None, mask=None, scale=1.0, want_grad=True):
+    """train.py:191 (labels) / :239-242 (probs, mask) -> (loss scalar tensor, dlogits or None)."""
+    _chk(logits, name="logits")
+    rows, C = logits.shape
+    loss = torch.zeros((), dtype=_f32, device=logits.device)
+    dz = torch.empty_like(logits) if want_grad else None
+    if labels is not None:
+        _chk(labels, torch.int64, "labels")
+    if probs is not None:
+        _chk(probs, name="probs")
+    if mask is not None:
+        _chk(mask, name="mask")
+    _lib.call("cmlpl_ce_fwd_bwd_f32", logits.data_ptr(), _p(labels), _p(probs), _p(mask), rows, C, float(scale),
+              loss.data_ptr(), _p(dz), _stream())
+    return loss, dz
+
+
+def bank_smooth(logits, feats, queue_feats, queue_probs, alpha, T, smooth, thr):
+    """train.py:203-222 -> (probs_orig, probs, mask)."""
+    _chk(logits, name="logits")
+    rows, C = logits.shape
+    probs_orig = torch.empty_like(logits)
+    probs = torch.empty_like(logits)
+    mask = torch.empty((rows,), dtype=_f32, device=logits.device)
+    work = None
+    queue, dim = 0, 0
+    if smooth:
+        _chk(feats, name="feats"); _chk(queue_feats, name="queue_feats"); _chk(queue_probs, name="queue_probs")
+        queue, dim = queue_feats.shape
+        work = torch.empty((rows, queue), dtype=_f32, device=logits.device)
+    _lib.call("cmlpl_bank_smooth_f32", logits.data_ptr(), _p(feats), _p(queue_feats), _p(queue_probs), rows, C, dim,
+              queue, float(alpha), float(T), int(bool(smooth)), float(thr), _p(work), probs_orig.data_ptr(),
+              probs.data_ptr(), mask.data_ptr(), _stream())
+    return probs_orig, probs, mask
+
+
+def graph_contrast(f_row, f_col, p1, p, T, grad_side, scale=1.0, want_grad=True):
+    """train.py:246-265 -> (scale*L, scale*dL/d(f_row|f_col))."""
+    for t, n in ((f_row, "f_row"), (f_col, "f_col"), (p1, "p1"), (p, "p")):
+        _chk(t, name=n)
+    n, dim = f_row.shape
+    C = p.shape[1]
+    work = torch.empty((3 * n * n,), dtype=_f32, device=f_row.device)
+    loss = torch.zeros((), dtype=_f32, device=f_row.device)
+    df = torch.empty_like(f_row) if want_grad else None
+    _lib.call("cmlpl_graph_contrast_f32", f_row.data_ptr(), f_col.data_ptr(), p1.data_ptr(), p.data_ptr(), n, dim, C,
+              float(T), int(grad_side), float(scale), work.data_ptr(), loss.data_ptr(), _p(df), _stream())
+    return loss, df
+
+
+def ntxent(z, bs, T, want_grad=True):
+    """models.py:22-39 on unit-norm rows z [2bs, dim] -> (L, dL/dz)."""
+    _chk(z, name="z")
+    n, dim = z.shape
+    assert n == 2 * bs
+    work = torch.empty((2 * n * n,), dtype=_f32, device=z.device)
+    loss = torch.zeros((), dtype=_f32, device=z.device)
+    dz = torch.empty_like(z) if want_grad else None
+    _lib.call("cmlpl_ntxent_f32", z.data_ptr(), bs, dim, float(T), work.data_ptr(), loss.data_ptr(), _p(dz), _stream())
+    return loss, dz
+
+
+def adam_multi(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+    """One fused Adam update over a list of tensors (grads entries may be None = skipped)."""
+    import ctypes
+    n = len(params)
+    PP = ctypes.c_void_p * n
+    LL = ctypes.c_int64 * n
+    for t in list(params) + list(exp_avg) + list(exp_avg_sq) + [g for g in grads if g is not None]:
+        _chk(t, name="adam tensor")
+    _lib.call("cmlpl_adam_multi_f32", n, PP(*[t.data_ptr() for t in params]),
+              PP(*[(g.data_ptr() if g is not None else None) for g in grads]),
+              PP(*[t.data_ptr() for t in exp_avg]), PP(*[t.data_ptr() for t in exp_avg_sq]),
+              LL(*[t.numel() for t in params]), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream())

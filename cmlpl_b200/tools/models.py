@@ -74,6 +74,26 @@ class _BaseNet2Fn(torch.autograd.Function):
         return None, None, dw0, db0, dw1, db1, dw2, db2, dws, dbs, dwc, dbc, None
 
 
+class ContrastiveLoss(nn.Module):
+    """models.py:14-39 (SimCLR NT-Xent over the [2bs, 2bs] cosine matrix) through cmlpl_ntxent_f32:
+    normalise -> similarity GEMM -> masked log-sum-exp, gradient in the same pass (never the
+    O(n^2 d) broadcast the reference allocates)."""
+
+    def __init__(self, batch_size, device='cuda', temperature=0.5):
+        super().__init__()
+        self.batch_size = batch_size
+        self.register_buffer("temperature", torch.tensor(temperature).to(device))
+        self.register_buffer("negatives_mask",
+                             (~torch.eye(batch_size * 2, batch_size * 2, dtype=bool).to(device)).float())
+        self._t = float(temperature)
+
+    def forward(self, emb_i, emb_j):
+        from ..losses import nt_xent
+        if emb_i.size(0) != self.batch_size:
+            raise ValueError("ContrastiveLoss was built for batch_size=%d" % self.batch_size)
+        return nt_xent(emb_i, emb_j, self._t)
+
+
 class Normalize(nn.Module):
     """models.py:81-90: x / ||x||_p along dim 1, no epsilon (power 2 only on device)."""
 

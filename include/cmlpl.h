@@ -158,6 +158,50 @@ int cmlpl_argmax_u8(const float* logits, int64_t n, int num_classes, uint8_t* la
 int cmlpl_confusion_i64(const uint8_t* pred, const int64_t* label, int64_t n, int num_classes,
                         int64_t* cm, cmlpl_stream_t stream);
 
+/* ------------------------------------------------------------------- losses --
+ * train.py:191-265 and tools/models.py:14-39.  All fp32, rows = samples; `loss` is a device
+ * scalar that is ACCUMULATED into (zero it first).
+ */
+/* Hard-label CE (train.py:191-192) or soft/masked CE (train.py:239-242):
+ *   loss_i = -sum_c log_softmax(z_i)_c * t_ic * m_i ;  *loss += scale * mean_i loss_i
+ *   dz_ic  = scale/rows * m_i * (softmax(z_i)_c * sum_c t_ic - t_ic)
+ * labels i64 [rows] (hard) XOR probs f32 [rows, C] (soft); mask f32 [rows] or NULL; dlogits may be NULL. */
+int cmlpl_ce_fwd_bwd_f32(const float* logits, const int64_t* labels, const float* probs,
+                         const float* mask, int64_t rows, int C, float scale,
+                         float* loss, float* dlogits, cmlpl_stream_t stream);
+
+/* train.py:203,213-215,220-222: probs_orig = softmax(logits); if smooth: A = exp(feats.Q^T/T)
+ * row-normalised, probs = alpha*probs_orig + (1-alpha)*A.Qp; mask = max(probs) >= thr.
+ * feats f32 [rows, dim], queue_feats f32 [queue, dim], queue_probs f32 [queue, C],
+ * work f32 [rows, queue] scratch (only when smooth).  probs_orig may be NULL. */
+int cmlpl_bank_smooth_f32(const float* logits, const float* feats, const float* queue_feats,
+                          const float* queue_probs, int64_t rows, int C, int dim, int64_t queue,
+                          float alpha, float T, int smooth, float thr, float* work,
+                          float* probs_orig, float* probs, float* mask, cmlpl_stream_t stream);
+
+/* train.py:246-265: pseudo-label-graph contrastive loss, forward + gradient.
+ * f_row, f_col f32 [n, dim]; p1 (rows), p (cols) f32 [n, C].
+ *   L = mean_i( -sum_j log(sp_ij) Q_ij + sum_j log(sp_ij + 1) Qn_ij ),  sp = row-softmax(f_row.f_col^T / T)
+ * grad_side 0 -> dfeat = scale*dL/df_row (loss_contrast, :260-262); 1 -> scale*dL/df_col (loss_contrast1,
+ * :263-265).  work f32 [3*n*n] scratch.  *loss += scale*L.  dfeat f32 [n, dim] may be NULL. */
+int cmlpl_graph_contrast_f32(const float* f_row, const float* f_col, const float* p1, const float* p,
+                             int64_t n, int dim, int C, float T, int grad_side, float scale,
+                             float* work, float* loss, float* dfeat, cmlpl_stream_t stream);
+
+/* tools/models.py:22-39 ContrastiveLoss (NT-Xent) on z = [normalize(emb_i); normalize(emb_j)]
+ * f32 [2*bs, dim] (unit rows; use cmlpl_l2norm_f32 / _bwd around it).  *loss += L;
+ * dz f32 [2*bs, dim] = dL/dz or NULL.  work f32 [2*(2bs)^2] scratch. */
+int cmlpl_ntxent_f32(const float* z, int64_t bs, int dim, float T, float* work, float* loss,
+                     float* dz, cmlpl_stream_t stream);
+
+/* torch.optim.Adam (train.py:131-132,268,272; default betas/eps) over a list of tensors, one launch
+ * per 16 tensors.  *_host are HOST arrays of n_tensors device pointers / element counts; step is the
+ * 1-based step count.  Tensors whose grad pointer is NULL are skipped (grad=None). */
+int cmlpl_adam_multi_f32(int n_tensors, float* const* p_host, const float* const* g_host,
+                         float* const* m_host, float* const* v_host, const int64_t* numel_host,
+                         float lr, float beta1, float beta2, float eps, int step,
+                         cmlpl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,7 @@ def replay_step(z, ti):
         ("xp_u1", XP_u.shape), ("x_u1", X_u.shape), ("xp_u2", XP_u.shape), ("x_u2", X_u.shape))}
     sa.thr = 0.1445
     inputs = dict(XP_l=XP_l, X_l=X_l, Y_l=Y_l, XP_u=XP_u, X_u=X_u, noise=nz, args=sa, sd=sd, sd1=sd1)
+    inputs["queues"] = [q.clone() for q in (st.queue_feats, st.queue_probs, st.queue_feats1, st.queue_probs1)]
     st.extras["inputs"] = inputs
     r = O.ref_step(st, XP_l, X_l, Y_l, XP_u, X_u, nz, epoch=1, batch_index=0, args=sa)
     return r, st
