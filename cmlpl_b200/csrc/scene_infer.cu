@@ -155,13 +155,10 @@ extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, 
   CMLPL_CHECK_ARG(band_row0 >= 0 && band_row0 + band_rows <= scene_rows, "conv0_map: band outside the scene");
   CMLPL_CHECK_ARG(reinterpret_cast<uintptr_t>(cube) % 16 == 0, "conv0_map: cube must be 16-byte aligned");
   // the slab must hold every (mirrored) source row of the band's halo
-  const int lo = window_lo(w);
-  int rmin = scene_rows, rmax = -1;
-  const int cand[4] = {band_row0 + lo, band_row0, band_row0 + band_rows - 1, band_row0 + band_rows - 1 + lo + w - 1};
-  for (int i = 0; i < 4; ++i) {
-    const int m = mirror_index(cand[i], scene_rows);
-    rmin = m < rmin ? m : rmin; rmax = m > rmax ? m : rmax;
-  }
+  const int a = band_row0 + window_lo(w), b = band_row0 + band_rows - 1 + window_lo(w) + w - 1;
+  int rmin = a < 0 ? 0 : a, rmax = b >= scene_rows ? scene_rows - 1 : b;
+  if (a < 0 && -a - 1 > rmax) rmax = -a - 1;                          // rows -1..a reflect to 0..-a-1
+  if (b >= scene_rows && 2 * scene_rows - 1 - b < rmin) rmin = 2 * scene_rows - 1 - b;
   CMLPL_CHECK_ARG(rmin >= slab_row0 && rmax < slab_row0 + slab_rows,
                   "conv0_map: slab rows [%d,%d) do not cover the band's halo [%d,%d]", slab_row0,
                   slab_row0 + slab_rows, rmin, rmax);

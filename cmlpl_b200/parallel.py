@@ -20,17 +20,19 @@ def band_of(rank: int, world: int, scene_rows: int):
     return r0, min(r0 + per, scene_rows)
 
 
-def _mirror(o, n):
-    return -o - 1 if o < 0 else (2 * n - 1 - o if o >= n else o)
-
-
 def slab_of(r0: int, r1: int, scene_rows: int, w: int):
-    """Cube rows [s0, s1) the band [r0, r1) reads (window rows r-w//2 .. r-w//2+w-1, mirrored)."""
+    """Cube rows [s0, s1) the band [r0, r1) reads: window rows r-w//2 .. r-w//2+w-1 of every band
+    row, mirrored at the true scene edges (single reflection)."""
     if r1 <= r0:
         return r0, r0
-    lo = -(w // 2)
-    cand = [_mirror(r0 + lo, scene_rows), r0, r1 - 1, _mirror(r1 - 1 + lo + w - 1, scene_rows)]
-    return min(cand), max(cand) + 1
+    R = scene_rows
+    a, b = r0 - (w // 2), r1 - 1 - (w // 2) + w - 1          # unmirrored range [a, b]
+    lo_v, hi_v = max(a, 0), min(b, R - 1)
+    if a < 0:
+        hi_v = max(hi_v, -a - 1)                               # rows -1..a reflect to 0..-a-1
+    if b >= R:
+        lo_v = min(lo_v, 2 * R - 1 - b)                        # rows R..b reflect to R-1..2R-1-b
+    return lo_v, hi_v + 1
 
 
 def gather_label_map(local_labels: torch.Tensor, scene_rows: int, cols: int, group=None) -> torch.Tensor:
