@@ -152,7 +152,7 @@ def workload_config(n_gpus, note=None):
            "pixels_per_step": R0 * C0 * n_gpus,
            "parallelism": f"row bands x{n_gpus} (weak: {R0} rows + halo per GPU, scene = {R0 * n_gpus} rows)",
            "l2_policy": "per-step working set (cube 50 MB + spectra 85 MB + conv0 map 29 MB + pooled features "
-                        "664 MB) exceeds the 126 MB L2; no explicit flush"}
+                        "664 MB + hidden features 425 MB) exceeds the 126 MB L2; no explicit flush"}
     if note:
         cfg["note"] = note
     return cfg
@@ -255,16 +255,18 @@ def main():
     # ---- per-kernel durations of the same step, CUDA events on the launching stream
     L = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
-    wsz = {k: None for k in ()}
     nb = r1 - r0
     f0_bytes = (nb + W0 - 1) * (C0 + W0 - 1) * 64 * 2
     al = lambda x: (x + 255) // 256 * 256
+    mtiles = (n_band + 127) // 128
+    kc_in = ((B0 + 15) // 16) * 2
+    # workspace carve-up of cmlpl_scene_infer's tensor-core path (csrc/scene_infer.cu::scene_ws)
     off_f0, off_p2 = 0, al(f0_bytes)
-    off_spe = off_p2 + al(n_band * 25 * 64 * 2)
-    off_hid = off_spe + al(n_band * K0 * 4)
+    off_x16 = off_p2 + al(mtiles * 128 * 25 * 64 * 2)
+    off_h16 = off_x16 + al(mtiles * kc_in * 2048)
+    assert off_h16 + al(mtiles * 128 * 2048) == ws.numel(), "bench stage offsets out of sync with scene_ws"
     base = ws.data_ptr()
-    chunk = min(n_band, 16384)
-    names = ["conv0_map", "spectral_head", "patch_cnn", "classify"]
+    names = ["conv0_map", "spectral_hidden", "patch_cnn", "head"]
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     for it in range(args.warmup + args.steps):
         e = ev[it - args.warmup] if it >= args.warmup else [None] * 5
@@ -272,12 +274,12 @@ def main():
         _lib.call("cmlpl_conv0_map_f16", slab.data_ptr(), scene_rows, C0, s0, s1 - s0, W0, r0, nb, packed.data_ptr(),
                   base + off_f0, st)
         if e[1]: e[1].record()
-        _lib.call("cmlpl_spectral_head_f32", spec.data_ptr(), n_band, B0, K0, W0, packed.data_ptr(), base + off_hid,
-                  chunk, base + off_spe, st)
+        _lib.call("cmlpl_spectral_hidden_tc", spec.data_ptr(), n_band, B0, K0, W0, packed.data_ptr(), base + off_x16,
+                  base + off_h16, st)
         if e[2]: e[2].record()
-        _lib.call("cmlpl_patch_cnn_f16", base + off_f0, C0, W0, nb, packed.data_ptr(), base + off_p2, st)
+        _lib.call("cmlpl_patch_cnn_f16_tiled", base + off_f0, C0, W0, nb, packed.data_ptr(), base + off_p2, st)
         if e[3]: e[3].record()
-        _lib.call("cmlpl_classify_f16", base + off_p2, base + off_spe, n_band, B0, K0, W0, packed.data_ptr(),
+        _lib.call("cmlpl_head_tc", base + off_p2, base + off_h16, n_band, B0, K0, W0, packed.data_ptr(),
                   labels.data_ptr(), None, st)
         if e[4]: e[4].record()
     torch.cuda.synchronize()
@@ -299,8 +301,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("patch_cnn_dram_bytes_per_launch")
-    n_spec_launch = 2 * ((n_band + chunk - 1) // chunk)
-    launches_per_step = 1 + n_spec_launch + 1 + 1 + (1 if world > 1 else 0)
+    # conv0_map, x16_tile, spectral_hidden, patch_cnn, head (+ confusion when sharded)
+    launches_per_step = 5 + (1 if world > 1 else 0)
     line = {
         "metric": "pixels/sec full-scene inference", "value": value, "unit": "pixels/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,

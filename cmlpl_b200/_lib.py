@@ -37,6 +37,9 @@ SIGNATURES = {
     "cmlpl_conv0_map_f16": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "cmlpl_patch_cnn_f16": (I, [P, I, I, I, P, P, P]),
     "cmlpl_debug_patch_cnn_trace": (I, [P, I, I, I, P, P, P, P]),
+    "cmlpl_patch_cnn_f16_tiled": (I, [P, I, I, I, P, P, P]),
+    "cmlpl_spectral_hidden_tc": (I, [P, L, I, I, I, P, P, P, P]),
+    "cmlpl_head_tc": (I, [P, P, L, I, I, I, P, P, P, P]),
     "cmlpl_spectral_head_f32": (I, [P, L, I, I, I, P, P, L, P, P]),
     "cmlpl_classify_f16": (I, [P, P, L, I, I, I, P, P, P, P]),
     "cmlpl_argmax_u8": (I, [P, L, I, P, P]),

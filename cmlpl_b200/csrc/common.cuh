@@ -73,9 +73,12 @@ struct PackedLayout {
   size_t bspe;    // f32 [1024]
   size_t wc_conv; // f32 [C][P*64]   classifier columns of the conv features, permuted to (pos, ch)
   size_t wc_spe;  // f32 [C][1024]
-  size_t bc;      // f32 [C]
+  size_t bc;      // f32 [C] (padded to 16)
+  size_t w1s;     // f16 [4 n-tiles][KC][256][8]  feat_spe weight, UMMA B operand tiles (K padded to 16)
+  size_t wc16;    // f16 [(P*8 + 128) k-chunks][16 classes][8]  classifier over [conv(pos,ch) | spectral]
   size_t total;
   int conv_pos;   // P = (w/4)^2 pooled positions
+  int kc_spe_in;  // KC = ceil(B/16)*2: 16-byte K-chunks of the spectral input
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -95,7 +98,10 @@ __host__ __device__ inline PackedLayout packed_layout(int B, int C, int w) {
   L.bspe = o; o = align256(o + 1024 * 4);
   L.wc_conv = o; o = align256(o + size_t(C) * L.conv_pos * 64 * 4);
   L.wc_spe = o; o = align256(o + size_t(C) * 1024 * 4);
-  L.bc = o; o = align256(o + size_t(C) * 4);
+  L.bc = o; o = align256(o + size_t(C > 16 ? C : 16) * 4);
+  L.kc_spe_in = ((B + 15) / 16) * 2;
+  L.w1s = o; o = align256(o + size_t(4) * L.kc_spe_in * 256 * 16);
+  L.wc16 = o; o = align256(o + size_t(L.conv_pos * 8 + 128) * 16 * 16);
   L.total = o;
   return L;
 }

@@ -35,7 +35,7 @@ __global__ void pack_kernel(PackArgs a) {
       float* bc = reinterpret_cast<float*>(o + a.L.bc);
       for (int64_t i = t0; i < 64; i += step) { b1[i] = a.c1b[i]; b2[i] = a.c2b[i]; b0[i] = a.c0b[i]; }
       for (int64_t i = t0; i < 1024; i += step) bs[i] = a.sb[i];
-      for (int64_t i = t0; i < a.C; i += step) bc[i] = a.cb[i];
+      for (int64_t i = t0; i < 16 || i < a.C; i += step) bc[i] = i < a.C ? a.cb[i] : 0.f;
     } break;
     case 3: {  // conv0 -> f32 [ci][n]
       float* d = reinterpret_cast<float*>(o + a.L.w0);
@@ -59,6 +59,28 @@ __global__ void pack_kernel(PackArgs a) {
       for (int64_t i = t0; i < int64_t(a.C) * 1024; i += step) {
         const int j = int(i & 1023), cls = int(i >> 10);
         ds[i] = a.cw[int64_t(cls) * in_f + 64 * P + j];
+      }
+    } break;
+    case 6: {  // feat_spe weight -> f16 [4][KC][256][8], zero for k >= B
+      __half* d = reinterpret_cast<__half*>(o + a.L.w1s);
+      const int KC = a.L.kc_spe_in;
+      for (int64_t i = t0; i < int64_t(4) * KC * 256 * 8; i += step) {
+        const int e = int(i & 7), r = int((i >> 3) & 255); const int64_t q = i >> 11; const int kc = int(q % KC), nt = int(q / KC);
+        const int k = kc * 8 + e, nrow = nt * 256 + r;
+        d[i] = __float2half_rn(k < a.B ? a.sw[int64_t(nrow) * a.B + k] : 0.f);
+      }
+    } break;
+    case 7: {  // classifier -> f16 [(P*8 + 128)][16][8]; K order = (pos, ch) then spectral j
+      __half* d = reinterpret_cast<__half*>(o + a.L.wc16);
+      const int P = a.P, in_f = 64 * P + 1024, kc_conv = P * 8;
+      for (int64_t i = t0; i < int64_t(kc_conv + 128) * 16 * 8; i += step) {
+        const int e = int(i & 7), cls = int((i >> 3) & 15), kc = int(i >> 7);
+        float v = 0.f;
+        if (cls < a.C) {
+          if (kc < kc_conv) { const int pos = kc >> 3, ch = (kc & 7) * 8 + e; v = a.cw[int64_t(cls) * in_f + ch * P + pos]; }
+          else { const int j = (kc - kc_conv) * 8 + e; v = a.cw[int64_t(cls) * in_f + 64 * P + j]; }
+        }
+        d[i] = __float2half_rn(v);
       }
     } break;
   }
@@ -89,7 +111,7 @@ extern "C" int cmlpl_pack_basenet2(const float* conv0_w, const float* conv0_b, c
   a.L = packed_layout(num_features, num_classes, w);
   a.P = a.L.conv_pos;
   a.out = static_cast<unsigned char*>(packed);
-  pack_kernel<<<dim3(64, 6), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  pack_kernel<<<dim3(64, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   CMLPL_CHECK_LAUNCH("pack_basenet2");
   return CMLPL_OK;
 }

@@ -20,6 +20,7 @@
 // two rows of every 2x2 pooling window land in the SAME TMEM lane of two accumulator tiles
 // and the two columns in adjacent lanes: pooling is one add + one shfl_xor in the epilogue.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace cmlpl {
 
@@ -69,102 +70,6 @@ struct PatchCfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-// ------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug must trap (kernel error), never hang the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-#pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 26); ++it)
-    if (mbar_try_wait(bar, parity)) return;
-  printf("patch_cnn: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-  __trap();
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// 1-D bulk async copy global -> shared (UBLKCP); completes `bytes` transaction bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, M=128 N=64 K=16, fp16 in / fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major (cute/arch/mma_sm100_desc.hpp):
-//   [0,14) start>>4 | [16,30) LBO>>4 (stride between the two 16-B K-chunks of one MMA)
-//   [32,46) SBO>>4 (stride between 8-row groups) | [46,48) version=1 | [61,64) layout=0
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) |
-         (uint64_t(1) << 46);
-}
-// instruction descriptor kind::f16: c=f32 (bit4), a=b=f16 (0), K-major both, N>>3 @17, M>>4 @24
-constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(64 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
-
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // One 128-row accumulator tile of a 3x3 convolution: 9 taps x 4 K-steps = 36 tcgen05.mma with
 // compile-time descriptor offsets (everything but the two base words is an immediate, so the
 // operands stay in uniform registers and the single issuing lane runs back-to-back UTCHMMA).
@@ -210,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
                  const unsigned char* __restrict__ packed_w1, const unsigned char* __restrict__ packed_w2,
                  const float* __restrict__ b1g, const float* __restrict__ b2g, __half* __restrict__ p2out,
-                 long long* __restrict__ trace) {
+                 int p2_tiled, long long* __restrict__ trace) {
   using Cfg = PatchCfg<W>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -456,7 +361,11 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
             ro[k] = *reinterpret_cast<const uint4*>(rO + k * Cfg::CH2);
           }
         }
-        __half* dst = p2out + (p * Cfg::P + (i * (Cfg::H2 / 2) + (x >> 1))) * 64 + chalf * 32;
+        // row-major [pixel][pos][64]  or  UMMA A-operand tiles [pixel/128][pos*8 + chunk][pixel%128][8]
+        const int pos = i * (Cfg::H2 / 2) + (x >> 1);
+        __half* dst = p2_tiled ? p2out + (((p >> 7) * (Cfg::P * 8) + pos * 8 + chalf * 4) * 128 + (p & 127)) * 8
+                               : p2out + (p * Cfg::P + pos) * 64 + chalf * 32;
+        const int dstep = p2_tiled ? 128 : 1;                  // uint4 stride between consecutive 8-channel chunks
         if (tid == 0) CMLPL_TRACE(10);
         mbar_wait(bars + 8 * BAR_C2_FULL, ph, 8);
         if (tid == 0) CMLPL_TRACE(11);
@@ -468,14 +377,14 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64, o);
         tmem_ld_wait();
         pool16(e, o, &re[0], &ro[0], bias2, w0, w1);
-        if (writer) { __stcs(d4, w0); __stcs(d4 + 1, w1); }
+        if (writer) { __stcs(d4, w0); __stcs(d4 + dstep, w1); }
         tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64 + 16, e);
         tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64 + 16, o);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bars + 8 * BAR_C2_EMPTY);
         pool16(e, o, &re[2], &ro[2], bias2 + 16, w0, w1);
-        if (writer) { __stcs(d4 + 2, w0); __stcs(d4 + 3, w1); }
+        if (writer) { __stcs(d4 + 2 * dstep, w0); __stcs(d4 + 3 * dstep, w1); }
       }
       if (tid == 0) CMLPL_TRACE(12);
       // A2 is rewritten by the next patch's conv1 epilogue: all residual reads must be done
@@ -497,7 +406,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
 using namespace cmlpl;
 
 static int launch_patch_cnn(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
-                            long long* trace, int grid_override, cudaStream_t stream) {
+                            int p2_tiled, long long* trace, int grid_override, cudaStream_t stream) {
   CMLPL_CHECK_ARG(f0pad && packed && p2, "patch_cnn: null pointer");
   CMLPL_CHECK_ARG(w == 20, "patch_cnn: w=%d unsupported (BaseNet2's classifier fixes w=20, tools/models.py:127)", w);
   CMLPL_CHECK_ARG(cols > 0 && band_rows > 0, "patch_cnn: bad dims");
@@ -514,19 +423,25 @@ static int launch_patch_cnn(const void* f0pad, int cols, int w, int band_rows, c
   kern<<<int(grid), kThreads, Cfg::SMEM, stream>>>(
       static_cast<const __half*>(f0pad), cols, band_rows, pk + L.w1, pk + L.w2,
       reinterpret_cast<const float*>(pk + L.b1), reinterpret_cast<const float*>(pk + L.b2),
-      static_cast<__half*>(p2), trace);
+      static_cast<__half*>(p2), p2_tiled, trace);
   CMLPL_CHECK_LAUNCH("patch_cnn");
   return CMLPL_OK;
 }
 
 extern "C" int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
                                    cmlpl_stream_t stream) {
-  return launch_patch_cnn(f0pad, cols, w, band_rows, packed, p2, nullptr, 0, static_cast<cudaStream_t>(stream));
+  return launch_patch_cnn(f0pad, cols, w, band_rows, packed, p2, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+// Same, writing the pooled features as UMMA A-operand tiles [ceil(n/128)][P*8][128][8] for cmlpl_head_tc.
+extern "C" int cmlpl_patch_cnn_f16_tiled(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                                         void* p2t, cmlpl_stream_t stream) {
+  return launch_patch_cnn(f0pad, cols, w, band_rows, packed, p2t, 1, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 // Diagnostics: same kernel, CTA 0 writes clock64() stamps of its first 64 patches to trace[64][16].
 extern "C" int cmlpl_debug_patch_cnn_trace(const void* f0pad, int cols, int w, int band_rows, const void* packed,
                                            void* p2, long long* trace, cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(trace, "patch_cnn_trace: null trace buffer");
-  return launch_patch_cnn(f0pad, cols, w, band_rows, packed, p2, trace, 0, static_cast<cudaStream_t>(stream));
+  return launch_patch_cnn(f0pad, cols, w, band_rows, packed, p2, 0, trace, 0, static_cast<cudaStream_t>(stream));
 }

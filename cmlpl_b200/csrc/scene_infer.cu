@@ -118,20 +118,33 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int64_t n, int C
   }
 }
 
+// Tensor-core head (head_sm100.cu) applies for <= 16 classes and <= 208 bands; otherwise the
+// CUDA-core spectral_head + classify kernels above run (same C ABI, same results contract).
+static bool use_tc_head(int B, int C) { return C <= 16 && ((B + 15) / 16) * 2 <= 26; }
+
 struct SceneWs {
-  size_t f0pad, p2, spe, hidden, total;
+  size_t f0pad, p2, spe, hidden, x16, h16, total;
   int64_t chunk;
+  bool tc;
 };
-static SceneWs scene_ws(int band_rows, int cols, int C, int w) {
+static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   SceneWs s;
   const int64_t n = int64_t(band_rows) * cols;
+  const int64_t mtiles = (n + 127) / 128;
   const int P = ((w / 2) / 2) * ((w / 2) / 2);
+  s.tc = use_tc_head(B, C);
   size_t o = 0;
   s.f0pad = o; o = align256(o + size_t(band_rows + w - 1) * (cols + w - 1) * 64 * 2);
-  s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);
-  s.spe = o; o = align256(o + size_t(n) * C * 4);
+  s.p2 = o; o = align256(o + size_t(s.tc ? mtiles * 128 : n) * P * 64 * 2);
+  s.spe = s.hidden = s.x16 = s.h16 = 0;
   s.chunk = n < 16384 ? n : 16384;
-  s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);
+  if (s.tc) {
+    s.x16 = o; o = align256(o + size_t(mtiles) * (((B + 15) / 16) * 2) * 2048);
+    s.h16 = o; o = align256(o + size_t(mtiles) * 128 * 2048);
+  } else {
+    s.spe = o; o = align256(o + size_t(n) * C * 4);
+    s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);
+  }
   s.total = o;
   return s;
 }
@@ -141,9 +154,8 @@ static SceneWs scene_ws(int band_rows, int cols, int C, int w) {
 using namespace cmlpl;
 
 extern "C" size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w) {
-  (void)num_features;
-  if (band_rows <= 0 || cols <= 0 || num_classes <= 0 || w < 4) return 0;
-  return scene_ws(band_rows, cols, num_classes, w).total;
+  if (band_rows <= 0 || cols <= 0 || num_classes <= 0 || num_features <= 0 || w < 4) return 0;
+  return scene_ws(band_rows, cols, num_features, num_classes, w).total;
 }
 
 extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows, int w,
@@ -248,7 +260,7 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
   CMLPL_CHECK_ARG(w == 20, "scene_infer: w=%d unsupported (the reference classifier is hard-wired to 2624 inputs, "
                   "tools/models.py:127, i.e. w=20)", w);
   CMLPL_CHECK_ARG(band_rows > 0 && cols > 0 && num_classes > 0 && num_classes <= 32, "scene_infer: bad dims");
-  const SceneWs ws = scene_ws(band_rows, cols, num_classes, w);
+  const SceneWs ws = scene_ws(band_rows, cols, num_features, num_classes, w);
   CMLPL_CHECK_ARG(workspace_bytes >= ws.total, "scene_infer: workspace %zu < required %zu", workspace_bytes, ws.total);
   CMLPL_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "scene_infer: workspace must be 256-byte aligned");
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
@@ -256,6 +268,13 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
   int rc = cmlpl_conv0_map_f16(cube, scene_rows, cols, slab_row0, slab_rows, w, band_row0, band_rows, packed,
                                wsb + ws.f0pad, stream);
   if (rc != CMLPL_OK) return rc;
+  if (ws.tc) {
+    rc = cmlpl_spectral_hidden_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16, wsb + ws.h16, stream);
+    if (rc != CMLPL_OK) return rc;
+    rc = cmlpl_patch_cnn_f16_tiled(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.p2, stream);
+    if (rc != CMLPL_OK) return rc;
+    return cmlpl_head_tc(wsb + ws.p2, wsb + ws.h16, n, num_features, num_classes, w, packed, labels, logits, stream);
+  }
   rc = cmlpl_spectral_head_f32(spectra, n, num_features, num_classes, w, packed,
                                reinterpret_cast<float*>(wsb + ws.hidden), ws.chunk,
                                reinterpret_cast<float*>(wsb + ws.spe), stream);

@@ -142,6 +142,17 @@ int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_features, i
 int cmlpl_classify_f16(const void* p2, const float* spe_logits /* may be NULL */, int64_t n,
                        int num_features, int num_classes, int w, const void* packed,
                        uint8_t* labels, float* logits /* may be NULL */, cmlpl_stream_t stream);
+/* Tensor-core head (<= 16 classes, <= 208 bands), fp16 operands / fp32 accumulate.  A operands are
+ * "UMMA tiles": f16 [ceil(n/128)][K/8][128 rows][8], pixel p = tile p/128, row p%128.
+ *   cmlpl_patch_cnn_f16_tiled : as cmlpl_patch_cnn_f16 but p2t is tiled with K = (w/4)^2*64 (pos, ch)
+ *   cmlpl_spectral_hidden_tc  : x16 (scratch, K = B padded to 16) and h16 = relu(feat_spe(x)) tiles, K = 1024
+ *   cmlpl_head_tc             : classifier over [p2t | h16] + bias, argmax -> labels (and logits) */
+int cmlpl_patch_cnn_f16_tiled(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                              void* p2t, cmlpl_stream_t stream);
+int cmlpl_spectral_hidden_tc(const float* spectra, int64_t n, int num_features, int num_classes, int w,
+                             const void* packed, void* x16, void* h16, cmlpl_stream_t stream);
+int cmlpl_head_tc(const void* p2t, const void* h16, int64_t n, int num_features, int num_classes, int w,
+                  const void* packed, uint8_t* labels, float* logits, cmlpl_stream_t stream);
 /* Diagnostics: cmlpl_patch_cnn_f16 with CTA 0 writing clock64() stamps of its first 64 patches
  * (16 slots each: loader / MMA issuer / epilogue protocol points) to trace i64 [64,16]. */
 int cmlpl_debug_patch_cnn_trace(const void* f0pad, int cols, int w, int band_rows, const void* packed,
