@@ -63,7 +63,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // ---- packed BaseNet2 weights (layout shared by pack.cu and the scene kernels) ----
 // All offsets in bytes from the start of the packed buffer, 256-B aligned.
 struct PackedLayout {
-  size_t w1;      // f16 [9 taps][8 kchunks][64 n][8]   conv1, UMMA no-swizzle K-major B operand
+  size_t w1;      // f16 [3 dx][8 kchunks][192 rows = (2-dy)*64+n][8]   conv1, UMMA no-swizzle K-major B operand
   size_t w2;      // f16 same for conv2
   size_t b1;      // f32 [64]
   size_t b2;      // f32 [64]

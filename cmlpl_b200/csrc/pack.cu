@@ -18,13 +18,15 @@ __global__ void pack_kernel(PackArgs a) {
   unsigned char* o = a.out;
   switch (seg) {
     case 0:
-    case 1: {  // conv1 / conv2 -> f16 [tap][kc][n][8]   (UMMA no-swizzle K-major B operand)
+    case 1: {  // conv1 / conv2 -> f16 [dx][kc][192 rows = (2-dy)*64 + n][8]  (UMMA no-swizzle K-major B operand;
+               // rows ordered W(dy=2), W(dy=1), W(dy=0) so that tap pairs are contiguous N=128 blocks)
       const float* w = seg == 0 ? a.c1w : a.c2w;
       __half* d = reinterpret_cast<__half*>(o + (seg == 0 ? a.L.w1 : a.L.w2));
-      for (int64_t i = t0; i < 9 * 8 * 64 * 8; i += step) {
-        const int e = int(i & 7), n = int((i >> 3) & 63), kc = int((i >> 9) & 7), tap = int(i >> 12);
-        const int ci = kc * 8 + e;
-        d[i] = __float2half_rn(w[(int64_t(n) * 64 + ci) * 9 + tap]);
+      for (int64_t i = t0; i < 3 * 8 * 192 * 8; i += step) {
+        const int e = int(i & 7); const int64_t q = i >> 3; const int r = int(q % 192); const int kc = int((q / 192) & 7);
+        const int dx = int(q / (192 * 8));
+        const int dy = 2 - r / 64, n = r % 64, ci = kc * 8 + e;
+        d[i] = __float2half_rn(w[(int64_t(n) * 64 + ci) * 9 + dy * 3 + dx]);
       }
     } break;
     case 2: {  // biases

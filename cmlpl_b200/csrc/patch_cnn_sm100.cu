@@ -15,8 +15,8 @@
 // K-major" canonical layout with SBO = 128 B, i.e. for every 16-byte K-chunk (8 channels) a
 // *linear* array of positions, 16 B apart.  A 3x3 tap is then nothing but a different start
 // address of the A descriptor (row-major positions with a zero-padded border), so the nine
-// taps x four K-steps of a tile are 36 back-to-back tcgen05.mma (M=128, N=64, K=16) on the
-// same buffer.  Rows are split by parity into two planes (even rows / odd rows) so that the
+// taps x four K-steps of a tile are back-to-back tcgen05.mma (M=128, K=16) on the same buffer
+// (taps that read the same rows for the even- and odd-row tile are fused into N=128 MMAs).  Rows are split by parity into two planes (even rows / odd rows) so that the
 // two rows of every 2x2 pooling window land in the SAME TMEM lane of two accumulator tiles
 // and the two columns in adjacent lanes: pooling is one add + one shfl_xor in the epilogue.
 #include "common.cuh"
@@ -70,29 +70,40 @@ struct PatchCfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-// One 128-row accumulator tile of a 3x3 convolution: 9 taps x 4 K-steps = 36 tcgen05.mma with
-// compile-time descriptor offsets (everything but the two base words is an immediate, so the
-// operands stay in uniform registers and the single issuing lane runs back-to-back UTCHMMA).
-//   Q      parity of the output rows of this tile
-//   PWX    padded row width (entries), CHX bytes between K-chunks, PLANEX bytes per parity plane
-//   a_lo   low descriptor word of (even plane, entry 1 + first output row of the tile)
-//   b_lo   low descriptor word of the weights (tap 0, K-step 0)
-template <int Q, int PWX, int CHX, int PLANEX>
-__device__ __forceinline__ void issue_conv_tile(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo) {
+// One PAIR of 128-row accumulator tiles (even-row tile at d_tmem, odd-row tile at d_tmem + 64) of a
+// 3x3 convolution.  tcgen05.mma costs ~64 cycles whether N is 64 or 128 (measured,
+// scripts/micro/mma_rate.cu), so taps are grouped by the A operand they read:
+//   A = (even plane, row i  , dx): feeds dy=1 of the even tile AND dy=0 of the odd tile -> one N=128 MMA
+//   A = (odd  plane, row i+1, dx): feeds dy=2 of the even tile AND dy=1 of the odd tile -> one N=128 MMA
+//   A = (odd  plane, row i  , dx): dy=0 of the even tile only (N=64)
+//   A = (even plane, row i+1, dx): dy=2 of the odd tile only  (N=64)
+// (row tables: even outputs y=2i read rows 2i-1, 2i, 2i+1 = odd-plane row i, even-plane row i,
+//  odd-plane row i+1; odd outputs y=2i+1 read even-plane row i, odd-plane row i+1, even-plane row i+1.)
+// The weights are packed per dx as 192 rows [W(dy=2); W(dy=1); W(dy=0)] x K, so [W2;W1] is rows 0..127,
+// [W1;W0] rows 64..191 and the singles are rows 0..63 / 128..191 of the same block: 48 MMAs per pair
+// instead of 72, all descriptor offsets immediates.
+//   PWX padded row width (entries), CHX bytes between K-chunks, PLANEX bytes per parity plane
+//   a_lo low descriptor word of (even plane, entry 1 + first output row of the tile)
+//   b_lo low descriptor word of the weight block of dx = 0 (LBO = 192 rows * 16 B)
+constexpr int kWRows = 192, kWLbo = kWRows * 16, kWDxBytes = 8 * kWLbo;
+template <int PWX, int CHX, int PLANEX>
+__device__ __forceinline__ void issue_conv_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo) {
   constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;   // SBO = 128 B, version 1
+  constexpr uint32_t kI128 = make_idesc_f16(128, 128), kI64 = make_idesc_f16(128, 64);
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3, dx = tap % 3;
-    // even outputs (y=2i): dy=0 -> odd plane row i, dy=1 -> even plane row i, dy=2 -> odd plane row i+1
-    // odd outputs (y=2i+1): dy=0 -> even plane row i, dy=1 -> odd plane row i+1, dy=2 -> even plane row i+1
-    const int plane = (Q == 0) ? (dy == 1 ? 0 : 1) : (dy == 1 ? 1 : 0);
-    const int roff = (Q == 0) ? (dy == 2 ? 1 : 0) : (dy == 0 ? 0 : 1);
-    const int a_off = plane * PLANEX + (roff * PWX + dx - 1) * 16;
+  for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t da = kHi | uint64_t(a_lo + uint32_t((a_off + ks * 2 * CHX) / 16));
-      const uint64_t db = kHi | uint64_t(b_lo + uint32_t((tap * 8192 + ks * 2048) / 16));
-      umma_f16(d_tmem, da, db, kIdesc, (tap | ks) != 0 ? 1u : 0u);
+      const int col = (dx - 1) * 16 + ks * 2 * CHX;
+      const uint64_t aE0 = kHi | uint64_t(a_lo + uint32_t(col / 16));
+      const uint64_t aE1 = kHi | uint64_t(a_lo + uint32_t((PWX * 16 + col) / 16));
+      const uint64_t aO0 = kHi | uint64_t(a_lo + uint32_t((PLANEX + col) / 16));
+      const uint64_t aO1 = kHi | uint64_t(a_lo + uint32_t((PLANEX + PWX * 16 + col) / 16));
+      const uint32_t b = b_lo + uint32_t((dx * kWDxBytes + ks * 2 * kWLbo) / 16);
+      umma_f16(d_tmem, aE0, kHi | uint64_t(b + 64), kI128, (dx | ks) != 0 ? 1u : 0u);   // [W1;W0] -> even|odd
+      umma_f16(d_tmem, aO1, kHi | uint64_t(b), kI128, 1u);                               // [W2;W1] -> even|odd
+      umma_f16(d_tmem, aO0, kHi | uint64_t(b + 128), kI64, 1u);                          // W0 -> even
+      umma_f16(d_tmem + 64, aE1, kHi | uint64_t(b), kI64, 1u);                           // W2 -> odd
     }
   }
 }
@@ -209,8 +220,8 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
     if (tmem != 0) { printf("patch_cnn: unexpected TMEM base %u\n", tmem); __trap(); }
     const uint32_t a1_lo = ((sbase + Cfg::S_A1 + 16) >> 4) | (uint32_t(Cfg::CH1 >> 4) << 16);
     const uint32_t a2_lo = ((sbase + Cfg::S_A2 + 16) >> 4) | (uint32_t(Cfg::CH2 >> 4) << 16);
-    const uint32_t w1_lo = ((sbase + Cfg::S_W1) >> 4) | (uint32_t(1024 >> 4) << 16);
-    const uint32_t w2_lo = ((sbase + Cfg::S_W2) >> 4) | (uint32_t(1024 >> 4) << 16);
+    const uint32_t w1_lo = ((sbase + Cfg::S_W1) >> 4) | (uint32_t(kWLbo >> 4) << 16);
+    const uint32_t w2_lo = ((sbase + Cfg::S_W2) >> 4) | (uint32_t(kWLbo >> 4) << 16);
     uint32_t ph = 0;
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
       mbar_wait(bars + 8 * BAR_A1_FULL, ph, 2);
@@ -221,8 +232,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         mbar_wait(bars + 8 * (BAR_C1_EMPTY0 + h), ph ^ 1, 3);     // epilogue drained this half (prev patch)
         tc_fence_after();
         if (elect_one_sync()) {
-          issue_conv_tile<0, Cfg::PW1, Cfg::CH1, Cfg::PLANE1>(Cfg::TM_C1 + (h * 2 + 0) * 64, a1_lo + h * 128, w1_lo);
-          issue_conv_tile<1, Cfg::PW1, Cfg::CH1, Cfg::PLANE1>(Cfg::TM_C1 + (h * 2 + 1) * 64, a1_lo + h * 128, w1_lo);
+          issue_conv_pair<Cfg::PW1, Cfg::CH1, Cfg::PLANE1>(Cfg::TM_C1 + h * 128, a1_lo + h * 128, w1_lo);
           umma_commit(bars + 8 * (BAR_C1_FULL0 + h));
           if (h == Cfg::NT1 - 1) umma_commit(bars + 8 * BAR_A1_EMPTY);   // every conv1 read of A1 has completed
         }
@@ -235,8 +245,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
       tc_fence_after();
       if (lane == 0) CMLPL_TRACE(4);
       if (elect_one_sync()) {
-        issue_conv_tile<0, Cfg::PW2, Cfg::CH2, Cfg::PLANE2>(Cfg::TM_C2, a2_lo, w2_lo);
-        issue_conv_tile<1, Cfg::PW2, Cfg::CH2, Cfg::PLANE2>(Cfg::TM_C2 + 64, a2_lo, w2_lo);
+        issue_conv_pair<Cfg::PW2, Cfg::CH2, Cfg::PLANE2>(Cfg::TM_C2, a2_lo, w2_lo);
         umma_commit(bars + 8 * BAR_C2_FULL);
       }
       __syncwarp();
