@@ -286,6 +286,30 @@ def main():
     clocks = sampler.stop()
     stage_ms = {names[i]: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in ev])) for i in range(4)}
 
+    # ---- the HBM-bound kernel of the path: materialising patch gather (training batches / ExtractPatches)
+    gather = None
+    if world == 1:
+        ng = 16384
+        gout = torch.empty((ng, 60, W0, W0), dtype=torch.float32, device=dev)
+        gres = {}
+        for gname, gidx in (("contiguous", torch.arange(50000, 50000 + ng, device=dev)),
+                            ("random", torch.randperm(n_band, device=dev)[:ng].contiguous())):
+            for _ in range(3):
+                ops.patch_gather(slab, W0, idx=gidx, out=gout)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            g0.record()
+            for _ in range(10):
+                ops.patch_gather(slab, W0, idx=gidx, out=gout)
+            g1.record()
+            torch.cuda.synchronize()
+            gres[gname] = g0.elapsed_time(g1) / 10
+        gms = gres["contiguous"]
+        gather = {"kernel": "patch_gather_reg_kernel (16384 raster-consecutive pixels = ExtractPatches over scene rows, "
+                            "60x20x20 f32 each; output 1.57 GB > L2)",
+                  "bound": "hbm", "ms": gms, "bytes_per_pixel": 96240, "ms_random_pixels": gres["random"]}
+        del gout
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -324,6 +348,13 @@ def main():
                      "whole_step_algorithmic_tflops": px_step / world * FLOP_PER_PX_ALL / (ms_dev / 1e3) / 1e12},
         "host_prep_s": t_data,
     }
+    if gather is not None:
+        gather["achieved"] = 16384 * 96240 / (gather["ms"] / 1e3) / 1e9
+        gather["peak"] = peaks["hbm"]
+        gather["unit"] = "GB/s"
+        gather["frac"] = gather["achieved"] / peaks["hbm"]
+        gather["frac_random_pixels"] = 16384 * 96240 / (gather["ms_random_pixels"] / 1e3) / 1e9 / peaks["hbm"]
+        line["aux_roofline"] = gather
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cmlpl_oracle as O      # cpu_baseline leg: the oracle port is the thing timed here
         torch.manual_seed(1088)
