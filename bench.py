@@ -310,6 +310,38 @@ def main():
                   "bound": "hbm", "ms": gms, "bytes_per_pixel": 96240, "ms_random_pixels": gres["random"]}
         del gout
 
+    # ---- second half of the BASELINE metric: one mutual-learning train step (train.py:149-278), 128+128
+    train_ms = None
+    if world == 1:
+        import argparse as _ap
+        from cmlpl_b200 import train as T
+        targs = _ap.Namespace(temperature=0.3, thr=1.0, num_epochs=20, queue_batch=17, alpha=0.95, lr=5e-4,
+                              labeled_batch_size=128, dropout=0.8, noise=0.5)
+        tst = T.make_state(B0, K0, targs, dev)
+        lab_idx = torch.nonzero(truth >= 0).flatten()
+        def train_step(i):
+            li = lab_idx[torch.randint(0, lab_idx.numel(), (128,), device=dev)]
+            ui = lab_idx[torch.randint(0, lab_idx.numel(), (128,), device=dev)]
+            both = torch.cat([li, ui])
+            def batch():
+                z = torch.randn((256, 60, W0, W0), device=dev)
+                xp = ops.patch_gather(slab, W0, idx=both, noise=z, noise_scale=0.5)      # train.py:157,170 fused
+                xs = spec[both] + torch.randn((256, B0), device=dev) * 0.5              # train.py:158,171
+                return xp, xs
+            xb, sb = batch()
+            xe, se = batch()
+            T.mutual_step(tst, xb, sb, xe, se, truth[li], 1, i, targs)
+        for i in range(3):
+            train_step(i)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0e.record()
+        for i in range(10):
+            train_step(3 + i)
+        t1e.record()
+        torch.cuda.synchronize()
+        train_ms = t0e.elapsed_time(t1e) / 10
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,6 +379,9 @@ def main():
                      "kernel_ms": cnn_ms, "stage_ms": stage_ms,
                      "whole_step_algorithmic_tflops": px_step / world * FLOP_PER_PX_ALL / (ms_dev / 1e3) / 1e12},
         "host_prep_s": t_data,
+        "train_step_ms": train_ms,
+        "train_step_config": "BaseNet2 x2 mutual-learning step (train.py:149-278), 128 labelled + 128 unlabelled, "
+                             "dropout 0.8, noise 0.5 from the device generator, smoothing branch on; fp32 kernels",
     }
     if gather is not None:
         gather["achieved"] = 16384 * 96240 / (gather["ms"] / 1e3) / 1e9

@@ -6,7 +6,7 @@
 using namespace cmlpl;
 namespace cmlpl { void set_error(const char*, ...) {} int sm_count() { return 148; } }
 
-template <int N>
+template <int N, int M = 128>
 __global__ void __launch_bounds__(128, 1) k(long long* out, int iters, int a_step, int concurrent_lsu) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int iters, int a_ste
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const uint32_t off = uint32_t((i % 16) * a_step) >> 4;
-      umma_f16(0, kHi | (a_lo + off), kHi | (b_lo + ((i % 8) * 512 >> 4)), make_idesc_f16(128, N), 1);
+      umma_f16(0, kHi | (a_lo + off), kHi | (b_lo + ((i % 8) * 512 >> 4)), make_idesc_f16(M, N), 1);
     }
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0, 99);
@@ -44,15 +44,15 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int iters, int a_ste
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
-template <int N> void run(long long* d, int a_step, int lsu) {
+template <int N, int M = 128> void run(long long* d, int a_step, int lsu) {
   const int iters = 2000;
-  cudaFuncSetAttribute(k<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k<N><<<148, 128, 200 * 1024>>>(d, iters, a_step, lsu);
+  cudaFuncSetAttribute(k<N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k<N, M><<<148, 128, 200 * 1024>>>(d, iters, a_step, lsu);
   cudaDeviceSynchronize();
-  k<N><<<148, 128, 200 * 1024>>>(d, iters, a_step, lsu);
+  k<N, M><<<148, 128, 200 * 1024>>>(d, iters, a_step, lsu);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-  printf("N=%3d a_step=%5d lsu=%5d : %.1f cycles/MMA  (%s)\n", N, a_step, lsu, double(h) / iters, cudaGetErrorString(e));
+  printf("M=%3d N=%3d a_step=%5d lsu=%5d : %.1f cycles/MMA  (%s)\n", M, N, a_step, lsu, double(h) / iters, cudaGetErrorString(e));
 }
 int main() {
   long long* d; cudaMalloc(&d, 64);
@@ -60,5 +60,6 @@ int main() {
     run<64>(d, a_step, 0); run<128>(d, a_step, 0); run<192>(d, a_step, 0); run<256>(d, a_step, 0);
   }
   run<64>(d, 2048, 20000); run<192>(d, 2048, 20000);
+  run<64, 64>(d, 2048, 0); run<128, 64>(d, 2048, 0); run<256, 64>(d, 2048, 0); run<32, 128>(d, 2048, 0); run<16, 128>(d, 2048, 0);
   return 0;
 }
