@@ -26,9 +26,10 @@ __global__ void ce_kernel(const float* __restrict__ z, const int64_t* __restrict
     const float g = scale / float(rows);
     if (labels) {
       const int y = int(labels[r]);
-      li = -(zr[y] - lse) * m;
+      const bool ok = y >= 0 && y < C;                       // e.g. ignore_index 255 with mask 0
+      li = ok ? -(zr[y] - lse) * m : 0.f;
       if (dz)
-        for (int c = 0; c < C; ++c) dz[r * C + c] = g * m * (expf(zr[c] - lse) - (c == y ? 1.f : 0.f));
+        for (int c = 0; c < C; ++c) dz[r * C + c] = ok ? g * m * (expf(zr[c] - lse) - (c == y ? 1.f : 0.f)) : 0.f;
     } else {
       const float* pr = probs + r * C;
       float tsum = 0.f, dot = 0.f;
@@ -46,6 +47,21 @@ __global__ void ce_kernel(const float* __restrict__ z, const int64_t* __restrict
     v = warp_sum(v);
     if (threadIdx.x == 0) atomicAdd(loss, v * scale / float(rows));
   }
+}
+
+// ---------------------------------------------------------------- softmax entropy (loss_helper.py:247-248)
+// entropy_i = -sum_c p_ic * log(p_ic + eps),  p = softmax(z_i); one thread per row
+__global__ void softmax_entropy_kernel(const float* __restrict__ z, int64_t rows, int C, float eps, float* __restrict__ ent) {
+  const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  const float* zr = z + r * C;
+  float mx = -INFINITY;
+  for (int c = 0; c < C; ++c) mx = fmaxf(mx, zr[c]);
+  float se = 0.f;
+  for (int c = 0; c < C; ++c) se += expf(zr[c] - mx);
+  float e = 0.f;
+  for (int c = 0; c < C; ++c) { const float p = expf(zr[c] - mx) / se; e -= p * logf(p + eps); }
+  ent[r] = e;
 }
 
 // ---------------------------------------------------------------- memory-bank smoothing (train.py:203-222)
@@ -204,6 +220,15 @@ extern "C" int cmlpl_ce_fwd_bwd_f32(const float* logits, const int64_t* labels, 
   ce_kernel<<<int((rows + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, probs, mask, rows, C,
                                                                                     scale, loss, dlogits);
   CMLPL_CHECK_LAUNCH("ce");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_softmax_entropy_f32(const float* logits, int64_t rows, int C, float eps, float* entropy,
+                                         cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(logits && entropy && rows >= 0 && C > 0, "softmax_entropy: bad args");
+  if (rows == 0) return CMLPL_OK;
+  softmax_entropy_kernel<<<int((rows + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, rows, C, eps, entropy);
+  CMLPL_CHECK_LAUNCH("softmax_entropy");
   return CMLPL_OK;
 }
 

@@ -298,3 +298,12 @@ def adam_multi(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
               PP(*[(g.data_ptr() if g is not None else None) for g in grads]),
               PP(*[t.data_ptr() for t in exp_avg]), PP(*[t.data_ptr() for t in exp_avg_sq]),
               LL(*[t.numel() for t in params]), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream())
+
+
+def softmax_entropy(logits, eps=1e-10):
+    """loss_helper.py:247-248 -> f32 [rows]."""
+    _chk(logits, name="logits")
+    rows, C = logits.shape
+    ent = torch.empty((rows,), dtype=_f32, device=logits.device)
+    _lib.call("cmlpl_softmax_entropy_f32", logits.data_ptr(), rows, C, float(eps), ent.data_ptr(), _stream())
+    return ent

@@ -181,6 +181,10 @@ int cmlpl_ce_fwd_bwd_f32(const float* logits, const int64_t* labels, const float
                          const float* mask, int64_t rows, int C, float scale,
                          float* loss, float* dlogits, cmlpl_stream_t stream);
 
+/* loss_helper.py:247-248: entropy_i = -sum_c p_ic log(p_ic + eps), p = softmax(logits_i).  f32 [rows]. */
+int cmlpl_softmax_entropy_f32(const float* logits, int64_t rows, int C, float eps, float* entropy,
+                              cmlpl_stream_t stream);
+
 /* train.py:203,213-215,220-222: probs_orig = softmax(logits); if smooth: A = exp(feats.Q^T/T)
  * row-normalised, probs = alpha*probs_orig + (1-alpha)*A.Qp; mask = max(probs) >= thr.
  * feats f32 [rows, dim], queue_feats f32 [queue, dim], queue_probs f32 [queue, C],

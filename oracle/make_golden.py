@@ -289,10 +289,69 @@ def gold_step():
     print("step.npz ok, hist =", r["hist"])
 
 
+def gold_loss_helper():
+    """Outputs of the reference's loss_helper callables (loss_helper.py) on seeded inputs."""
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    # segmentation-style criteria on [b, 19, h, w]
+    pred = torch.randn(2, 19, 12, 10, generator=g)
+    aux = torch.randn(2, 19, 12, 10, generator=g)
+    tgt = torch.randint(0, 19, (2, 12, 10), generator=g)
+    tgt[0, :3] = 255
+    out.update(seg_pred=pred.numpy(), seg_aux=aux.numpy(), seg_tgt=tgt.numpy())
+    out["crit_plain"] = RLH.Criterion(0)(pred, tgt).numpy()
+    out["crit_aux"] = RLH.Criterion(0.4)((pred, aux), tgt).numpy()
+    out["crit_weight"] = RLH.Criterion(0.4, use_weight=True)((pred, aux), tgt).numpy()
+    out["ohem_tensor"] = RLH.OhemCrossEntropy2dTensor(255, 0.7, 40)(pred, tgt.clone()).numpy()
+    out["ohem_tensor_w"] = RLH.OhemCrossEntropy2dTensor(255, 0.05, 30, use_weight=True)(pred, tgt.clone()).numpy()
+    out["crit_ohem"] = RLH.CriterionOhem(0.4, thresh=0.7, min_kept=50)((pred, aux), tgt.clone()).numpy()
+    cfg = {"criterion": {"type": "ohem", "kwargs": {"thresh": 0.7, "min_kept": 50}}, "net": {"aux_loss": {"loss_weight": 0.4}},
+           "dataset": {"ignore_label": 255}}
+    out["get_criterion"] = RLH.get_criterion(cfg)((pred, aux), tgt.clone()).numpy()
+    torch.Tensor.get_device = lambda self: "cpu"
+    out["ohem_host"] = RLH.OhemCrossEntropy2d(255, 0.7, 160, factor=2)(pred, tgt.clone()).numpy()
+    out["rce"] = RLH.compute_rce_loss(pred, tgt.clone()).numpy()
+    # dequeue_and_enqueue
+    q, ptr = [torch.zeros(0, 8)], torch.zeros(1, dtype=torch.long)
+    hist = []
+    for n in (5, 9, 4):
+        keys = torch.randn(n, 8, generator=g)
+        RLH.dequeue_and_enqueue(keys, q, ptr, 12)
+        hist.append((q[0].clone().numpy(), int(ptr[0])))
+    out["dq_final"] = hist[-1][0]; out["dq_ptrs"] = np.array([h[1] for h in hist]); out["dq_mid"] = hist[1][0]
+    # compute_contra_memobank_loss: 6 classes, 24 labelled + 24 unlabelled, 32-d representations
+    C, nl, nu, D = 6, 24, 24, 32
+    rep = torch.randn(nl + nu, D, generator=g); rep_t = torch.randn(nl + nu, D, generator=g)
+    yl = torch.randint(0, C, (nl,), generator=g); yu = torch.randint(0, C, (nu,), generator=g)
+    label_l = torch.nn.functional.one_hot(yl, C).float(); label_u = torch.nn.functional.one_hot(yu, C).float()
+    prob_l = torch.softmax(torch.randn(nl, C, generator=g) * 2, 1); prob_u = torch.softmax(torch.randn(nu, C, generator=g) * 2, 1)
+    low_mask = (torch.rand(nl + nu, 1, generator=g) > 0.3).float(); high_mask = (torch.rand(nl + nu, 1, generator=g) > 0.3).float()
+    def banks():
+        gg = torch.Generator().manual_seed(5)
+        return [[torch.randn(7, D, generator=gg)] for _ in range(C)], [torch.zeros(1, dtype=torch.long) for _ in range(C)]
+    mb, ptrs = banks()
+    torch.manual_seed(77)
+    rr = rep.clone().requires_grad_(True)
+    keys, loss = RLH.compute_contra_memobank_loss(rr, label_l, label_u, prob_l, prob_u, low_mask, high_mask, mb, ptrs,
+                                                  [30] * C, rep_t)
+    loss.backward()
+    out.update(mb_rep=rep.numpy(), mb_rep_t=rep_t.numpy(), mb_label_l=label_l.numpy(), mb_label_u=label_u.numpy(),
+               mb_prob_l=prob_l.numpy(), mb_prob_u=prob_u.numpy(), mb_low=low_mask.numpy(), mb_high=high_mask.numpy(),
+               mb_loss=loss.detach().numpy(), mb_keys=np.array(keys), mb_grad=rr.grad.numpy(),
+               mb_bank_sizes=np.array([b[0].shape[0] for b in mb]))
+    mb, ptrs = banks()
+    torch.manual_seed(78)
+    proto, keys, loss = RLH.compute_contra_memobank_loss(rep, label_l, label_u, prob_l, prob_u, low_mask, high_mask, mb,
+                                                         ptrs, [30] * C, rep_t, momentum_prototype=torch.ones(C, 256, 1, D) * 0.1, i_iter=5)
+    out.update(mb_loss_mom=loss.numpy(), mb_proto_sum=proto.sum((1, 2, 3)).numpy())
+    np.savez_compressed(os.path.join(GOLD, "loss_helper.npz"), **out)
+    print("loss_helper.npz ok")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
-    which = sys.argv[1:] or ["patches", "basenet2", "metrics", "train", "step"]
+    which = sys.argv[1:] or ["patches", "basenet2", "metrics", "train", "step", "loss_helper"]
     if "patches" in which:
         gold_patches()
     if "basenet2" in which:
@@ -303,3 +362,5 @@ if __name__ == "__main__":
         gold_train()
     if "step" in which:
         gold_step()
+    if "loss_helper" in which:
+        gold_loss_helper()
