@@ -217,14 +217,19 @@ def main():
             cm.zero_()
             parallel.reduce_confusion(ops.confusion(labels, truth, K0, cm))
 
+    from cmlpl_b200.tools.hyper_tools import StreamedScene
+    streamed = StreamedScene(scene_rows, C0, B0, K0, W0, nsplit=4, row0=r0, rows=r1 - r0, device=dev)
+    assert (streamed.s0, streamed.s1) == (s0, s1)
+
     def step_e2e():
-        d_slab = slab_host.to(dev, non_blocking=True)
-        d_spec = spec_host.to(dev, non_blocking=True)
-        ops.scene_infer(d_slab, d_spec, packed, K0, W0, band_row0=r0, band_rows=r1 - r0, scene_rows=scene_rows,
-                        slab_row0=s0, workspace=ws, labels=labels)
+        # public end-to-end call: pinned host cube slab + spectra in, uint8 labels out (H2D overlapped
+        # with compute band by band, D2H of the label map at the end)
         if world > 1:
-            parallel.gather_label_map(labels, scene_rows, C0)
-        labels_host.copy_(labels, non_blocking=True)
+            lab = streamed(packed, slab_host, spec_host, d2h=False)
+            parallel.gather_label_map(lab, scene_rows, C0)
+            streamed.labels_host.copy_(lab, non_blocking=True)
+        else:
+            streamed(packed, slab_host, spec_host)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):

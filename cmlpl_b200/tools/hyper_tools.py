@@ -147,6 +147,61 @@ def scene_labels(model, cube, spectra, w=20, band=None, scene_rows=None, slab_ro
                            scene_rows=R, slab_row0=slab_row0, want_logits=want_logits)
 
 
+class StreamedScene:
+    """End-to-end scene inference from HOST buffers with the H2D copies overlapped with compute:
+    the scene is cut into ``nsplit`` row bands; band k+1's cube rows (+halo) and spectra are copied on
+    a side stream while band k runs through cmlpl_scene_infer on the current stream.  Device buffers,
+    the workspace and the pinned label buffer are allocated once and reused across calls."""
+
+    def __init__(self, scene_rows, cols, num_features, num_classes, w=20, nsplit=4, row0=0, rows=None, device=None):
+        self.R, self.C, self.B, self.K, self.w = scene_rows, cols, num_features, num_classes, w
+        self.r0 = row0
+        self.r1 = scene_rows if rows is None else row0 + rows
+        dev = _device() if device is None else device
+        n = (self.r1 - self.r0) * cols
+        lo = w // 2
+        self.s0 = max(0, self.r0 - lo)
+        self.s1 = min(scene_rows, self.r1 + (w - lo - 1))
+        # mirrored halo rows at true scene edges always lie inside [s0, s1) because hw <= band rows here
+        self.cube = torch.empty((self.s1 - self.s0, cols, 60), dtype=torch.float32, device=dev)
+        self.spectra = torch.empty((n, num_features), dtype=torch.float32, device=dev)
+        self.labels = torch.empty((n,), dtype=torch.uint8, device=dev)
+        self.labels_host = torch.empty((n,), dtype=torch.uint8).pin_memory()
+        per = -(-(self.r1 - self.r0) // nsplit)
+        self.bands = [(a, min(a + per, self.r1)) for a in range(self.r0, self.r1, per)]
+        self.ws = ops.scene_workspace(per, cols, num_features, num_classes, w, dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.events = [torch.cuda.Event() for _ in self.bands]
+        self.done = torch.cuda.Event()
+
+    def __call__(self, packed, cube_host, spectra_host, d2h=True):
+        """cube_host f32 [s1-s0, C, 60] (pinned; slab rows s0..s1 of the scene), spectra_host f32
+        [n, B] (pinned).  Returns the uint8 labels (pinned host tensor if d2h else the CUDA tensor)."""
+        main = torch.cuda.current_stream()
+        lo, C = self.w // 2, self.C
+        self.copy_stream.wait_event(self.done)          # previous call's compute has consumed the buffers
+        copied = self.s0
+        with torch.cuda.stream(self.copy_stream):
+            for (a, b), ev in zip(self.bands, self.events):
+                upto = min(self.s1, b + (self.w - lo - 1))
+                if upto > copied:
+                    self.cube[copied - self.s0:upto - self.s0].copy_(cube_host[copied - self.s0:upto - self.s0], non_blocking=True)
+                    copied = upto
+                pa, pb = (a - self.r0) * C, (b - self.r0) * C
+                self.spectra[pa:pb].copy_(spectra_host[pa:pb], non_blocking=True)
+                ev.record(self.copy_stream)
+        for (a, b), ev in zip(self.bands, self.events):
+            main.wait_event(ev)
+            pa, pb = (a - self.r0) * C, (b - self.r0) * C
+            ops.scene_infer(self.cube, self.spectra[pa:pb], packed, self.K, self.w, band_row0=a, band_rows=b - a,
+                            scene_rows=self.R, slab_row0=self.s0, workspace=self.ws, labels=self.labels[pa:pb])
+        self.done.record(main)
+        if not d2h:
+            return self.labels
+        self.labels_host.copy_(self.labels, non_blocking=True)
+        return self.labels_host
+
+
 def confusion_matrix(predict, label, num_classes):
     """int64 [C, C] counts cm[label, predict] computed on device."""
     dev = _device()

@@ -284,3 +284,28 @@ def test_test_whole_generic_loader(dev, golden_dir):
     loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(XP, X), batch_size=128)
     out = H.test_whole(net, loader)
     assert out.dtype == np.int64 and np.array_equal(out, z["predict_label"][idx].astype(np.int64))
+
+
+def test_streamed_scene_equals_plain(dev):
+    """Host-buffer entry point (band-wise H2D overlapped with compute) returns the same labels."""
+    from cmlpl_b200 import ops
+    from cmlpl_b200.tools.hyper_tools import StreamedScene
+    rng = np.random.default_rng(13)
+    R, C, B, K = 53, 41, 103, 9
+    cube = torch.from_numpy(rng.standard_normal((R, C, 60)).astype(np.float32)).pin_memory()
+    spectra = torch.from_numpy(rng.standard_normal((R * C, B)).astype(np.float32)).pin_memory()
+    torch.manual_seed(9)
+    sd = {k: v.to(dev) for k, v in O.basenet2_init(B, K).items()}
+    packed = ops.pack_basenet2(sd, B, K, 20)
+    ref = ops.scene_infer(cube.to(dev), spectra.to(dev), packed, K, 20)
+    for nsplit in (1, 3, 4):
+        st = StreamedScene(R, C, B, K, 20, nsplit=nsplit)
+        for _ in range(2):                                    # second call reuses the buffers
+            got = st(packed, cube, spectra)
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref.cpu())
+    # a band of a larger scene (multi-GPU shape): rows 20..40 with its halo slab
+    st = StreamedScene(R, C, B, K, 20, nsplit=2, row0=20, rows=20)
+    got = st(packed, cube[st.s0:st.s1].contiguous().pin_memory(), spectra[20 * C:40 * C].contiguous().pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref.cpu()[20 * C:40 * C])
