@@ -50,6 +50,27 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
     out[col] = t;
   }
 }
+// db[co] = sum_{b,pos} dy[b][co][pos]: one CTA per output channel, grid-stride over (b, pos), tree reduce
+__global__ void __launch_bounds__(256)
+conv_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int b, int co, int hw) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  const int total = b * hw;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int bi = i / hw, r = i - bi * hw;
+    s += dy[(int64_t(bi) * co + c) * hw + r];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) db[c] = v;
+  }
+}
+
 // one warp per row
 __global__ void l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norm, int64_t rows, int64_t cols) {
   const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -135,12 +156,8 @@ extern "C" int cmlpl_conv2d_wgrad_f32(const float* x, const float* dy, float* dw
   else rc = launch_gemm(co, N, Kp, splits, WgradA{dy, co, h * w}, WgradB<3>{x, ci, h, w}, fc, s, "conv3x3_wgrad");
   if (rc != CMLPL_OK) return rc;
   if (db) {
-    // db[co] = sum_{b,pos} dy : a GEMM with a ones vector would waste work; use strided row sums
-    // via the GEMM core with N=1: C[co,0] = sum_k A(co,k) * 1
-    CMLPL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * co, s));
-    AtomicC fb{db, 1};
-    int sp = Kp / 2048; if (sp < 1) sp = 1; if (sp > 64) sp = 64;
-    rc = launch_gemm(co, 1, Kp, sp, WgradA{dy, co, h * w}, OnesB{}, fb, s, "conv_bgrad");
+    conv_bias_grad_kernel<<<co, 256, 0, s>>>(dy, db, b, co, h * w);
+    CMLPL_CHECK_LAUNCH("conv_bias_grad");
   }
   return rc;
 }
