@@ -4,8 +4,10 @@
 //                    halo-padded fp16 map F0pad[8 chunks][(rows+w-1)][(cols+w-1)][8 channels]; a pixel's patch
 //                    is then a plain w x w window of this map (hyper_tools.py:35-55,226-243)
 //   2. spectral_head relu(feat_spe(x)) (models.py:142-143) and its classifier columns
-//   3. patch_cnn     conv1/conv2 + residual + ReLU + avg-pool per pixel (patch_cnn_sm100.cu,
-//                    tcgen05) -> pooled features P2[n,(w/4)^2,64] fp16
+//   3. conv1_scene   conv1 + residual + ReLU once per scene position in 9 patch-border classes and the
+//                    pooled maps (conv1_scene_sm100.cu), then patch_conv2: conv2 + residual + ReLU +
+//                    avg-pool per pixel pair (patch_conv2_sm100.cu) -> pooled features P2 (UMMA tiles).
+//                    (> 16 classes / > 208 bands: the all-per-pixel patch_cnn_sm100.cu kernel instead)
 //   4. classify      classifier (models.py:150) over [P2 | spectral] + argmax
 //                    (hyper_tools.py:426, first index wins ties)
 #include "common.cuh"
@@ -123,7 +125,7 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int64_t n, int C
 static bool use_tc_head(int B, int C) { return C <= 16 && ((B + 15) / 16) * 2 <= 26; }
 
 struct SceneWs {
-  size_t f0pad, p2, spe, hidden, x16, h16, total;
+  size_t f0pad, p2, spe, hidden, x16, h16, g, pm, total;
   int64_t chunk;
   bool tc;
 };
@@ -136,11 +138,14 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   size_t o = 0;
   s.f0pad = o; o = align256(o + size_t(band_rows + w - 1) * (cols + w - 1) * 64 * 2);
   s.p2 = o; o = align256(o + size_t(s.tc ? mtiles * 128 : n) * P * 64 * 2);
-  s.spe = s.hidden = s.x16 = s.h16 = 0;
+  s.spe = s.hidden = s.x16 = s.h16 = s.g = s.pm = 0;
   s.chunk = n < 16384 ? n : 16384;
   if (s.tc) {
     s.x16 = o; o = align256(o + size_t(mtiles) * (((B + 15) / 16) * 2) * 2048);
     s.h16 = o; o = align256(o + size_t(mtiles) * 128 * 2048);
+    const size_t ppos = size_t(band_rows + w - 1) * (cols + w - 1);
+    s.g = o; o = align256(o + ppos * 9 * 64 * 4);          // conv1 border-class variants, fp32
+    s.pm = o; o = align256(o + ppos * 9 * 64 * 2);         // pooled variants, fp16 chunk-planar
   } else {
     s.spe = o; o = align256(o + size_t(n) * C * 4);
     s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);
@@ -271,7 +276,11 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
   if (ws.tc) {
     rc = cmlpl_spectral_hidden_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16, wsb + ws.h16, stream);
     if (rc != CMLPL_OK) return rc;
-    rc = cmlpl_patch_cnn_f16_tiled(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.p2, stream);
+    // conv1 once per scene position (9 border classes) + pooled maps, then conv2 per pixel pair
+    rc = cmlpl_conv1_scene_f16(wsb + ws.f0pad, cols, w, band_rows, packed, reinterpret_cast<float*>(wsb + ws.g),
+                               wsb + ws.pm, stream);
+    if (rc != CMLPL_OK) return rc;
+    rc = cmlpl_patch_conv2_f16_tiled(wsb + ws.pm, cols, w, band_rows, packed, wsb + ws.p2, stream);
     if (rc != CMLPL_OK) return rc;
     return cmlpl_head_tc(wsb + ws.p2, wsb + ws.h16, n, num_features, num_classes, w, packed, labels, logits, stream);
   }
