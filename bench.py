@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -152,8 +152,8 @@ def workload_config(n_gpus, note=None):
            "scene_rows": R0 * n_gpus, "scene_cols": C0, "bands": B0, "classes": K0, "patch": W0,
            "pixels_per_step": R0 * C0 * n_gpus,
            "parallelism": f"row bands x{n_gpus} (weak: {R0} rows + halo per GPU, scene = {R0 * n_gpus} rows)",
-           "l2_policy": "per-step working set (cube 50 MB + spectra 85 MB + conv0 map 29 MB + pooled features "
-                        "664 MB + hidden features 425 MB) exceeds the 126 MB L2; no explicit flush"}
+           "l2_policy": "per-step working set (cube 50 MB + spectra 85 MB + conv0 map 29 MB + conv1 variants 520 MB + pooled "
+                        "maps 260 MB + pooled features 664 MB + hidden features 425 MB) exceeds the 126 MB L2; no explicit flush"}
     if note:
         cfg["note"] = note
     return cfg
@@ -219,7 +219,7 @@ def main():
             parallel.reduce_confusion(ops.confusion(labels, truth, K0, cm))
 
     from cmlpl_b200.tools.hyper_tools import StreamedScene
-    streamed = StreamedScene(scene_rows, C0, B0, K0, W0, nsplit=4, row0=r0, rows=r1 - r0, device=dev)
+    streamed = StreamedScene(scene_rows, C0, B0, K0, W0, nsplit=8, row0=r0, rows=r1 - r0, device=dev)
     assert (streamed.s0, streamed.s1) == (s0, s1)
 
     def step_e2e():

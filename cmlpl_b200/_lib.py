@@ -40,6 +40,7 @@ SIGNATURES = {
     "cmlpl_patch_cnn_f16_tiled": (I, [P, I, I, I, P, P, P]),
     "cmlpl_conv1_scene_f16": (I, [P, I, I, I, P, P, P, P]),
     "cmlpl_patch_conv2_f16_tiled": (I, [P, I, I, I, P, P, P]),
+    "cmlpl_debug_patch_conv2_trace": (I, [P, I, I, I, P, P, P, P]),
     "cmlpl_spectral_hidden_tc": (I, [P, L, I, I, I, P, P, P, P]),
     "cmlpl_head_tc": (I, [P, P, L, I, I, I, P, P, P, P]),
     "cmlpl_spectral_head_f32": (I, [P, L, I, I, I, P, P, L, P, P]),

@@ -203,13 +203,14 @@ conv1_scene_kernel(const __half* __restrict__ f0, int PR, int PC, const unsigned
 // 2x2 average pools of the conv1 variants for every top-left position (pr, pc), pr < PR-1, pc < PC-1:
 //   PM[A][B][pr,pc] = 1/4 sum_{u,v in {0,1}} G[a(A,u)][b(B,v)][pr+u, pc+v]
 //   a(top,0)=top a(top,1)=mid   a(mid,.)=mid   a(bot,0)=mid a(bot,1)=bot     (pooled row 0 / 1..8 / 9)
-// written f16 chunk-planar [9][8 chunks][PR][PC][8] (the per-pixel conv2 loader copies 16-byte pieces).
+// written f16 position-major [9][PR][PC][64]: one 128-byte line per pooled cell, which is what the
+// per-pixel conv2 gather (every other row / column) fetches -- 100 lines per pixel.
 __global__ void pool1_scene_kernel(const float* __restrict__ g, int PR, int PC, __half* __restrict__ pm) {
   const int64_t plane = int64_t(PR) * PC;
   const int64_t total = plane * 8;
   for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t pos = t % plane;
-    const int ch = int(t / plane);
+    const int64_t pos = t >> 3;
+    const int ch = int(t & 7);
     const int pr = int(pos / PC), pc = int(pos - int64_t(pr) * PC);
     if (pr >= PR - 1 || pc >= PC - 1) continue;
 #pragma unroll
@@ -230,7 +231,7 @@ __global__ void pool1_scene_kernel(const float* __restrict__ g, int PR, int PC, 
           h[2 * q] = __floats2half2_rn(((x00.x + x10.x) + (x01.x + x11.x)) * 0.25f, ((x00.y + x10.y) + (x01.y + x11.y)) * 0.25f);
           h[2 * q + 1] = __floats2half2_rn(((x00.z + x10.z) + (x01.z + x11.z)) * 0.25f, ((x00.w + x10.w) + (x01.w + x11.w)) * 0.25f);
         }
-        *reinterpret_cast<uint4*>(pm + ((int64_t((A * 3 + B) * 8 + ch) * plane) + pos) * 8) = *reinterpret_cast<uint4*>(h);
+        *reinterpret_cast<uint4*>(pm + (int64_t(A * 3 + B) * plane + pos) * 64 + ch * 8) = *reinterpret_cast<uint4*>(h);
       }
     }
   }

@@ -145,7 +145,7 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
     s.h16 = o; o = align256(o + size_t(mtiles) * 128 * 2048);
     const size_t ppos = size_t(band_rows + w - 1) * (cols + w - 1);
     s.g = o; o = align256(o + ppos * 9 * 64 * 4);          // conv1 border-class variants, fp32
-    s.pm = o; o = align256(o + ppos * 9 * 64 * 2);         // pooled variants, fp16 chunk-planar
+    s.pm = o; o = align256(o + ppos * 9 * 64 * 2);         // pooled variants, fp16 [9][PR][PC][64]
   } else {
     s.spe = o; o = align256(o + size_t(n) * C * 4);
     s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);

@@ -157,13 +157,15 @@ int cmlpl_head_tc(const void* p2t, const void* h16, int64_t n, int num_features,
  * position of the conv0 map in 3x3 = 9 patch-border classes, then the 2x2 average pools of every
  * top-left position in the 9 pooled border classes (tools/models.py:133-136 for all patches at once).
  *   f0pad f16 [8][PR][PC][8] (PR = band_rows+w-1, PC = cols+w-1), g f32 [9][PR*PC][64] scratch,
- *   pm f16 [9][8][PR][PC][8]: pooled maps, variant = A*3+B (A,B in top/mid/bot, left/mid/right). */
+ *   pm f16 [9][PR][PC][64]: pooled maps, variant = A*3+B (A,B in top/mid/bot, left/mid/right). */
 int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
                           void* pm, cmlpl_stream_t stream);
 /* Per-pixel conv2 stage on the pooled conv1 maps of cmlpl_conv1_scene_f16 (models.py:137-140 per patch):
- * pm f16 [9][8][PR][PC][8] -> p2t UMMA tiles [ceil(n/128)][(w/4)^2*8][128][8] for cmlpl_head_tc. */
+ * pm f16 [9][PR][PC][64] -> p2t UMMA tiles [ceil(n/128)][(w/4)^2*8][128][8] for cmlpl_head_tc. */
 int cmlpl_patch_conv2_f16_tiled(const void* pm, int cols, int w, int band_rows, const void* packed,
                                 void* p2t, cmlpl_stream_t stream);
+int cmlpl_debug_patch_conv2_trace(const void* pm, int cols, int w, int band_rows, const void* packed,
+                                  void* p2t, long long* trace, cmlpl_stream_t stream);
 /* Diagnostics: cmlpl_patch_cnn_f16 with CTA 0 writing clock64() stamps of its first 64 patches
  * (16 slots each: loader / MMA issuer / epilogue protocol points) to trace i64 [64,16]. */
 int cmlpl_debug_patch_cnn_trace(const void* f0pad, int cols, int w, int band_rows, const void* packed,

@@ -14,7 +14,7 @@ sd = O.basenet2_init(103, 9)
 packed = ops.pack_basenet2({k: v.to(dev) for k, v in sd.items()}, 103, 9, w)
 f0 = (torch.randn(8, PR, PC, 8, device=dev) * 0.7).half()
 g = torch.zeros(9, PR * PC, 64, device=dev)
-pm = torch.zeros(9, 8, PR, PC, 8, dtype=torch.float16, device=dev)
+pm = torch.zeros(9, PR, PC, 64, dtype=torch.float16, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 _lib.call("cmlpl_conv1_scene_f16", f0.data_ptr(), C, w, R, packed.data_ptr(), g.data_ptr(), pm.data_ptr(), st)
 torch.cuda.synchronize()
@@ -40,6 +40,6 @@ for A in range(3):
     for B in range(3):
         b0, b1 = (0 if B == 0 else 1), (2 if B == 2 else 1)
         ref = 0.25 * (G[a0, b0][:, :-1, :-1] + G[a0, b1][:, :-1, 1:] + G[a1, b0][:, 1:, :-1] + G[a1, b1][:, 1:, 1:])
-        got = pm[A * 3 + B].float().cpu().permute(0, 3, 1, 2).reshape(64, PR, PC)[:, :-1, :-1]
+        got = pm[A * 3 + B].float().cpu().permute(2, 0, 1)[:, :-1, :-1]
         worst = max(worst, float((got - ref).abs().max() / ref.abs().max()))
 print("pool1_scene PM variants: worst rel err %.2e" % worst)

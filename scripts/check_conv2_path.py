@@ -13,7 +13,7 @@ for (R, C) in ((37, 45), (610, 340)):
     packed = ops.pack_basenet2({k: v.to(dev) for k, v in sd.items()}, 103, 9, w)
     f0 = (torch.randn(8, PR, PC, 8, device=dev) * 0.7).half()
     g = torch.empty(9, PR * PC, 64, device=dev)
-    pm = torch.zeros(9, 8, PR, PC, 8, dtype=torch.float16, device=dev)
+    pm = torch.zeros(9, PR, PC, 64, dtype=torch.float16, device=dev)
     mt = (n + 127) // 128
     p2a = torch.zeros(mt, 200, 128, 8, dtype=torch.float16, device=dev)
     p2b = torch.zeros(mt, 200, 128, 8, dtype=torch.float16, device=dev)
