@@ -219,7 +219,7 @@ def main():
             parallel.reduce_confusion(ops.confusion(labels, truth, K0, cm))
 
     from cmlpl_b200.tools.hyper_tools import StreamedScene
-    streamed = StreamedScene(scene_rows, C0, B0, K0, W0, nsplit=8, row0=r0, rows=r1 - r0, device=dev)
+    streamed = StreamedScene(scene_rows, C0, B0, K0, W0, nsplit=4, row0=r0, rows=r1 - r0, device=dev)
     assert (streamed.s0, streamed.s1) == (s0, s1)
 
     def step_e2e():
