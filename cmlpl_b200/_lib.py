@@ -46,6 +46,8 @@ SIGNATURES = {
     "cmlpl_spectral_head_f32": (I, [P, L, I, I, I, P, P, L, P, P]),
     "cmlpl_classify_f16": (I, [P, P, L, I, I, I, P, P, P, P]),
     "cmlpl_argmax_u8": (I, [P, L, I, P, P]),
+    "cmlpl_preprocess_fit_f64": (I, [P, I, L, I, P, P, P]),
+    "cmlpl_preprocess_apply": (I, [P, I, L, I, I, P, P, P, P, P, P, P]),
     "cmlpl_confusion_i64": (I, [P, P, L, I, P, P]),
     "cmlpl_ce_fwd_bwd_f32": (I, [P, P, P, P, L, I, F, P, P, P]),
     "cmlpl_softmax_entropy_f32": (I, [P, L, I, F, P, P]),

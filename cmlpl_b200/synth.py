@@ -27,7 +27,7 @@ def synth_scene(R: int, C: int, B: int, K: int, seed: int = 1088, block: int = 8
     return np.clip(cube, 0, 8000).astype(np.uint16), gt.astype(np.uint8)
 
 
-def preprocessed_scene(R, C, B, K, n_PC=60, seed=1088):
+def preprocessed_scene(R, C, B, K, n_PC=60, seed=1088, return_raw=False):
     """(cubePCA f32 [R,C,n_PC], spectra f32 [R*C,B], gt) through the reference's preprocessing
     (tools/hyper_tools.py:285-292: PCA + per-channel z-score, float64 on the host)."""
     from .tools.hyper_tools import PCANorm, featureNormalize
@@ -36,4 +36,6 @@ def preprocessed_scene(R, C, B, K, n_PC=60, seed=1088):
     X = cube.reshape(R * C, B)
     cube_pca = featureNormalize(PCANorm(X, n_PC), 1).reshape(R, C, n_PC).astype(np.float32)
     spectra = featureNormalize(X, 1).astype(np.float32)
+    if return_raw:
+        return cube_pca, spectra, gt, cube
     return cube_pca, spectra, gt

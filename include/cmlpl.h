@@ -174,6 +174,19 @@ int cmlpl_debug_patch_cnn_trace(const void* f0pad, int cols, int w, int band_row
 int cmlpl_argmax_u8(const float* logits, int64_t n, int num_classes, uint8_t* labels,
                     cmlpl_stream_t stream);
 
+/* ------------------------------------------------------------- preprocessing --
+ * tools/hyper_tools.py:8-32 (featureNormalize, PCANorm) as called at :289-292, on device.
+ * x: raw scene [n, B], dtype 0 = uint16, 1 = float32.
+ * fit  : mean f64 [B] = column means, gram f64 [B,B] = sum_n (x-mean)(x-mean)^T, upper 32x32 tiles only
+ *        (mirror on the host; np.cov = gram/(n-1), np.std^2 = diag(gram)/n).  The B x B SVD stays on the host.
+ * apply: spectra f32 [n,B] = (x-mu)*inv_sigma (may be NULL);  cube f32 [n,npc] = (x-mu).Us - shift with
+ *        Us f32 [B,npc] = U[:, :npc]/s and shift = m/s (m, s = mean/std of the projected data). */
+int cmlpl_preprocess_fit_f64(const void* x, int dtype, int64_t n, int B, double* mean, double* gram,
+                             cmlpl_stream_t stream);
+int cmlpl_preprocess_apply(const void* x, int dtype, int64_t n, int B, int npc, const float* mu,
+                           const float* inv_sigma, const float* Us, const float* shift, float* cube,
+                           float* spectra, cmlpl_stream_t stream);
+
 /* ------------------------------------------------------------------ metrics --
  * tools/hyper_tools.py:208-223 (CalAccuracy): integer confusion matrix
  * cm[label, pred] += 1 for pairs with both in [0, C).  pred u8 [n], label i64 [n],

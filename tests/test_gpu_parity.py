@@ -309,3 +309,44 @@ def test_streamed_scene_equals_plain(dev):
     got = st(packed, cube[st.s0:st.s1].contiguous().pin_memory(), spectra[20 * C:40 * C].contiguous().pin_memory())
     torch.cuda.synchronize()
     assert torch.equal(got, ref.cpu()[20 * C:40 * C])
+
+
+def test_device_preprocessing_matches_reference_numpy(dev):
+    """fit (float64 moments on device + host SVD) and apply reproduce PCANorm + featureNormalize
+    (tools/hyper_tools.py:8-32,289-292; oracle.preprocess is pinned bit-equal to the reference files)."""
+    from cmlpl_b200 import preprocess, synth
+    cube_u16, _ = synth.synth_scene(64, 50, 103, 9, seed=5)
+    X = cube_u16.reshape(-1, 103)
+    ref_cube, ref_spec = O.preprocess(cube_u16, 60)
+    raw = torch.from_numpy(X.copy()).to(dev)
+    pp = preprocess.fit(raw, 60)
+    assert np.abs(pp.mu - X.mean(0)).max() < 1e-9 and np.abs(pp.sigma - X.astype(np.float64).std(0)).max() < 1e-9
+    cube, spec = preprocess.apply(raw, pp)
+    assert rel(spec.cpu(), ref_spec) < 1e-6
+    got = cube.cpu().numpy().reshape(64, 50, 60)
+    # singular vectors are defined up to sign: align each component before comparing
+    sgn = np.sign((got * ref_cube).sum((0, 1)))
+    assert rel(got * sgn, ref_cube) < 2e-5
+    assert np.mean(sgn > 0) > 0.9                        # same LAPACK on (almost) the same matrix: same signs
+    # float32 raw input path
+    cube_f, _ = preprocess.apply(raw.float(), pp, want_spectra=False)
+    assert rel(cube_f.cpu(), cube.cpu()) < 1e-6
+
+
+def test_streamed_raw_scene_equals_preprocessed_path(dev):
+    from cmlpl_b200 import ops, preprocess, synth
+    from cmlpl_b200.tools.hyper_tools import StreamedRawScene
+    R, C, B, K = 47, 39, 103, 9
+    cube_u16, _ = synth.synth_scene(R, C, B, K, seed=6)
+    raw_host = torch.from_numpy(cube_u16.reshape(-1, B).copy()).pin_memory()
+    pp = preprocess.fit(raw_host.to(dev), 60)
+    cube, spec = preprocess.apply(raw_host.to(dev), pp)
+    torch.manual_seed(10)
+    sd = {k: v.to(dev) for k, v in O.basenet2_init(B, K).items()}
+    packed = ops.pack_basenet2(sd, B, K, 20)
+    ref = ops.scene_infer(cube.view(R, C, 60), spec, packed, K, 20)
+    for nsplit in (1, 3):
+        st = StreamedRawScene(pp, R, C, B, K, 20, nsplit=nsplit)
+        got = st(packed, raw_host)
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref.cpu())
