@@ -27,10 +27,10 @@ confusion_kernel(const uint8_t* __restrict__ pred, const int64_t* __restrict__ l
 extern "C" int cmlpl_confusion_i64(const uint8_t* pred, const int64_t* label, int64_t n, int num_classes,
                                    int64_t* cm, cmlpl_stream_t stream) {
   using namespace cmlpl;
-  CMLPL_CHECK_ARG(pred && label && cm, "confusion: null pointer");
   CMLPL_CHECK_ARG(n >= 0 && num_classes > 0 && num_classes <= 64, "confusion: bad dims (n=%lld C=%d)", (long long)n,
                   num_classes);
-  if (n == 0) return CMLPL_OK;
+  if (n == 0) return CMLPL_OK;                             // empty inputs: nothing to count (pointers may be null)
+  CMLPL_CHECK_ARG(pred && label && cm, "confusion: null pointer");
   // each CTA sees < 2^32 samples: grid-stride over n with at most 2^31 per CTA by construction
   int64_t grid = (n + 255) / 256;
   const int64_t cap = int64_t(sm_count()) * 8;
