@@ -89,6 +89,7 @@ patch_conv2_kernel(const __half* __restrict__ pm, int cols, int band_rows, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
+  const int dbg = trace ? int(trace[1023]) : 0;            // diagnostics only: bit0 skip gather, bit1 skip epilogue work
 
   if (warp >= 8 && warp < kMmaWarp) {
     // ================================================================ loaders
@@ -105,7 +106,7 @@ patch_conv2_kernel(const __half* __restrict__ pm, int cols, int band_rows, const
         const __half* src0 = pm + (int64_t(rb) * PC + c) * 64;
         const uint32_t dst0 = sbase + S_A + buf * ABYTES + px * (PW2 * 16);
 #pragma unroll
-        for (int it = lt; it < NITEM; it += kLoad) {
+        for (int it = lt; it < ((dbg & 1) ? 0 : NITEM); it += kLoad) {
           const uint4 rec = *reinterpret_cast<const uint4*>(smem + S_TAB + it * 16);
           const int64_t goff = int64_t((uint64_t(rec.y) << 32) | rec.x);
           cp_async16(dst0 + rec.z, src0 + goff);
@@ -196,6 +197,7 @@ patch_conv2_kernel(const __half* __restrict__ pm, int cols, int band_rows, const
         tmem_ld16(lane_addr + stage * 128 + 64 + hg * 16, o);
         tmem_ld_wait();
         if (hg == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (D_EMPTY0 + stage)); }
+        if (dbg & 2) continue;
         const __half2* he = reinterpret_cast<const __half2*>(&re[hg * 2]);
         const __half2* ho = reinterpret_cast<const __half2*>(&ro[hg * 2]);
         float pooled[16];
