@@ -34,6 +34,8 @@ SIGNATURES = {
     "cmlpl_pack_basenet2": (I, [P] * 10 + [I, I, I, P, P]),
     "cmlpl_scene_workspace_bytes": (Z, [I, I, I, I, I]),
     "cmlpl_scene_infer": (I, [P, I, I, I, I, P, I, I, I, I, I, P, P, Z, P, P, P]),
+    "cmlpl_scene_infer_raw": (I, [P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, Z, P, P, P]),
+    "cmlpl_spectral_hidden_raw_tc": (I, [P, I, L, I, I, I, P, P, P, P, P, P]),
     "cmlpl_conv0_map_f16": (I, [P, I, I, I, I, I, I, I, P, P, P]),
     "cmlpl_patch_cnn_f16": (I, [P, I, I, I, P, P, P]),
     "cmlpl_debug_patch_cnn_trace": (I, [P, I, I, I, P, P, P, P]),

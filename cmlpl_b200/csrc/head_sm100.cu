@@ -36,6 +36,28 @@ __global__ void x16_tile_kernel(const float* __restrict__ X, int64_t n, int B, i
   }
 }
 
+// same from the raw cube: x16 = (raw - mu) * inv_sigma  (featureNormalize(X, 1), hyper_tools.py:292)
+template <typename T>
+__global__ void x16_tile_raw_kernel(const T* __restrict__ X, int64_t n, int B, int KC, int64_t total,
+                                    const float* __restrict__ mu, const float* __restrict__ inv_sigma,
+                                    __half* __restrict__ out) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int row = int(t & 127);
+    const int64_t r = t >> 7;
+    const int kc = int(r % KC);
+    const int64_t p = (r / KC) * 128 + row;
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = kc * 8 + 2 * e;
+      const float a = (p < n && k < B) ? (float(X[p * B + k]) - __ldg(mu + k)) * __ldg(inv_sigma + k) : 0.f;
+      const float b = (p < n && k + 1 < B) ? (float(X[p * B + k + 1]) - __ldg(mu + k + 1)) * __ldg(inv_sigma + k + 1) : 0.f;
+      h[e] = __floats2half2_rn(a, b);
+    }
+    *reinterpret_cast<uint4*>(out + t * 8) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
 // ------------------------------------------------------------------ H = relu(X . W^T + b)
 constexpr int kHidThreads = 320;   // warps 0-7 epilogue, warp 8 loader, warp 9 MMA issuer
 
@@ -251,9 +273,10 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
 
 using namespace cmlpl;
 
-extern "C" int cmlpl_spectral_hidden_tc(const float* spectra, int64_t n, int num_features, int num_classes, int w,
-                                        const void* packed, void* x16, void* h16, cmlpl_stream_t stream) {
-  CMLPL_CHECK_ARG(spectra && packed && x16 && h16, "spectral_hidden_tc: null pointer");
+static int spectral_hidden_impl(const void* x, int dtype /* -1 = preprocessed f32 spectra */, int64_t n, int num_features,
+                                int num_classes, int w, const float* mu, const float* inv_sigma, const void* packed,
+                                void* x16, void* h16, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(x && packed && x16 && h16, "spectral_hidden_tc: null pointer");
   CMLPL_CHECK_ARG(n > 0 && num_features > 0, "spectral_hidden_tc: bad dims");
   const PackedLayout L = packed_layout(num_features, num_classes, w);
   CMLPL_CHECK_ARG(L.kc_spe_in <= 26, "spectral_hidden_tc: %d bands exceed the 208 the tensor-core tile supports",
@@ -262,7 +285,12 @@ extern "C" int cmlpl_spectral_hidden_tc(const float* spectra, int64_t n, int num
   const int KC = L.kc_spe_in;
   const int64_t mtiles = (n + 127) / 128, total = mtiles * KC * 128;
   int64_t g = (total + 255) / 256; const int64_t cap = int64_t(sm_count()) * 16; if (g > cap) g = cap;
-  x16_tile_kernel<<<int(g), 256, 0, s>>>(spectra, n, num_features, KC, total, static_cast<__half*>(x16));
+  if (dtype < 0)
+    x16_tile_kernel<<<int(g), 256, 0, s>>>(static_cast<const float*>(x), n, num_features, KC, total, static_cast<__half*>(x16));
+  else if (dtype == 0)
+    x16_tile_raw_kernel<uint16_t><<<int(g), 256, 0, s>>>(static_cast<const uint16_t*>(x), n, num_features, KC, total, mu, inv_sigma, static_cast<__half*>(x16));
+  else
+    x16_tile_raw_kernel<float><<<int(g), 256, 0, s>>>(static_cast<const float*>(x), n, num_features, KC, total, mu, inv_sigma, static_cast<__half*>(x16));
   CMLPL_CHECK_LAUNCH("x16_tile");
   const size_t smem = size_t(KC) * 8192 + 1024 + 64 + 64;
   CMLPL_CUDA(cudaFuncSetAttribute(spectral_hidden_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -275,6 +303,18 @@ extern "C" int cmlpl_spectral_hidden_tc(const float* spectra, int64_t n, int num
                                                          static_cast<__half*>(h16));
   CMLPL_CHECK_LAUNCH("spectral_hidden");
   return CMLPL_OK;
+}
+
+extern "C" int cmlpl_spectral_hidden_tc(const float* spectra, int64_t n, int num_features, int num_classes, int w,
+                                        const void* packed, void* x16, void* h16, cmlpl_stream_t stream) {
+  return spectral_hidden_impl(spectra, -1, n, num_features, num_classes, w, nullptr, nullptr, packed, x16, h16, stream);
+}
+
+extern "C" int cmlpl_spectral_hidden_raw_tc(const void* raw, int dtype, int64_t n, int num_features, int num_classes, int w,
+                                            const float* mu, const float* inv_sigma, const void* packed, void* x16,
+                                            void* h16, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG((dtype == 0 || dtype == 1) && mu && inv_sigma, "spectral_hidden_raw_tc: bad args");
+  return spectral_hidden_impl(raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed, x16, h16, stream);
 }
 
 extern "C" int cmlpl_head_tc(const void* p2t, const void* h16, int64_t n, int num_features, int num_classes, int w,

@@ -62,6 +62,48 @@ conv0_map_kernel(const float* __restrict__ cube, int scene_rows, int cols, int s
   }
 }
 
+// conv0 map straight from the RAW cube: PCA projection, both z-scores and conv0 are per-pixel affine
+// maps, so they fold into one  F0 = Wf . (x - mu) + bf  with Wf = W0 . (U/s)^T  [64 x B].
+// thread = (padded pixel, 8 output channels); folded weights [B][64] in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv0_map_raw_kernel(const T* __restrict__ raw, int B, int scene_rows, int cols, int slab_row0, int w, int band_row0,
+                     int prow_n, int pcol_n, const float* __restrict__ wf, const float* __restrict__ bf,
+                     const float* __restrict__ mu, __half* __restrict__ f0pad) {
+  extern __shared__ __align__(16) float sm0[];              // wf [B][64] | mu [B] | bf [64]
+  float* ws = sm0; float* mus = sm0 + B * 64; float* bs = mus + B;
+  for (int i = threadIdx.x; i < B * 64; i += blockDim.x) ws[i] = wf[i];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) mus[i] = mu[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bf[threadIdx.x];
+  __syncthreads();
+  const int lo = window_lo(w);
+  const int64_t plane = int64_t(prow_n) * pcol_n;
+  const int64_t total = plane * 8;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    // consecutive threads -> the 8 channel groups of one pixel (they share the raw spectrum through L1)
+    const int g = int(t & 7);
+    const int64_t pp = t >> 3;
+    const int pr = int(pp / pcol_n), pc = int(pp - int64_t(pr) * pcol_n);
+    const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0;
+    const int sc = mirror_index(pc + lo, cols);
+    const T* src = raw + (int64_t(sr) * cols + sc) * B;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
+    for (int b = 0; b < B; ++b) {
+      const float xv = float(src[b]) - mus[b];
+      const float4 wa = *reinterpret_cast<const float4*>(&ws[b * 64 + g * 8]);
+      const float4 wb = *reinterpret_cast<const float4*>(&ws[b * 64 + g * 8 + 4]);
+      acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]); acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
+      acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]); acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(f0pad + (int64_t(g) * plane + pp) * 8) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
 // ------------------------------------------------------------------ classifier + argmax
 // one warp per pixel; lanes stride over the K = P*64 pooled features in 8-half chunks.
 template <int CMAX>
@@ -292,4 +334,64 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
   if (rc != CMLPL_OK) return rc;
   return cmlpl_classify_f16(wsb + ws.p2, reinterpret_cast<const float*>(wsb + ws.spe), n, num_features, num_classes,
                             w, packed, labels, logits, stream);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Scene inference from the RAW cube (uint16 / float32): the preprocessing of
+// tools/hyper_tools.py:285-292 is folded into the first kernels (no PCA cube / z-scored spectra in HBM).
+//   raw       [slab_rows*cols, B]  raw scene rows slab_row0..  (dtype 0 = uint16, 1 = float32)
+//   wf f32 [B][64], bf f32 [64]    conv0 folded with the PCA projection and both z-scores
+//   mu, inv_sigma f32 [B]          band means / 1/std (z-score of the spectral branch)
+extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows, int cols, int slab_row0, int slab_rows,
+                                     int num_features, int num_classes, int w, int band_row0, int band_rows,
+                                     const float* wf, const float* bf, const float* mu, const float* inv_sigma,
+                                     const void* packed, void* workspace, size_t workspace_bytes, uint8_t* labels,
+                                     float* logits, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(raw && wf && bf && mu && inv_sigma && packed && workspace && labels, "scene_infer_raw: null pointer");
+  CMLPL_CHECK_ARG(dtype == 0 || dtype == 1, "scene_infer_raw: dtype must be 0 (uint16) or 1 (float32)");
+  CMLPL_CHECK_ARG(w == 20, "scene_infer_raw: w=%d unsupported (tools/models.py:127 fixes w=20)", w);
+  CMLPL_CHECK_ARG(band_rows > 0 && cols > 0 && num_classes > 0 && num_features > 0, "scene_infer_raw: bad dims");
+  CMLPL_CHECK_ARG(use_tc_head(num_features, num_classes), "scene_infer_raw: needs <= 16 classes and <= 208 bands");
+  CMLPL_CHECK_ARG(w / 2 <= scene_rows && w / 2 <= cols, "scene_infer_raw: window larger than the scene");
+  CMLPL_CHECK_ARG(band_row0 >= 0 && band_row0 + band_rows <= scene_rows, "scene_infer_raw: band outside the scene");
+  const int a = band_row0 + window_lo(w), b = band_row0 + band_rows - 1 + window_lo(w) + w - 1;
+  int rmin = a < 0 ? 0 : a, rmax = b >= scene_rows ? scene_rows - 1 : b;
+  if (a < 0 && -a - 1 > rmax) rmax = -a - 1;
+  if (b >= scene_rows && 2 * scene_rows - 1 - b < rmin) rmin = 2 * scene_rows - 1 - b;
+  CMLPL_CHECK_ARG(rmin >= slab_row0 && rmax < slab_row0 + slab_rows && band_row0 >= slab_row0,
+                  "scene_infer_raw: slab rows [%d,%d) do not cover the band's halo [%d,%d]", slab_row0,
+                  slab_row0 + slab_rows, rmin, rmax);
+  const SceneWs ws = scene_ws(band_rows, cols, num_features, num_classes, w);
+  CMLPL_CHECK_ARG(workspace_bytes >= ws.total, "scene_infer_raw: workspace %zu < required %zu", workspace_bytes, ws.total);
+  unsigned char* wsb = static_cast<unsigned char*>(workspace);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t n = int64_t(band_rows) * cols;
+  const int prow_n = band_rows + w - 1, pcol_n = cols + w - 1;
+  {
+    const int64_t total = int64_t(prow_n) * pcol_n * 8;
+    int64_t grid = (total + 255) / 256; const int64_t cap = int64_t(sm_count()) * 8; if (grid > cap) grid = cap;
+    const size_t smem = sizeof(float) * (size_t(num_features) * 64 + num_features + 64);
+    if (dtype == 0) {
+      CMLPL_CUDA(cudaFuncSetAttribute(conv0_map_raw_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      conv0_map_raw_kernel<uint16_t><<<int(grid), 256, smem, s>>>(static_cast<const uint16_t*>(raw), num_features, scene_rows, cols,
+          slab_row0, w, band_row0, prow_n, pcol_n, wf, bf, mu, reinterpret_cast<__half*>(wsb + ws.f0pad));
+    } else {
+      CMLPL_CUDA(cudaFuncSetAttribute(conv0_map_raw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      conv0_map_raw_kernel<float><<<int(grid), 256, smem, s>>>(static_cast<const float*>(raw), num_features, scene_rows, cols,
+          slab_row0, w, band_row0, prow_n, pcol_n, wf, bf, mu, reinterpret_cast<__half*>(wsb + ws.f0pad));
+    }
+    CMLPL_CHECK_LAUNCH("conv0_map_raw");
+  }
+  const size_t esz = dtype == 0 ? 2 : 4;
+  const void* band_raw = static_cast<const unsigned char*>(raw) + size_t(band_row0 - slab_row0) * cols * num_features * esz;
+  int rc = cmlpl_spectral_hidden_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
+                                        wsb + ws.x16, wsb + ws.h16, stream);
+  if (rc != CMLPL_OK) return rc;
+  rc = cmlpl_conv1_scene_f16(wsb + ws.f0pad, cols, w, band_rows, packed, reinterpret_cast<float*>(wsb + ws.g),
+                             wsb + ws.pm, stream);
+  if (rc != CMLPL_OK) return rc;
+  rc = cmlpl_patch_conv2_f16_tiled(wsb + ws.pm, cols, w, band_rows, packed, wsb + ws.p2, stream);
+  if (rc != CMLPL_OK) return rc;
+  return cmlpl_head_tc(wsb + ws.p2, wsb + ws.h16, n, num_features, num_classes, w, packed, labels, logits, stream);
 }

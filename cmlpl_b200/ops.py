@@ -206,6 +206,44 @@ def scene_infer(cube, spectra, packed, num_classes: int, w: int = 20, band_row0:
     return (labels, logits) if want_logits else labels
 
 
+def scene_infer_raw(raw, folded, packed, num_classes: int, cols: int, w: int = 20, band_row0: int = 0,
+                    band_rows: int | None = None, scene_rows: int | None = None, slab_row0: int = 0,
+                    want_logits: bool = False, workspace: torch.Tensor | None = None,
+                    labels: torch.Tensor | None = None):
+    """hyper_tools.py:285-292 + :416-437 from the RAW cube: raw uint16/f32 [slab_rows*cols, B] (scene rows
+    slab_row0..), ``folded`` = Preproc.folded_conv0(...) (conv0 folded with PCA + z-scores; band mean / 1/std).
+    Neither the PCA cube nor the z-scored spectra are materialised."""
+    if not raw.is_cuda or not raw.is_contiguous():
+        raise _lib.CmlplError("raw must be a contiguous CUDA tensor (cmlpl_b200 has no CPU path)")
+    if raw.dtype == torch.uint16:
+        code = 0
+    elif raw.dtype == _f32:
+        code = 1
+    else:
+        raise _lib.CmlplError(f"raw scene must be uint16 or float32, got {raw.dtype}")
+    ns, B = raw.shape
+    if ns % cols:
+        raise _lib.CmlplError("raw rows are not a multiple of cols")
+    slab_rows = ns // cols
+    scene_rows = slab_rows if scene_rows is None else scene_rows
+    band_rows = scene_rows - band_row0 if band_rows is None else band_rows
+    n = band_rows * cols
+    for k in ("wf", "bf", "mu", "inv_sigma"):
+        _chk(folded[k], name=k)
+    if folded["wf"].shape != (B, 64):
+        raise _lib.CmlplError(f"folded conv0 weight must be [{B}, 64]")
+    if workspace is None:
+        workspace = scene_workspace(band_rows, cols, B, num_classes, w, raw.device)
+    if labels is None:
+        labels = torch.empty((n,), dtype=torch.uint8, device=raw.device)
+    logits = torch.empty((n, num_classes), dtype=_f32, device=raw.device) if want_logits else None
+    _lib.call("cmlpl_scene_infer_raw", raw.data_ptr(), code, scene_rows, cols, slab_row0, slab_rows, B, num_classes, w,
+              band_row0, band_rows, folded["wf"].data_ptr(), folded["bf"].data_ptr(), folded["mu"].data_ptr(),
+              folded["inv_sigma"].data_ptr(), packed.data_ptr(), workspace.data_ptr(), workspace.numel(),
+              labels.data_ptr(), _p(logits), _stream())
+    return (labels, logits) if want_logits else labels
+
+
 def argmax_u8(logits):
     _chk(logits, name="logits")
     n, c = logits.shape

@@ -29,6 +29,18 @@ class Preproc:
                          "Us": t(self.U / self.pca_sigma[None, :]), "shift": t(self.pca_mu / self.pca_sigma)}
         return self._dev
 
+    def folded_conv0(self, conv0_w, conv0_b, device):
+        """PCA projection, both z-scores and conv0 (models.py:102,132) are per-pixel affine maps of the raw
+        spectrum, so they fold into F0 = wf^T (x - mu) + bf.  Returns device f32 tensors
+        wf [B, 64], bf [64] (+ mu, inv_sigma [B]) for cmlpl_scene_infer_raw; folded in float64 on the host."""
+        W0 = conv0_w.detach().double().cpu().numpy().reshape(conv0_w.shape[0], -1)        # [64, n_PC]
+        b0 = conv0_b.detach().double().cpu().numpy()
+        Us = self.U / self.pca_sigma[None, :]                                              # [B, n_PC]
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+        d = self.device_params(device)
+        return {"wf": t(Us @ W0.T), "bf": t(b0 - W0 @ (self.pca_mu / self.pca_sigma)), "mu": d["mu"],
+                "inv_sigma": d["inv_sigma"]}
+
 
 def _dtype_code(x: torch.Tensor) -> int:
     if x.dtype == torch.uint16:

@@ -204,11 +204,13 @@ class StreamedScene:
 
 class StreamedRawScene:
     """Like StreamedScene, but from the RAW cube (uint16 / float32 [rows*cols, B], pinned host memory)
-    and a fitted ``cmlpl_b200.preprocess.Preproc``: each band's raw rows are copied on a side stream,
-    turned into the z-scored PCA cube rows and the z-scored spectra on device (cmlpl_preprocess_apply),
-    and fed to cmlpl_scene_infer -- 42.7 MB over PCIe for a PaviaU scene instead of 135 MB.  Two sets of
-    device buffers alternate between calls, so the copies of the next scene overlap the compute of the
-    current one when calls are issued back to back."""
+    and a fitted ``cmlpl_b200.preprocess.Preproc``: each band's raw rows are copied on a side stream and fed
+    to cmlpl_scene_infer_raw, whose first kernels apply the preprocessing folded into conv0 / the fp16
+    conversion of the spectra (``folded=`` from Preproc.folded_conv0; nothing preprocessed touches HBM) --
+    42.7 MB over PCIe for a PaviaU scene instead of 135 MB.  Without ``folded`` the rows go through
+    cmlpl_preprocess_apply + cmlpl_scene_infer (materialised PCA cube / spectra).  Two sets of device
+    buffers alternate between calls, so the copies of the next scene overlap the compute of the current one
+    when calls are issued back to back."""
 
     def __init__(self, preproc, scene_rows, cols, num_features, num_classes, w=20, nsplit=2, row0=0, rows=None,
                  raw_dtype=torch.uint16, device=None):
@@ -223,9 +225,8 @@ class StreamedRawScene:
         self.s1 = min(scene_rows, self.r1 + (w - lo - 1))
         ns = (self.s1 - self.s0) * cols
         n = (self.r1 - self.r0) * cols
-        self.sets = [dict(raw=torch.empty((ns, num_features), dtype=raw_dtype, device=dev),
-                          cube=torch.empty((self.s1 - self.s0, cols, 60), dtype=torch.float32, device=dev),
-                          spectra=torch.empty((ns, num_features), dtype=torch.float32, device=dev),
+        self._ns, self._dev = ns, dev
+        self.sets = [dict(raw=torch.empty((ns, num_features), dtype=raw_dtype, device=dev), cube=None, spectra=None,
                           labels=torch.empty((n,), dtype=torch.uint8, device=dev),
                           labels_host=torch.empty((n,), dtype=torch.uint8).pin_memory(),
                           done=torch.cuda.Event()) for _ in range(2)]
@@ -240,12 +241,15 @@ class StreamedRawScene:
     def labels_host(self):
         return self.sets[(self.calls - 1) & 1]["labels_host"]
 
-    def __call__(self, packed, raw_host, d2h=True):
+    def __call__(self, packed, raw_host, d2h=True, folded=None):
         """raw_host [(s1-s0)*cols, B] pinned: raw rows s0..s1 of the scene.  Returns uint8 labels of the band
         (the pinned host tensor of this call's buffer set when d2h, else the CUDA tensor)."""
         main = torch.cuda.current_stream()
         S, events = self.sets[self.calls & 1], self.events[self.calls & 1]
         self.calls += 1
+        if folded is None and S["cube"] is None:
+            S["cube"] = torch.empty((self.s1 - self.s0, self.C, 60), dtype=torch.float32, device=self._dev)
+            S["spectra"] = torch.empty((self._ns, self.B), dtype=torch.float32, device=self._dev)
         lo, C = self.w // 2, self.C
         self.copy_stream.wait_event(S["done"])               # the call two scenes ago has consumed this set
         copied, spans = self.s0, []
@@ -260,10 +264,14 @@ class StreamedRawScene:
                 ev.record(self.copy_stream)
         for (a, b), ev, (c0, c1) in zip(self.bands, events, spans):
             main.wait_event(ev)
+            qa, qb = (a - self.r0) * C, (b - self.r0) * C
+            if folded is not None:
+                ops.scene_infer_raw(S["raw"], folded, packed, self.K, C, self.w, band_row0=a, band_rows=b - a,
+                                    scene_rows=self.R, slab_row0=self.s0, workspace=self.ws, labels=S["labels"][qa:qb])
+                continue
             if c1 > c0:                                       # preprocess the rows that just arrived
                 pa, pb = (c0 - self.s0) * C, (c1 - self.s0) * C
                 self._pp_mod.apply(S["raw"][pa:pb], self.pp, cube=S["cube"].view(-1, 60)[pa:pb], spectra=S["spectra"][pa:pb])
-            qa, qb = (a - self.r0) * C, (b - self.r0) * C
             sa = (a - self.s0) * C
             ops.scene_infer(S["cube"], S["spectra"][sa:sa + (b - a) * C], packed, self.K, self.w, band_row0=a,
                             band_rows=b - a, scene_rows=self.R, slab_row0=self.s0, workspace=self.ws,

@@ -130,6 +130,20 @@ int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, int slab_row0
                       void* workspace, size_t workspace_bytes,
                       uint8_t* labels, float* logits, cmlpl_stream_t stream);
 
+/* The same from the RAW cube (dtype 0 = uint16, 1 = float32; <= 16 classes, <= 208 bands): the PCA
+ * projection and both z-scores of tools/hyper_tools.py:285-292 are folded into conv0
+ * (wf f32 [B][64] = (W0 . (U/s)^T)^T, bf f32 [64] = b0 - W0 . m/s) and into the fp16 conversion of the
+ * spectral branch (mu, inv_sigma f32 [B]); neither the PCA cube nor the z-scored spectra touch HBM.
+ * raw [slab_rows*cols, B] holds scene rows slab_row0.. (halo included, like `cube` above). */
+int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows, int cols, int slab_row0, int slab_rows,
+                          int num_features, int num_classes, int w, int band_row0, int band_rows,
+                          const float* wf, const float* bf, const float* mu, const float* inv_sigma,
+                          const void* packed, void* workspace, size_t workspace_bytes,
+                          uint8_t* labels, float* logits, cmlpl_stream_t stream);
+int cmlpl_spectral_hidden_raw_tc(const void* raw, int dtype, int64_t n, int num_features, int num_classes, int w,
+                                 const float* mu, const float* inv_sigma, const void* packed, void* x16,
+                                 void* h16, cmlpl_stream_t stream);
+
 /* Individual stages of cmlpl_scene_infer (exposed for tests / profiling). */
 int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows,
                         int w, int band_row0, int band_rows, const void* packed,

@@ -350,3 +350,50 @@ def test_streamed_raw_scene_equals_preprocessed_path(dev):
         got = st(packed, raw_host)
         torch.cuda.synchronize()
         assert torch.equal(got, ref.cpu())
+    # folded entry point (preprocessing inside conv0 / the fp16 conversion): same labels as its own one-shot call,
+    # band splits bit-identical
+    folded = pp.folded_conv0(sd["conv0.weight"], sd["conv0.bias"], dev)
+    ref_f = ops.scene_infer_raw(raw_host.to(dev), folded, packed, K, C, 20)
+    assert (ref_f == ref).float().mean() >= 0.99
+    for nsplit in (1, 3):
+        st = StreamedRawScene(pp, R, C, B, K, 20, nsplit=nsplit)
+        for _ in range(3):                                    # alternating buffer sets
+            got = st(packed, raw_host, folded=folded)
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref_f.cpu())
+
+
+@pytest.mark.parametrize("B,K,dtype", [(103, 9, "u16"), (200, 16, "f32")])
+def test_scene_infer_raw_folded_matches_oracle(dev, B, K, dtype):
+    """cmlpl_scene_infer_raw (PCA + z-scores folded into conv0 and into the spectral fp16 conversion) against the
+    oracle's float64 preprocessing (hyper_tools.py:285-292) + test_whole on the same raw scene."""
+    from cmlpl_b200 import ops, preprocess, synth
+    R, C = 41, 37
+    cube_u16, _ = synth.synth_scene(R, C, B, K, seed=7)
+    ref_cube, ref_spec = O.preprocess(cube_u16, 60)
+    raw = torch.from_numpy(cube_u16.reshape(-1, B).copy()).to(dev)
+    pp = preprocess.fit(raw, 60)
+    cube, _ = preprocess.apply(raw, pp, want_spectra=False)
+    # singular vectors are defined up to sign: adopt the oracle's signs before folding
+    sgn = np.sign((cube.cpu().numpy().reshape(R, C, 60) * ref_cube).sum((0, 1)))
+    pp.U = pp.U * sgn[None, :]
+    pp._dev = None
+    torch.manual_seed(21)
+    sd = O.basenet2_init(B, K)
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    packed = ops.pack_basenet2(sdd, B, K, 20)
+    folded = pp.folded_conv0(sd["conv0.weight"], sd["conv0.bias"], dev)
+    raw_in = raw if dtype == "u16" else raw.float()
+    labels, logits = ops.scene_infer_raw(raw_in, folded, packed, K, C, 20, want_logits=True)
+    lab_ref, log_ref = O.test_whole(sd, ref_cube.astype(np.float32), ref_spec.astype(np.float32), 20, return_logits=True)
+    assert rel(logits.cpu(), log_ref) < 1e-3
+    lab = labels.cpu().numpy()
+    assert np.array_equal(lab, logits.cpu().numpy().argmax(1))
+    diff = lab != lab_ref
+    srt = np.sort(log_ref, 1)
+    assert np.all((srt[diff, -1] - srt[diff, -2]) <= 2e-3 * np.abs(log_ref).max())
+    # a band with its halo slab gives the same bits as the full call
+    r0, r1, s0, s1 = O.band_rows(R, 3, 1, 20)
+    l2, z2 = ops.scene_infer_raw(raw_in[s0 * C:s1 * C].contiguous(), folded, packed, K, C, 20, band_row0=r0,
+                                 band_rows=r1 - r0, scene_rows=R, slab_row0=s0, want_logits=True)
+    assert torch.equal(l2, labels[r0 * C:r1 * C]) and torch.equal(z2, logits[r0 * C:r1 * C])
