@@ -42,6 +42,12 @@ SIGNATURES = {
     "cmlpl_patch_cnn_f16_tiled": (I, [P, I, I, I, P, P, P]),
     "cmlpl_conv1_scene_f16": (I, [P, I, I, I, P, P, P, P]),
     "cmlpl_patch_conv2_f16_tiled": (I, [P, I, I, I, P, P, P]),
+    "cmlpl_scene_workspace_layout": (I, [I, I, I, I, I, P]),
+    "cmlpl_conv1_scene_variants_f32": (I, [P, I, I, I, P, P, P]),
+    "cmlpl_conv1_scene_planes_f16": (I, [P, I, I, I, P, P, P, P]),
+    "cmlpl_conv2_scene_f16": (I, [P, I, I, I, P, P, P]),
+    "cmlpl_pool2_cls_f16": (I, [P, I, I, I, I, I, P, P, P]),
+    "cmlpl_head_lmap_tc": (I, [P, P, I, I, I, I, I, P, P, P, P]),
     "cmlpl_debug_patch_conv2_trace": (I, [P, I, I, I, P, P, P, P]),
     "cmlpl_spectral_hidden_tc": (I, [P, L, I, I, I, P, P, P, P]),
     "cmlpl_head_tc": (I, [P, P, L, I, I, I, P, P, P, P]),

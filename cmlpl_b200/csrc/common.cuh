@@ -60,6 +60,25 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- class bookkeeping of the dense (scene-level) conv2 / pool / classifier path (conv2_scene_sm100.cu) ----
+// pooled row/column index that represents conv2 class k (0: i=0, 1: i=1, 2: i=2..7, 3: i=8, 4: i=9) of a
+// 10-wide pooled window, and the PM border class (top/mid/bot) of pooled index i
+__host__ __device__ constexpr int rep_of(int k) { return k == 0 ? 0 : (k == 1 ? 1 : (k == 2 ? 4 : (k == 3 ? 8 : 9))); }
+__host__ __device__ constexpr int cls_of(int i) { return i == 0 ? 0 : (i == 9 ? 2 : 1); }
+// block b = Alpha*3 + Beta: number of I / J values, first map index, Y classes per (Alpha,u)
+__host__ __device__ constexpr int blk_n(int cls) { return cls == 1 ? 3 : 1; }
+__host__ __device__ constexpr int blk_first(int cls) { return cls == 0 ? 0 : (cls == 1 ? 1 : 4); }
+__host__ __device__ constexpr int blk_start(int b) {
+  return b == 0 ? 0 : b == 1 ? 1 : b == 2 ? 4 : b == 3 ? 5 : b == 4 ? 8 : b == 5 ? 17 : b == 6 ? 20 : b == 7 ? 21 : 24;
+}
+__host__ __device__ constexpr int ycls(int cls, int u) { return cls == 0 ? u : (cls == 1 ? 2 : 3 + u); }
+// map index of pooled cell (I, J) in the block-ordered list of 25 (shared with pack.cu / head_sm100.cu)
+__host__ __device__ constexpr int lmap_index(int I, int J) {
+  const int A = I == 0 ? 0 : (I == 4 ? 2 : 1), B = J == 0 ? 0 : (J == 4 ? 2 : 1);
+  return blk_start(A * 3 + B) + (I - blk_first(A)) * blk_n(B) + (J - blk_first(B));
+}
+
+
 // ---- packed BaseNet2 weights (layout shared by pack.cu and the scene kernels) ----
 // All offsets in bytes from the start of the packed buffer, 256-B aligned.
 struct PackedLayout {
@@ -76,6 +95,8 @@ struct PackedLayout {
   size_t bc;      // f32 [C] (padded to 16)
   size_t w1s;     // f16 [4 n-tiles][KC][256][8]  feat_spe weight, UMMA B operand tiles (K padded to 16)
   size_t wc16;    // f16 [(P*8 + 128) k-chunks][16 classes][8]  classifier over [conv(pos,ch) | spectral]
+  size_t wcq;     // f16 per (Alpha,Beta) block [8 k-chunks][N = maps*16 rows = map*16+cls][8]: 0.25 * conv classifier
+                  //     columns of pooled cell (I,J), maps in lmap_index order (w = 20 only; pool2_cls_kernel)
   size_t total;
   int conv_pos;   // P = (w/4)^2 pooled positions
   int kc_spe_in;  // KC = ceil(B/16)*2: 16-byte K-chunks of the spectral input
@@ -102,6 +123,7 @@ __host__ __device__ inline PackedLayout packed_layout(int B, int C, int w) {
   L.kc_spe_in = ((B + 15) / 16) * 2;
   L.w1s = o; o = align256(o + size_t(4) * L.kc_spe_in * 256 * 16);
   L.wc16 = o; o = align256(o + size_t(L.conv_pos * 8 + 128) * 16 * 16);
+  L.wcq = o; o = align256(o + size_t(400) * 128);
   L.total = o;
   return L;
 }

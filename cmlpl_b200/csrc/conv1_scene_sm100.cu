@@ -33,10 +33,6 @@ constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
 enum { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, D_FULL0, D_FULL1, D_EMPTY0, D_EMPTY1 };
 }  // namespace c1s
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
-}
-
 // f0: f16 chunk-planar [8][PR][PC][8];  g: f32 [9 variants = a*3+b][PR*PC][64]
 __global__ void __launch_bounds__(c1s::kThreads, 1)
 conv1_scene_kernel(const __half* __restrict__ f0, int PR, int PC, const unsigned char* __restrict__ w1p,
@@ -241,9 +237,9 @@ __global__ void pool1_scene_kernel(const float* __restrict__ g, int PR, int PC, 
 
 using namespace cmlpl;
 
-extern "C" int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
-                                     void* pm, cmlpl_stream_t stream) {
-  CMLPL_CHECK_ARG(f0pad && packed && g && pm, "conv1_scene: null pointer");
+extern "C" int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                                              float* g, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(f0pad && packed && g, "conv1_scene: null pointer");
   CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "conv1_scene: bad dims (w must be 20)");
   const int PR = band_rows + w - 1, PC = cols + w - 1;
   const PackedLayout L = packed_layout(1, 1, w);
@@ -255,9 +251,18 @@ extern "C" int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int ban
   conv1_scene_kernel<<<grid, c1s::kThreads, c1s::SMEM, s>>>(static_cast<const __half*>(f0pad), PR, PC, pk + L.w1,
                                                             reinterpret_cast<const float*>(pk + L.b1), g);
   CMLPL_CHECK_LAUNCH("conv1_scene");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
+                                     void* pm, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(pm, "conv1_scene: null pointer");
+  const int rc = cmlpl_conv1_scene_variants_f32(f0pad, cols, w, band_rows, packed, g, stream);
+  if (rc != CMLPL_OK) return rc;
+  const int PR = band_rows + w - 1, PC = cols + w - 1;
   const int64_t total = int64_t(PR) * PC * 8;
   int64_t pg = (total + 255) / 256; const int64_t cap = int64_t(sm_count()) * 16; if (pg > cap) pg = cap;
-  pool1_scene_kernel<<<int(pg), 256, 0, s>>>(g, PR, PC, static_cast<__half*>(pm));
+  pool1_scene_kernel<<<int(pg), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, PR, PC, static_cast<__half*>(pm));
   CMLPL_CHECK_LAUNCH("pool1_scene");
   return CMLPL_OK;
 }

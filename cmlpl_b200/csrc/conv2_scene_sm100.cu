@@ -1,0 +1,487 @@
+// Scene-level conv2 + pool + classifier with exact compute sharing (second half).
+//
+// After conv1_scene the pooled conv1 window of pixel (r,c) is  PM[A(i)][B(j)][r+2i, c+2j]  (i,j = 0..9,
+// A/B = top/mid/bot border class of the pooled row/column).  Everything downstream of it
+// (tools/models.py:137-150: conv2 3x3 with zero padding at the PATCH border, +residual, ReLU, 2x2
+// average pool, the conv columns of the classifier) again depends only on the scene position and on
+// which border the patch cuts, so it is evaluated ONCE per scene position instead of once per pixel:
+//
+//   * positions (r+2i, c+2j) keep the parity of (r,c): the padded map splits into 4 PARITY PLANES
+//     (y' = pr>>1, x' = pc>>1) on which conv2 is a plain 3x3 convolution and the pool a 2x2 window;
+//   * conv2 output row i of a patch has row class rho(i) in {0: i=0, 1: i=1, 2: i=2..7, 3: i=8, 4: i=9}
+//     (which taps the border drops AND which PM row class each remaining tap reads); same for columns:
+//       Y[rho][kap][y',x'] = relu(b2 + PM[A(rho)][B(kap)][y',x']
+//                                 + sum_{di in S(rho), dj in S(kap)} W2[di,dj] . PM[A(rho,di)][B(kap,dj)][y'+di, x'+dj])
+//     -> conv2_scene_kernel: 25 variants per position, 169 tap products instead of 900 per pixel;
+//   * pool + classifier are linear after the ReLU:  logit_conv(r,c) = sum_{I,J} L[I][J][r'+2I, c'+2J] with
+//       L[I][J][y',x'] = sum_{u,v in {0,1}} (Wc[I,J]/4) . Y[rho(2I+u)][kap(2J+v)][y'+u, x'+v]
+//     -> pool2_cls_kernel: the 2x2 pool is four accumulating tcgen05.mma whose A descriptors are shifted
+//        by (u,v) inside the tile; 25 maps of 16 class partials per position;
+//   * the head (head_sm100.cu) adds the 25 gathered partials of a pixel to its spectral logits.
+//
+// Identical math up to fp32 summation order; per PaviaU scene conv2 executes 0.32 TFLOP instead of 1.53.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cmlpl {
+
+// 2x2 average pools of the conv1 variants (see pool1_scene_kernel) written as PARITY PLANES, chunk-planar:
+//   pmq f16 [9 variants][4 planes = (pr&1)*2 + (pc&1)][8 chunks][PR2][PC2][8 channels]
+// entries without a pooled cell (pr >= PR-1 or pc >= PC-1) are zero.
+__global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC, int PR2, int PC2,
+                                    __half* __restrict__ pmq) {
+  const int64_t plane = int64_t(PR) * PC;
+  const int64_t psz = int64_t(PR2) * PC2;
+  const int64_t total = 4 * psz * 8;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int x2 = int(t % PC2);
+    int64_t r = t / PC2;
+    const int ch = int(r & 7); r >>= 3;
+    const int y2 = int(r % PR2), pl = int(r / PR2);
+    const int pr = 2 * y2 + (pl >> 1), pc = 2 * x2 + (pl & 1);
+    const bool valid = pr < PR - 1 && pc < PC - 1;
+    const int64_t pos = int64_t(pr) * PC + pc;
+#pragma unroll
+    for (int A = 0; A < 3; ++A) {
+      const int a0 = A == 0 ? 0 : 1, a1 = A == 2 ? 2 : 1;
+#pragma unroll
+      for (int B = 0; B < 3; ++B) {
+        const int b0 = B == 0 ? 0 : 1, b1 = B == 2 ? 2 : 1;
+        __half2 h[4];
+        if (valid) {
+          const float4* p00 = reinterpret_cast<const float4*>(g + (int64_t(a0 * 3 + b0) * plane + pos) * 64 + ch * 8);
+          const float4* p01 = reinterpret_cast<const float4*>(g + (int64_t(a0 * 3 + b1) * plane + pos + 1) * 64 + ch * 8);
+          const float4* p10 = reinterpret_cast<const float4*>(g + (int64_t(a1 * 3 + b0) * plane + pos + PC) * 64 + ch * 8);
+          const float4* p11 = reinterpret_cast<const float4*>(g + (int64_t(a1 * 3 + b1) * plane + pos + PC + 1) * 64 + ch * 8);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 x00 = __ldg(p00 + q), x01 = __ldg(p01 + q), x10 = __ldg(p10 + q), x11 = __ldg(p11 + q);
+            h[2 * q] = __floats2half2_rn(((x00.x + x10.x) + (x01.x + x11.x)) * 0.25f, ((x00.y + x10.y) + (x01.y + x11.y)) * 0.25f);
+            h[2 * q + 1] = __floats2half2_rn(((x00.z + x10.z) + (x01.z + x11.z)) * 0.25f, ((x00.w + x10.w) + (x01.w + x11.w)) * 0.25f);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(0.f, 0.f);
+        }
+        *reinterpret_cast<uint4*>(pmq + ((int64_t((A * 3 + B) * 4 + pl) * 8 + ch) * psz + int64_t(y2) * PC2 + x2) * 8) =
+            *reinterpret_cast<uint4*>(h);
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// conv2_scene_kernel: persistent, warp-specialised tcgen05 implicit GEMM over 4x30-position tiles of a
+// parity plane (M = 128 rows = 4 rows x 32 columns incl. one halo column each side; taps = A-descriptor
+// offsets in zero-haloed row-major tiles, exactly like conv1_scene_kernel).  Per tile the nine PM
+// variant tiles are loaded once, as three "slabs" of 3 row classes x one column class:
+//     slab X <- left, slab M <- mid   : column classes kap = 0, 1
+//                        (mid only)    : kap = 2
+//     slab X <- right                  : kap = 3, 4
+// and every (rho, kap) variant accumulates its <= 9 taps into its own 64-column TMEM slot (ring of 8), so
+// the epilogue (bias + residual + ReLU -> fp16) of one variant overlaps the MMAs of the next ones.
+namespace c2s {
+constexpr int TH = 4, TP = 32, TW = 30;
+constexpr int ENT = 1 + (TH + 2) * TP + 1;           // 194 entries per 16-byte chunk plane
+constexpr int CH = ENT * 16 + 16;                    // bytes between chunk planes (+16: bank spread)
+constexpr int TBYTES = 8 * CH;                       // one PM variant tile
+constexpr int WBYTES = 3 * 8 * 192 * 16;             // 73 728
+constexpr int S_W = 0, S_T = WBYTES, S_BIAS = S_T + 6 * TBYTES, S_BAR = S_BIAS + 256, S_TMEM = S_BAR + 256;
+constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
+constexpr int kEpi = 256, kLoad = 128, kThreads = kEpi + kLoad + 32;
+constexpr int kMmaWarp = (kEpi + kLoad) / 32;
+constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
+constexpr int kSlabItems = 3 * (TH + 2) * TP * 8;    // 16-byte copies per slab
+enum { XF = 0, MF, XE, ME, DF0 = 4, DE0 = 12 };
+static_assert(SMEM <= 232448, "conv2_scene: shared memory over the 227 KB limit");
+
+// all taps of variant (RHO, KAP) into TMEM columns [d, d+64); t_lo / w_lo = low descriptor words of tile 0 /
+// the weight block of dx = 0.  Every offset is an immediate.
+template <int RHO, int KAP>
+__device__ __forceinline__ void issue_variant(uint32_t d, uint32_t t_lo, uint32_t w_lo) {
+  constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;   // SBO = 128 B, version 1
+  constexpr uint32_t kI64 = make_idesc_f16(128, 64);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int i2 = rep_of(RHO) + dy - 1;
+    if (i2 < 0 || i2 > 9) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int j2 = rep_of(KAP) + dx - 1;
+      if (j2 < 0 || j2 > 9) continue;
+      const int tile = (cls_of(j2) == 1 ? 3 : 0) + cls_of(i2);     // slab M holds the mid column class
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a = t_lo + uint32_t((tile * TBYTES + (dy * TP + dx) * 16 + ks * 2 * CH) / 16);
+        const uint32_t b = w_lo + uint32_t((dx * kWDx + ks * 2 * kWLbo) / 16) + uint32_t((2 - dy) * 64);
+        umma_f16(d, kHi | uint64_t(a), kHi | uint64_t(b), kI64, acc);
+        acc = 1;
+      }
+    }
+  }
+}
+}  // namespace c2s
+
+// pmq f16 [9][4][8][PR2][PC2][8];  yq f16 [25 = rho*5+kap][4][8][PR2][PC2][8]
+__global__ void __launch_bounds__(c2s::kThreads, 1)
+conv2_scene_kernel(const __half* __restrict__ pmq, int PR2, int PC2, const unsigned char* __restrict__ w2p,
+                   const float* __restrict__ b2g, __half* __restrict__ yq) {
+  using namespace c2s;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + S_BAR;
+  float* sbias = reinterpret_cast<float*>(smem + S_BIAS);
+  const int tiles_c = (PC2 + TW - 1) / TW, tiles_r = (PR2 + TH - 1) / TH;
+  const int tiles_p = tiles_r * tiles_c, ntiles = 4 * tiles_p;
+  const int64_t psz = int64_t(PR2) * PC2;
+
+  {
+    const uint4* gw = reinterpret_cast<const uint4*>(w2p);
+    uint4* sw = reinterpret_cast<uint4*>(smem + S_W);
+    for (int i = tid; i < WBYTES / 16; i += kThreads) sw[i] = __ldg(gw + i);
+    uint4* z = reinterpret_cast<uint4*>(smem + S_T);
+    for (int i = tid; i < 6 * TBYTES / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid < 64) sbias[tid] = b2g[tid];
+  if (tid == 0) {
+    mbar_init(bars + 8 * XF, kLoad); mbar_init(bars + 8 * MF, kLoad);
+    mbar_init(bars + 8 * XE, 1); mbar_init(bars + 8 * ME, 1);
+    for (int s = 0; s < 8; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi); }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
+
+  if (warp >= 8 && warp < kMmaWarp) {
+    // ================================================================ loaders
+    const int lt = tid - kEpi;
+    uint32_t fx = 0, fm = 0;                                   // fills of slab X / slab M so far
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int pl = t / tiles_p, tt = t - pl * tiles_p;
+      const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
+      const int y0 = tr * TH - 1, x0 = tc * TW - 1;            // plane coords of entry (ry=0, rx=0)
+#pragma unroll 1
+      for (int step = 0; step < 3; ++step) {                   // left -> X, mid -> M, right -> X
+        const int slab = step == 1 ? 1 : 0, bcls = step;
+        const uint32_t k = slab ? fm : fx;
+        mbar_wait(bars + 8 * (slab ? ME : XE), (k & 1) ^ 1, 61);
+        for (int it = lt; it < kSlabItems; it += kLoad) {
+          const int rx = it & 31, ch = (it >> 5) & 7, q = it >> 8;
+          const int a = q / (TH + 2), ry = q - a * (TH + 2);
+          const int y = y0 + ry, x = x0 + rx;
+          const bool in = y >= 0 && y < PR2 && x >= 0 && x < PC2;
+          const __half* src = pmq + ((int64_t((a * 3 + bcls) * 4 + pl) * 8 + ch) * psz + (in ? int64_t(y) * PC2 + x : 0)) * 8;
+          cp_async16_zfill(sbase + S_T + (slab * 3 + a) * TBYTES + ch * CH + (1 + ry * TP + rx) * 16, src, in ? 16u : 0u);
+        }
+        cp_async_wait_all();
+        fence_proxy_async();
+        mbar_arrive(bars + 8 * (slab ? MF : XF));
+        if (slab) ++fm; else ++fx;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA issuer
+    if (tmem != 0) { printf("conv2_scene: unexpected TMEM base %u\n", tmem); __trap(); }
+    const uint32_t t_lo = ((sbase + S_T) >> 4) | (uint32_t(CH >> 4) << 16);
+    const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
+    uint32_t fx = 0, fm = 0, vc = 0;                           // slab fills consumed, variants issued
+#define C2S_VARIANT(RHO, KAP)                                                        \
+    do {                                                                             \
+      const uint32_t slot = vc & 7;                                                  \
+      mbar_wait(bars + 8 * (DE0 + slot), ((vc >> 3) & 1) ^ 1, 63);                   \
+      tc_fence_after();                                                              \
+      if (elect_one_sync()) {                                                        \
+        issue_variant<RHO, KAP>(slot * 64, t_lo, w_lo);                              \
+        umma_commit(bars + 8 * (DF0 + slot));                                        \
+      }                                                                              \
+      __syncwarp();                                                                  \
+      ++vc;                                                                          \
+    } while (0)
+#define C2S_COLUMN(KAP) C2S_VARIANT(0, KAP); C2S_VARIANT(1, KAP); C2S_VARIANT(2, KAP); C2S_VARIANT(3, KAP); C2S_VARIANT(4, KAP)
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(bars + 8 * XF, fx & 1, 62); ++fx;              // left
+      mbar_wait(bars + 8 * MF, fm & 1, 62); ++fm;              // mid
+      tc_fence_after();
+      C2S_COLUMN(0);
+      C2S_COLUMN(1);
+      if (elect_one_sync()) umma_commit(bars + 8 * XE);        // left tiles consumed
+      __syncwarp();
+      C2S_COLUMN(2);
+      mbar_wait(bars + 8 * XF, fx & 1, 62); ++fx;              // right
+      tc_fence_after();
+      C2S_COLUMN(3);
+      C2S_COLUMN(4);
+      if (elect_one_sync()) { umma_commit(bars + 8 * XE); umma_commit(bars + 8 * ME); }
+      __syncwarp();
+    }
+#undef C2S_COLUMN
+#undef C2S_VARIANT
+  } else {
+    // ================================================================ epilogue (warps 0-7)
+    const int L = (warp & 3) * 32 + lane, chalf = warp >> 2;
+    const uint32_t lane_addr = (uint32_t((warp & 3) * 32) << 16) + chalf * 32;
+    const int ty = L >> 5, tx = L & 31;
+    uint32_t vc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int pl = t / tiles_p, tt = t - pl * tiles_p;
+      const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
+      const int y = tr * TH + ty, x = tc * TW + tx - 1;
+      const bool valid = tx >= 1 && tx <= TW && y < PR2 && x < PC2;
+      const int64_t pos = valid ? int64_t(y) * PC2 + x : 0;
+#pragma unroll 1
+      for (int kap = 0; kap < 5; ++kap) {
+#pragma unroll 1
+        for (int rho = 0; rho < 5; ++rho, ++vc) {
+          const uint32_t slot = vc & 7;
+          // residual = centre cell PM[A(rho)][B(kap)][y,x] (L2-resident), issued before the wait
+          const int rv = cls_of(rep_of(rho)) * 3 + cls_of(rep_of(kap));
+          const __half* rp = pmq + ((int64_t(rv * 4 + pl) * 8 + chalf * 4) * psz + pos) * 8;
+          uint4 res[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) res[k] = valid ? __ldg(reinterpret_cast<const uint4*>(rp + int64_t(k) * psz * 8)) : make_uint4(0, 0, 0, 0);
+          mbar_wait(bars + 8 * (DF0 + slot), (vc >> 3) & 1, 64);
+          tc_fence_after();
+          float v0[16], v1[16];
+          tmem_ld16(lane_addr + slot * 64, v0);
+          tmem_ld16(lane_addr + slot * 64 + 16, v1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bars + 8 * (DE0 + slot));
+          if (valid) {
+            __half* dst = yq + ((int64_t((rho * 5 + kap) * 4 + pl) * 8 + chalf * 4) * psz + pos) * 8;
+            const float* bb = sbias + chalf * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __half2* hr = reinterpret_cast<const __half2*>(&res[k]);
+              const float* v = k < 2 ? v0 + k * 8 : v1 + (k - 2) * 8;
+              __half2 h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(hr[e]);
+                h[e] = __floats2half2_rn(fmaxf(v[2 * e] + (f.x + bb[k * 8 + 2 * e]), 0.f),
+                                         fmaxf(v[2 * e + 1] + (f.y + bb[k * 8 + 2 * e + 1]), 0.f));
+              }
+              *reinterpret_cast<uint4*>(dst + int64_t(k) * psz * 8) = *reinterpret_cast<uint4*>(h);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// =================================================================================================
+// pool2_cls_kernel: L[m][y',x'][cls] = sum_{u,v} (Wc[I,J]/4) . Y[rho(2I+u)][kap(2J+v)][y'+u, x'+v]
+// The 25 (I,J) maps are grouped in 9 blocks by the pooled border class (Alpha, Beta) of (I, J)
+// (Alpha = 0: I=0, 1: I=1..3, 2: I=4): all maps of a block read the same <= 4 Y variants, so a block is
+// 4 (u,v) x 4 k-steps tcgen05.mma with M = 128 positions, N = 16 classes x maps of the block (16/48/144),
+// accumulating into the block's TMEM columns; the (u,v) shift is an A-descriptor offset in the tile.
+namespace p2c {
+constexpr int TH = 4, TP = 32, TW = 31;              // outputs valid for tx = 0..30 (tx+1 must be in the tile)
+constexpr int ENT = (TH + 1) * TP + 2;               // 162 entries per chunk plane
+constexpr int CH = ENT * 16 + 16;
+constexpr int TBYTES = 8 * CH;                       // 20 864
+constexpr int NSLOT = 4, NSTAGE = 2;
+constexpr int WBYTES = 400 * 128;                    // 25 maps x 16 classes x 64 channels, f16
+constexpr int S_W = 0, S_T = WBYTES, S_BAR = S_T + NSTAGE * NSLOT * TBYTES, S_TMEM = S_BAR + 128;
+constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
+constexpr int kEpi = 256, kLoad = 128, kThreads = kEpi + kLoad + 32;
+constexpr int kMmaWarp = (kEpi + kLoad) / 32;
+constexpr int kTileItems = (TH + 1) * TP * 8;        // 16-byte copies per Y variant tile
+enum { F0 = 0, E0 = NSTAGE, DFULL = 2 * NSTAGE, DEMPTY };
+static_assert(SMEM <= 232448, "pool2_cls: shared memory over the 227 KB limit");
+}  // namespace p2c
+
+// yq f16 [25][4][8][PR2][PC2][8];  wcq f16 per block [8 kchunks][N rows = map*16 + cls][8];
+// lmap f32 [4][PR2][PC2][25][16]
+__global__ void __launch_bounds__(p2c::kThreads, 1)
+pool2_cls_kernel(const __half* __restrict__ yq, int PR2, int PC2, const unsigned char* __restrict__ wcq,
+                 float* __restrict__ lmap) {
+  using namespace p2c;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + S_BAR;
+  const int tiles_c = (PC2 + TW - 1) / TW, tiles_r = (PR2 + TH - 1) / TH;
+  const int tiles_p = tiles_r * tiles_c, ntiles = 4 * tiles_p;
+  const int64_t psz = int64_t(PR2) * PC2;
+
+  {
+    const uint4* gw = reinterpret_cast<const uint4*>(wcq);
+    uint4* sw = reinterpret_cast<uint4*>(smem + S_W);
+    for (int i = tid; i < WBYTES / 16; i += kThreads) sw[i] = __ldg(gw + i);
+    uint4* z = reinterpret_cast<uint4*>(smem + S_T);
+    for (int i = tid; i < NSTAGE * NSLOT * TBYTES / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bars + 8 * (F0 + s), kLoad); mbar_init(bars + 8 * (E0 + s), 1); }
+    mbar_init(bars + 8 * DFULL, 1); mbar_init(bars + 8 * DEMPTY, kEpi);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
+
+  if (warp >= 8 && warp < kMmaWarp) {
+    // ================================================================ loaders
+    const int lt = tid - kEpi;
+    uint32_t bc = 0;                                           // block stages filled so far
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int pl = t / tiles_p, tt = t - pl * tiles_p;
+      const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
+      const int y0 = tr * TH, x0 = tc * TW;
+#pragma unroll 1
+      for (int b = 0; b < 9; ++b, ++bc) {
+        const int Al = b / 3, Be = b - Al * 3;
+        const int nr = Al == 1 ? 1 : 2, nk = Be == 1 ? 1 : 2;
+        const uint32_t stage = bc & 1;
+        mbar_wait(bars + 8 * (E0 + stage), ((bc >> 1) & 1) ^ 1, 71);
+        for (int it = lt; it < nr * nk * kTileItems; it += kLoad) {
+          const int q = it / kTileItems, e = it - q * kTileItems;
+          const int su = q / nk, sv = q - su * nk;
+          const int rx = e & 31, ch = (e >> 5) & 7, ry = e >> 8;
+          const int var = ycls(Al, su) * 5 + ycls(Be, sv);
+          const int y = y0 + ry, x = x0 + rx;
+          const bool in = y < PR2 && x < PC2;
+          const __half* src = yq + ((int64_t(var * 4 + pl) * 8 + ch) * psz + (in ? int64_t(y) * PC2 + x : 0)) * 8;
+          cp_async16_zfill(sbase + S_T + (stage * NSLOT + su * 2 + sv) * TBYTES + ch * CH + (ry * TP + rx) * 16, src,
+                           in ? 16u : 0u);
+        }
+        cp_async_wait_all();
+        fence_proxy_async();
+        mbar_arrive(bars + 8 * (F0 + stage));
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA issuer
+    if (tmem != 0) { printf("pool2_cls: unexpected TMEM base %u\n", tmem); __trap(); }
+    constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
+    uint32_t bc = 0, tj = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tj) {
+      mbar_wait(bars + 8 * DEMPTY, (tj & 1) ^ 1, 72);          // epilogue of the previous tile has drained TMEM
+      tc_fence_after();
+#pragma unroll
+      for (int b = 0; b < 9; ++b, ++bc) {
+        const int Al = b / 3, Be = b % 3;
+        const int N = blk_n(Al) * blk_n(Be) * 16;
+        const uint32_t stage = bc & 1;
+        mbar_wait(bars + 8 * (F0 + stage), (bc >> 1) & 1, 73);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t idesc = make_idesc_f16(128, N);
+          const uint32_t t_lo = ((sbase + S_T + stage * NSLOT * TBYTES) >> 4) | (uint32_t(CH >> 4) << 16);
+          const uint32_t w_lo = ((sbase + S_W + blk_start(b) * 16 * 128) >> 4) | (uint32_t((N * 16) >> 4) << 16);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const int slot = (Al == 1 ? 0 : u) * 2 + (Be == 1 ? 0 : v);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t a = t_lo + uint32_t((slot * TBYTES + (u * TP + v) * 16 + ks * 2 * CH) / 16);
+                const uint32_t bw = w_lo + uint32_t((ks * 2 * N * 16) / 16);
+                umma_f16(uint32_t(blk_start(b) * 16), kHi | uint64_t(a), kHi | uint64_t(bw), idesc, (u | v | ks) ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(bars + 8 * (E0 + stage));
+          if (b == 8) umma_commit(bars + 8 * DFULL);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 0-7)
+    const int L = (warp & 3) * 32 + lane, half = warp >> 2;
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const int ty = L >> 5, tx = L & 31;
+    const int m0 = half ? 13 : 0, m1 = half ? 25 : 13;
+    uint32_t tj = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tj) {
+      const int pl = t / tiles_p, tt = t - pl * tiles_p;
+      const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
+      const int y = tr * TH + ty, x = tc * TW + tx;
+      const bool valid = tx < TW && y < PR2 && x < PC2;
+      float4* dst = reinterpret_cast<float4*>(lmap + ((int64_t(pl) * psz + (valid ? int64_t(y) * PC2 + x : 0)) * 25) * 16);
+      mbar_wait(bars + 8 * DFULL, tj & 1, 74);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = m0; m < m1; ++m) {
+        float v[16];
+        tmem_ld16(lane_addr + m * 16, v);
+        tmem_ld_wait();
+        if (m == m1 - 1) { tc_fence_before(); mbar_arrive(bars + 8 * DEMPTY); }
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[m * 4 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+}  // namespace cmlpl
+
+using namespace cmlpl;
+
+extern "C" int cmlpl_conv1_scene_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                                            float* g, void* pmq, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(f0pad && packed && g && pmq, "conv1_scene_planes: null pointer");
+  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "conv1_scene_planes: bad dims (w must be 20)");
+  const int rc = cmlpl_conv1_scene_variants_f32(f0pad, cols, w, band_rows, packed, g, stream);
+  if (rc != CMLPL_OK) return rc;
+  const int PR = band_rows + w - 1, PC = cols + w - 1, PR2 = (PR + 1) / 2, PC2 = (PC + 1) / 2;
+  const int64_t total = int64_t(4) * PR2 * PC2 * 8;
+  int64_t pg = (total + 255) / 256; const int64_t cap = int64_t(sm_count()) * 16; if (pg > cap) pg = cap;
+  pool1q_scene_kernel<<<int(pg), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, PR, PC, PR2, PC2, static_cast<__half*>(pmq));
+  CMLPL_CHECK_LAUNCH("pool1q_scene");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_rows, const void* packed, void* yq,
+                                     cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(pmq && packed && yq, "conv2_scene: null pointer");
+  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "conv2_scene: bad dims (w must be 20)");
+  const int PR2 = (band_rows + w) / 2, PC2 = (cols + w) / 2;
+  const PackedLayout L = packed_layout(1, 1, w);
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  CMLPL_CUDA(cudaFuncSetAttribute(conv2_scene_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c2s::SMEM));
+  const int ntiles = 4 * ((PR2 + c2s::TH - 1) / c2s::TH) * ((PC2 + c2s::TW - 1) / c2s::TW);
+  int grid = sm_count(); if (grid > ntiles) grid = ntiles;
+  conv2_scene_kernel<<<grid, c2s::kThreads, c2s::SMEM, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(pmq), PR2, PC2, pk + L.w2, reinterpret_cast<const float*>(pk + L.b2), static_cast<__half*>(yq));
+  CMLPL_CHECK_LAUNCH("conv2_scene");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_rows, int num_features, int num_classes,
+                                   const void* packed, float* lmap, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(yq && packed && lmap, "pool2_cls: null pointer");
+  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0 && num_classes > 0 && num_classes <= 16,
+                  "pool2_cls: bad dims (w must be 20, <= 16 classes)");
+  const int PR2 = (band_rows + w) / 2, PC2 = (cols + w) / 2;
+  const PackedLayout L = packed_layout(num_features, num_classes, w);
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  CMLPL_CUDA(cudaFuncSetAttribute(pool2_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2c::SMEM));
+  const int ntiles = 4 * ((PR2 + p2c::TH - 1) / p2c::TH) * ((PC2 + p2c::TW - 1) / p2c::TW);
+  int grid = sm_count(); if (grid > ntiles) grid = ntiles;
+  pool2_cls_kernel<<<grid, p2c::kThreads, p2c::SMEM, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(yq), PR2, PC2, pk + L.wcq, lmap);
+  CMLPL_CHECK_LAUNCH("pool2_cls");
+  return CMLPL_OK;
+}

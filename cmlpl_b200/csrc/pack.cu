@@ -85,6 +85,21 @@ __global__ void pack_kernel(PackArgs a) {
         d[i] = __float2half_rn(v);
       }
     } break;
+    case 8: {  // dense-path classifier: per block [8 kc][N][8], row = map*16 + cls, value = Wc[cls][ch,I,J] / 4
+      if (a.P != 25) break;
+      __half* d = reinterpret_cast<__half*>(o + a.L.wcq);
+      const int in_f = 64 * 25 + 1024;
+      for (int64_t i = t0; i < 400 * 64; i += step) {
+        int b = 0;
+        while (b < 8 && i >= int64_t(blk_start(b + 1)) * 16 * 64) ++b;
+        const int Al = b / 3, Be = b % 3, N = blk_n(Al) * blk_n(Be) * 16;
+        const int64_t li = i - int64_t(blk_start(b)) * 16 * 64;
+        const int e = int(li & 7), row = int((li >> 3) % N), kc = int((li >> 3) / N);
+        const int mi = row >> 4, cls = row & 15, ch = kc * 8 + e;
+        const int I = blk_first(Al) + mi / blk_n(Be), J = blk_first(Be) + mi % blk_n(Be);
+        d[i] = __float2half_rn(cls < a.C ? 0.25f * a.cw[int64_t(cls) * in_f + ch * 25 + I * 5 + J] : 0.f);
+      }
+    } break;
   }
 }
 
@@ -113,7 +128,7 @@ extern "C" int cmlpl_pack_basenet2(const float* conv0_w, const float* conv0_b, c
   a.L = packed_layout(num_features, num_classes, w);
   a.P = a.L.conv_pos;
   a.out = static_cast<unsigned char*>(packed);
-  pack_kernel<<<dim3(64, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  pack_kernel<<<dim3(64, 9), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   CMLPL_CHECK_LAUNCH("pack_basenet2");
   return CMLPL_OK;
 }

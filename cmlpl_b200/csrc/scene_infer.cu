@@ -5,11 +5,12 @@
 //                    is then a plain w x w window of this map (hyper_tools.py:35-55,226-243)
 //   2. spectral_head relu(feat_spe(x)) (models.py:142-143) and its classifier columns
 //   3. conv1_scene   conv1 + residual + ReLU once per scene position in 9 patch-border classes and the
-//                    pooled maps (conv1_scene_sm100.cu), then patch_conv2: conv2 + residual + ReLU +
-//                    avg-pool per pixel pair (patch_conv2_sm100.cu) -> pooled features P2 (UMMA tiles).
-//                    (> 16 classes / > 208 bands: the all-per-pixel patch_cnn_sm100.cu kernel instead)
-//   4. classify      classifier (models.py:150) over [P2 | spectral] + argmax
-//                    (hyper_tools.py:426, first index wins ties)
+//                    pooled maps as parity planes (conv1_scene_sm100.cu); conv2_scene: conv2 + residual +
+//                    ReLU once per position in 25 classes; pool2_cls: avg-pool + conv columns of the
+//                    classifier -> 25 class-partial maps (conv2_scene_sm100.cu)
+//   4. head          spectral columns of the classifier (models.py:150) + the pixel's 25 gathered conv
+//                    partials + bias, argmax (hyper_tools.py:426, first index wins ties)
+//   (> 16 classes / > 208 bands: the all-per-pixel patch_cnn_sm100.cu kernel + CUDA-core classify instead)
 #include "common.cuh"
 #include "gemm_core.cuh"
 
@@ -167,10 +168,13 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int64_t n, int C
 static bool use_tc_head(int B, int C) { return C <= 16 && ((B + 15) / 16) * 2 <= 26; }
 
 struct SceneWs {
-  size_t f0pad, p2, spe, hidden, x16, h16, g, pm, total;
+  size_t f0pad, p2, spe, hidden, x16, h16, g, pm, yq, lmap, total;
   int64_t chunk;
   bool tc;
 };
+// tensor-core path (<= 16 classes, <= 208 bands): conv0 map, spectral tiles, conv1 variants (fp32 scratch), pooled
+// parity planes, the 25 conv2 variants, the 25 class-partial maps.  CUDA-core path: conv0 map, per-pixel pooled
+// features, spectral logits, hidden chunk.
 static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   SceneWs s;
   const int64_t n = int64_t(band_rows) * cols;
@@ -179,16 +183,19 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   s.tc = use_tc_head(B, C);
   size_t o = 0;
   s.f0pad = o; o = align256(o + size_t(band_rows + w - 1) * (cols + w - 1) * 64 * 2);
-  s.p2 = o; o = align256(o + size_t(s.tc ? mtiles * 128 : n) * P * 64 * 2);
-  s.spe = s.hidden = s.x16 = s.h16 = s.g = s.pm = 0;
+  s.p2 = s.spe = s.hidden = s.x16 = s.h16 = s.g = s.pm = s.yq = s.lmap = 0;
   s.chunk = n < 16384 ? n : 16384;
   if (s.tc) {
     s.x16 = o; o = align256(o + size_t(mtiles) * (((B + 15) / 16) * 2) * 2048);
     s.h16 = o; o = align256(o + size_t(mtiles) * 128 * 2048);
     const size_t ppos = size_t(band_rows + w - 1) * (cols + w - 1);
+    const size_t qpos = size_t(4) * ((band_rows + w) / 2) * ((cols + w) / 2);     // positions of the 4 parity planes
     s.g = o; o = align256(o + ppos * 9 * 64 * 4);          // conv1 border-class variants, fp32
-    s.pm = o; o = align256(o + ppos * 9 * 64 * 2);         // pooled variants, fp16 [9][PR][PC][64]
+    s.pm = o; o = align256(o + qpos * 9 * 64 * 2);         // pooled variants, f16 parity planes [9][4][8][PR2][PC2][8]
+    s.yq = o; o = align256(o + qpos * 25 * 64 * 2);        // conv2 variants, f16 [25][4][8][PR2][PC2][8]
+    s.lmap = o; o = align256(o + qpos * 25 * 16 * 4);      // class partials, f32 [4][PR2][PC2][25][16]
   } else {
+    s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);
     s.spe = o; o = align256(o + size_t(n) * C * 4);
     s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);
   }
@@ -203,6 +210,32 @@ using namespace cmlpl;
 extern "C" size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w) {
   if (band_rows <= 0 || cols <= 0 || num_classes <= 0 || num_features <= 0 || w < 4) return 0;
   return scene_ws(band_rows, cols, num_features, num_classes, w).total;
+}
+
+extern "C" int cmlpl_scene_workspace_layout(int band_rows, int cols, int num_features, int num_classes, int w,
+                                            size_t* offsets) {
+  CMLPL_CHECK_ARG(offsets && band_rows > 0 && cols > 0 && num_classes > 0 && num_features > 0 && w >= 4,
+                  "scene_workspace_layout: bad args");
+  const SceneWs s = scene_ws(band_rows, cols, num_features, num_classes, w);
+  const size_t v[12] = {s.f0pad, s.x16, s.h16, s.g, s.pm, s.yq, s.lmap, s.p2, s.spe, s.hidden, s.total, size_t(s.tc)};
+  for (int i = 0; i < 12; ++i) offsets[i] = v[i];
+  return CMLPL_OK;
+}
+
+// conv1 (9 border classes) -> pooled parity planes -> conv2 (25 classes) -> pool + conv classifier columns ->
+// spectral classifier columns + gathered conv partials + argmax: everything after conv0 / the spectral GEMM
+static int dense_tail(unsigned char* wsb, const SceneWs& ws, int cols, int w, int band_rows, int num_features,
+                      int num_classes, const void* packed, uint8_t* labels, float* logits, cmlpl_stream_t stream) {
+  int rc = cmlpl_conv1_scene_planes_f16(wsb + ws.f0pad, cols, w, band_rows, packed, reinterpret_cast<float*>(wsb + ws.g),
+                                        wsb + ws.pm, stream);
+  if (rc != CMLPL_OK) return rc;
+  rc = cmlpl_conv2_scene_f16(wsb + ws.pm, cols, w, band_rows, packed, wsb + ws.yq, stream);
+  if (rc != CMLPL_OK) return rc;
+  rc = cmlpl_pool2_cls_f16(wsb + ws.yq, cols, w, band_rows, num_features, num_classes, packed,
+                           reinterpret_cast<float*>(wsb + ws.lmap), stream);
+  if (rc != CMLPL_OK) return rc;
+  return cmlpl_head_lmap_tc(wsb + ws.h16, reinterpret_cast<const float*>(wsb + ws.lmap), cols, band_rows, num_features,
+                            num_classes, w, packed, labels, logits, stream);
 }
 
 extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows, int w,
@@ -318,13 +351,7 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
   if (ws.tc) {
     rc = cmlpl_spectral_hidden_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16, wsb + ws.h16, stream);
     if (rc != CMLPL_OK) return rc;
-    // conv1 once per scene position (9 border classes) + pooled maps, then conv2 per pixel pair
-    rc = cmlpl_conv1_scene_f16(wsb + ws.f0pad, cols, w, band_rows, packed, reinterpret_cast<float*>(wsb + ws.g),
-                               wsb + ws.pm, stream);
-    if (rc != CMLPL_OK) return rc;
-    rc = cmlpl_patch_conv2_f16_tiled(wsb + ws.pm, cols, w, band_rows, packed, wsb + ws.p2, stream);
-    if (rc != CMLPL_OK) return rc;
-    return cmlpl_head_tc(wsb + ws.p2, wsb + ws.h16, n, num_features, num_classes, w, packed, labels, logits, stream);
+    return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
   }
   rc = cmlpl_spectral_head_f32(spectra, n, num_features, num_classes, w, packed,
                                reinterpret_cast<float*>(wsb + ws.hidden), ws.chunk,
@@ -388,10 +415,5 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
   int rc = cmlpl_spectral_hidden_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
                                         wsb + ws.x16, wsb + ws.h16, stream);
   if (rc != CMLPL_OK) return rc;
-  rc = cmlpl_conv1_scene_f16(wsb + ws.f0pad, cols, w, band_rows, packed, reinterpret_cast<float*>(wsb + ws.g),
-                             wsb + ws.pm, stream);
-  if (rc != CMLPL_OK) return rc;
-  rc = cmlpl_patch_conv2_f16_tiled(wsb + ws.pm, cols, w, band_rows, packed, wsb + ws.p2, stream);
-  if (rc != CMLPL_OK) return rc;
-  return cmlpl_head_tc(wsb + ws.p2, wsb + ws.h16, n, num_features, num_classes, w, packed, labels, logits, stream);
+  return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
 }

@@ -119,6 +119,11 @@ int cmlpl_pack_basenet2(const float* conv0_w, const float* conv0_b,
 /* Workspace needed to infer `band_rows` rows of a scene with `cols` columns. */
 size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w);
 
+/* Byte offsets of the workspace regions (for stage-level profiling): offsets[12] =
+ * {f0pad, x16, h16, g, pmq, yq, lmap, p2, spe_logits, hidden, total, uses_tensor_core_path}. */
+int cmlpl_scene_workspace_layout(int band_rows, int cols, int num_features, int num_classes, int w,
+                                 size_t* offsets);
+
 /* cube     f32 [slab_rows, cols, 60]  PCA cube slab (rows slab_row0.. of the scene)
  * spectra  f32 [band_rows*cols, num_features]   rows of X for the band's pixels
  * labels   u8  [band_rows*cols]  argmax (first index on ties, hyper_tools.py:426)
@@ -174,6 +179,28 @@ int cmlpl_head_tc(const void* p2t, const void* h16, int64_t n, int num_features,
  *   pm f16 [9][PR][PC][64]: pooled maps, variant = A*3+B (A,B in top/mid/bot, left/mid/right). */
 int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
                           void* pm, cmlpl_stream_t stream);
+/* Dense (scene-level) rest of the conv tower, exact compute sharing of conv2 / pool / classifier
+ * (tools/models.py:137-150 for all patches at once; csrc/conv2_scene_sm100.cu).  PR2 = (band_rows+w)/2,
+ * PC2 = (cols+w)/2; "planes" = the 4 parity planes (pr&1)*2+(pc&1) of the padded map, y' = pr>>1, x' = pc>>1.
+ *   cmlpl_conv1_scene_variants_f32: g f32 [9][PR*PC][64] only (no pooling)
+ *   cmlpl_conv1_scene_planes_f16  : + pooled maps as planes   pmq f16 [9][4][8 chunks][PR2][PC2][8]
+ *   cmlpl_conv2_scene_f16         : conv2+bias+residual+ReLU in 25 border classes (rho*5+kap)
+ *                                   yq f16 [25][4][8][PR2][PC2][8]
+ *   cmlpl_pool2_cls_f16           : 2x2 avg-pool + conv columns of the classifier per pooled cell (I,J)
+ *                                   lmap f32 [4][PR2][PC2][25][16]
+ *   cmlpl_head_lmap_tc            : spectral classifier columns (h16 tiles) + the 25 gathered partials of each
+ *                                   pixel + bias, argmax -> labels u8 [band_rows*cols] (and logits) */
+int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
+                                   cmlpl_stream_t stream);
+int cmlpl_conv1_scene_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
+                                 void* pmq, cmlpl_stream_t stream);
+int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_rows, const void* packed, void* yq,
+                          cmlpl_stream_t stream);
+int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_rows, int num_features, int num_classes,
+                        const void* packed, float* lmap, cmlpl_stream_t stream);
+int cmlpl_head_lmap_tc(const void* h16, const float* lmap, int cols, int band_rows, int num_features,
+                       int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
+                       cmlpl_stream_t stream);
 /* Per-pixel conv2 stage on the pooled conv1 maps of cmlpl_conv1_scene_f16 (models.py:137-140 per patch):
  * pm f16 [9][PR][PC][64] -> p2t UMMA tiles [ceil(n/128)][(w/4)^2*8][128][8] for cmlpl_head_tc. */
 int cmlpl_patch_conv2_f16_tiled(const void* pm, int cols, int w, int band_rows, const void* packed,
