@@ -34,9 +34,11 @@ __global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC,
   const int64_t psz = int64_t(PR2) * PC2;
   const int64_t total = 4 * psz * 8;
   for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int x2 = int(t % PC2);
-    int64_t r = t / PC2;
-    const int ch = int(r & 7); r >>= 3;
+    // 8 consecutive threads = the 8 channel chunks of one position: 256-B contiguous reads of g, and a warp's
+    // four positions write 64 contiguous bytes into each chunk plane
+    const int ch = int(t & 7);
+    int64_t r = t >> 3;
+    const int x2 = int(r % PC2); r /= PC2;
     const int y2 = int(r % PR2), pl = int(r / PR2);
     const int pr = 2 * y2 + (pl >> 1), pc = 2 * x2 + (pl & 1);
     const bool valid = pr < PR - 1 && pc < PC - 1;
@@ -302,7 +304,7 @@ static_assert(SMEM <= 232448, "pool2_cls: shared memory over the 227 KB limit");
 }  // namespace p2c
 
 // yq f16 [25][4][8][PR2][PC2][8];  wcq f16 per block [8 kchunks][N rows = map*16 + cls][8];
-// lmap f32 [4][PR2][PC2][25][16]
+// lmap f32 [4][25][4][PR2][PC2][4]
 __global__ void __launch_bounds__(p2c::kThreads, 1)
 pool2_cls_kernel(const __half* __restrict__ yq, int PR2, int PC2, const unsigned char* __restrict__ wcq,
                  float* __restrict__ lmap) {
@@ -414,7 +416,8 @@ pool2_cls_kernel(const __half* __restrict__ yq, int PR2, int PC2, const unsigned
       const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
       const int y = tr * TH + ty, x = tc * TW + tx;
       const bool valid = tx < TW && y < PR2 && x < PC2;
-      float4* dst = reinterpret_cast<float4*>(lmap + ((int64_t(pl) * psz + (valid ? int64_t(y) * PC2 + x : 0)) * 25) * 16);
+      // lmap f32 [4 planes][25 maps][4 class quads][PR2][PC2][4]: a warp's store of one (map, quad) is 512 contiguous bytes
+      float4* dst = reinterpret_cast<float4*>(lmap) + int64_t(pl) * 100 * psz + (valid ? int64_t(y) * PC2 + x : 0);
       mbar_wait(bars + 8 * DFULL, tj & 1, 74);
       tc_fence_after();
 #pragma unroll 1
@@ -425,7 +428,7 @@ pool2_cls_kernel(const __half* __restrict__ yq, int PR2, int PC2, const unsigned
         if (m == m1 - 1) { tc_fence_before(); mbar_arrive(bars + 8 * DEMPTY); }
         if (valid) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[m * 4 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) dst[int64_t(m * 4 + q) * psz] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
     }

@@ -256,16 +256,17 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
           // conv part of the classifier from the dense path: 25 gathered class-partial vectors
           // L[I][J][r'+2I, c'+2J] of this pixel's parity plane (conv2_scene_sm100.cu), fixed summation order
           const int r = int(p / cols), c = int(p - int64_t(r) * cols);
-          const float4* base = reinterpret_cast<const float4*>(lmap) +
-              ((int64_t((r & 1) * 2 + (c & 1)) * PR2 + (r >> 1)) * PC2 + (c >> 1)) * 100;
+          const int64_t psz = int64_t(PR2) * PC2;
+          const float4* base = reinterpret_cast<const float4*>(lmap) + int64_t((r & 1) * 2 + (c & 1)) * 100 * psz +
+                               int64_t(r >> 1) * PC2 + (c >> 1);
 #pragma unroll
           for (int I = 0; I < 5; ++I) {
 #pragma unroll
             for (int J = 0; J < 5; ++J) {
-              const float4* q = base + (int64_t(2 * I) * PC2 + 2 * J) * 100 + lmap_index(I, J) * 4;
+              const float4* q = base + int64_t(lmap_index(I, J) * 4) * psz + (2 * I) * PC2 + 2 * J;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const float4 t = __ldg(q + k);
+                const float4 t = __ldg(q + int64_t(k) * psz);
                 v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
               }
             }

@@ -193,7 +193,7 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
     s.g = o; o = align256(o + ppos * 9 * 64 * 4);          // conv1 border-class variants, fp32
     s.pm = o; o = align256(o + qpos * 9 * 64 * 2);         // pooled variants, f16 parity planes [9][4][8][PR2][PC2][8]
     s.yq = o; o = align256(o + qpos * 25 * 64 * 2);        // conv2 variants, f16 [25][4][8][PR2][PC2][8]
-    s.lmap = o; o = align256(o + qpos * 25 * 16 * 4);      // class partials, f32 [4][PR2][PC2][25][16]
+    s.lmap = o; o = align256(o + qpos * 25 * 16 * 4);      // class partials, f32 [4][25][4][PR2][PC2][4]
   } else {
     s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);
     s.spe = o; o = align256(o + size_t(n) * C * 4);

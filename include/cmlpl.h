@@ -187,7 +187,7 @@ int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, con
  *   cmlpl_conv2_scene_f16         : conv2+bias+residual+ReLU in 25 border classes (rho*5+kap)
  *                                   yq f16 [25][4][8][PR2][PC2][8]
  *   cmlpl_pool2_cls_f16           : 2x2 avg-pool + conv columns of the classifier per pooled cell (I,J)
- *                                   lmap f32 [4][PR2][PC2][25][16]
+ *                                   lmap f32 [4][25][4 class quads][PR2][PC2][4]
  *   cmlpl_head_lmap_tc            : spectral classifier columns (h16 tiles) + the 25 gathered partials of each
  *                                   pixel + bias, argmax -> labels u8 [band_rows*cols] (and logits) */
 int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,

@@ -36,7 +36,7 @@ def run(R, C, B, K, seed, time_it=False):
     pm = torch.zeros(9 * PR * PC * 64, dtype=torch.float16, device=dev)
     pmq = torch.full((9, 4, 8, PR2, PC2, 8), float("nan"), dtype=torch.float16, device=dev)
     yq = torch.full((25, 4, 8, PR2, PC2, 8), float("nan"), dtype=torch.float16, device=dev)
-    lmap = torch.full((4, PR2, PC2, 25, 16), float("nan"), dtype=torch.float32, device=dev)
+    lmap = torch.full((4, 25, 4, PR2, PC2, 4), float("nan"), dtype=torch.float32, device=dev)
     _lib.call("cmlpl_conv0_map_f16", cube.data_ptr(), R, C, 0, R, w, 0, R, packed.data_ptr(), f0.data_ptr(), st)
     _lib.call("cmlpl_conv1_scene_f16", f0.data_ptr(), C, w, R, packed.data_ptr(), g.data_ptr(), pm.data_ptr(), st)
     _lib.call("cmlpl_conv1_scene_planes_f16", f0.data_ptr(), C, w, R, packed.data_ptr(), g.data_ptr(), pmq.data_ptr(), st)
@@ -99,11 +99,11 @@ def run(R, C, B, K, seed, time_it=False):
                 src = yz[ycl(Al, u) * 5 + ycl(Be, v)]
                 sh = F.pad(src, (0, 1, 0, 1))[:, :, u:u + PR2, v:v + PC2]
                 ref += 0.25 * torch.einsum("kc,pcyx->pkyx", Wc[:, :, I, J], sh)
-        got = lmap[:, :, :, m, :K].permute(0, 3, 1, 2)
+        got = lmap[:, m].permute(0, 1, 4, 2, 3).reshape(4, 16, PR2, PC2)[:, :K]
         # only positions whose four inputs exist matter; compare on the interior
         e = rel(got[:, :, :PR2 - 1, :PC2 - 1], ref[:, :, :PR2 - 1, :PC2 - 1])
         worst = max(worst, e)
-    print(f"   class-partial maps: worst rel err {worst:.2e} nan(interior)={int(torch.isnan(lmap[:, :PR2 - 1, :PC2 - 1]).sum())}")
+    print(f"   class-partial maps: worst rel err {worst:.2e} nan(interior)={int(torch.isnan(lmap[:, :, :, :PR2 - 1, :PC2 - 1]).sum())}")
     # ---- stage 4: whole path vs per-pixel path vs oracle
     labels, logits = ops.scene_infer(cube, spectra, packed, K, w, want_logits=True)
     torch.cuda.synchronize()
