@@ -300,7 +300,7 @@ def main():
         if e[1]: e[1].record()
         _lib.call("cmlpl_spectral_hidden_tc", spec.data_ptr(), n_band, B0, K0, W0, pk, o_x16, o_h16, st)
         if e[2]: e[2].record()
-        _lib.call("cmlpl_conv1_scene_planes_f16", o_f0, C0, W0, nb, pk, o_g, o_pmq, st)
+        _lib.call("cmlpl_conv1_pool_planes_f16", o_f0, C0, W0, nb, pk, o_pmq, st)
         if e[3]: e[3].record()
         _lib.call("cmlpl_conv2_scene_f16", o_pmq, C0, W0, nb, pk, o_yq, st)
         if e[4]: e[4].record()

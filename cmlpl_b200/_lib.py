@@ -45,6 +45,7 @@ SIGNATURES = {
     "cmlpl_scene_workspace_layout": (I, [I, I, I, I, I, P]),
     "cmlpl_conv1_scene_variants_f32": (I, [P, I, I, I, P, P, P]),
     "cmlpl_conv1_scene_planes_f16": (I, [P, I, I, I, P, P, P, P]),
+    "cmlpl_conv1_pool_planes_f16": (I, [P, I, I, I, P, P, P]),
     "cmlpl_conv2_scene_f16": (I, [P, I, I, I, P, P, P]),
     "cmlpl_pool2_cls_f16": (I, [P, I, I, I, I, I, P, P, P]),
     "cmlpl_head_lmap_tc": (I, [P, P, I, I, I, I, I, P, P, P, P]),

@@ -233,6 +233,262 @@ __global__ void pool1_scene_kernel(const float* __restrict__ g, int PR, int PC, 
   }
 }
 
+
+// =================================================================================================
+// conv1_pool_kernel: the 9 conv1 border-class variants AND their 2x2 average pools in ONE kernel -- the fp32
+// variants G (2.3 KB per scene position) never touch HBM.  Same tile / tap-as-descriptor-offset machinery as
+// conv1_scene_kernel, but
+//   * the tensor core produces the nine single-tap-column sums  T[dy][dx] = sum_ci W1[dy,dx] . F0[p+(dy-1,dx-1)]
+//     separately (N = 32 channels at a time: sub-stage (h, dy) = T[dy][0..2] in 96 TMEM columns, ring of 5), so
+//     that all three column classes  R[dy][left|mid|right] = T1+T2 | T0+T1+T2 | T0+T1  are formed in the
+//     epilogue from one TMEM read (36 MMAs per 32 channels instead of 84);
+//   * a tile's 4 conv rows give 3 pooled rows and its 30 conv columns 29 pooled columns: the vertical 2x2
+//     partner (ty+1, tx) lives in another warp (TMEM lane quarter) and comes through a double-buffered
+//     shared-memory exchange, the horizontal partner (tx+1) through a warp shuffle;
+//   * pooled cells go straight to the parity planes pmq (f16, chunk-planar), 8 channels = one 16-byte chunk
+//     per thread and pass.
+//   V[A][b]  = G[a0(A)][b](y,x) + G[a1(A)][b](y+1,x)                 (a0,a1 = top,mid | mid,mid | mid,bot)
+//   PM[A][B] = 1/4 (V[A][b0(B)](x) + V[A][b1(B)](x+1))               (b0,b1 = left,mid | mid,mid | mid,right)
+namespace c1p {
+constexpr int TH = 4, TP = 32, OH = 3, OW = 29;      // conv rows, row pitch; pooled rows / columns per tile
+constexpr int ENT = 1 + (TH + 2) * TP + 1;
+constexpr int CH = ENT * 16 + 16;
+constexpr int ABYTES = 8 * CH;
+constexpr int WBYTES = 3 * 8 * 192 * 16;
+constexpr int kEpi = 256, kLoad = 64, kThreads = kEpi + kLoad + 32;
+constexpr int XBYTES = 12 * kEpi * 16;               // exchange: 12 float4 (G[mid|bot][3 b][8 ch]) per epilogue thread
+constexpr int S_W = 0, S_A = WBYTES, S_X = S_A + 2 * ABYTES, S_BIAS = S_X + 2 * XBYTES, S_BAR = S_BIAS + 256,
+              S_TMEM = S_BAR + 128;
+constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
+constexpr int NSUB = 5, SUBCOLS = 96;
+constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
+enum { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, S_FULL0 = 4, S_EMPTY0 = 4 + NSUB };
+static_assert(SMEM <= 232448, "conv1_pool: shared memory over the 227 KB limit");
+static_assert(S_EMPTY0 + NSUB <= 16, "conv1_pool: barrier area too small");
+}  // namespace c1p
+
+// f0: f16 chunk-planar [8][PR][PC][8];  pmq f16 [9 = A*3+B][4 planes][8 chunks][PR2][PC2][8]
+__global__ void __launch_bounds__(c1p::kThreads, 1)
+conv1_pool_kernel(const __half* __restrict__ f0, int PR, int PC, int PR2, int PC2, const unsigned char* __restrict__ w1p,
+                  const float* __restrict__ b1g, __half* __restrict__ pmq) {
+  using namespace c1p;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + S_BAR;
+  float* sbias = reinterpret_cast<float*>(smem + S_BIAS);
+  const int tiles_c = (2 * PC2 + OW - 1) / OW, tiles_r = (2 * PR2 + OH - 1) / OH;
+  const int ntiles = tiles_r * tiles_c;
+  const int64_t psz = int64_t(PR2) * PC2;
+
+  {
+    const uint4* gw = reinterpret_cast<const uint4*>(w1p);
+    uint4* sw = reinterpret_cast<uint4*>(smem + S_W);
+    for (int i = tid; i < WBYTES / 16; i += kThreads) sw[i] = __ldg(gw + i);
+    uint4* z = reinterpret_cast<uint4*>(smem + S_A);
+    for (int i = tid; i < 2 * ABYTES / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid < 64) sbias[tid] = b1g[tid];
+  if (tid == 0) {
+    mbar_init(bars + 8 * A_FULL0, kLoad); mbar_init(bars + 8 * A_FULL1, kLoad);
+    mbar_init(bars + 8 * A_EMPTY0, 1 + kEpi); mbar_init(bars + 8 * A_EMPTY1, 1 + kEpi);
+    for (int s = 0; s < NSUB; ++s) { mbar_init(bars + 8 * (S_FULL0 + s), 1); mbar_init(bars + 8 * (S_EMPTY0 + s), kEpi); }
+    fence_barrier_init();
+  }
+  if (warp == 10) tmem_alloc(sbase + S_TMEM, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
+
+  if (warp >= 8 && warp < 10) {
+    // ================================================================ loaders: (TH+2) x TP entries, zero outside the map
+    const int lt = tid - kEpi;
+    uint32_t j = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+      const uint32_t buf = j & 1, ph = (j >> 1) & 1;
+      const int tr = t / tiles_c, tc = t - tr * tiles_c;
+      const int pr0 = tr * OH - 1, pc0 = tc * OW - 1;          // map coords of entry (ry=0, rx=0)
+      mbar_wait(bars + 8 * (A_EMPTY0 + buf), ph ^ 1, 81);
+      for (int it = lt; it < (TH + 2) * TP * 8; it += kLoad) {
+        const int ch = it & 7, e = it >> 3;
+        const int ry = e / TP, rx = e - ry * TP;
+        const int pr = pr0 + ry, pc = pc0 + rx;
+        const bool in = pr >= 0 && pr < PR && pc >= 0 && pc < PC;
+        const __half* src = f0 + ((int64_t(ch) * PR + (in ? pr : 0)) * PC + (in ? pc : 0)) * 8;
+        cp_async16_zfill(sbase + S_A + buf * ABYTES + ch * CH + (1 + e) * 16, src, in ? 16u : 0u);
+      }
+      cp_async_wait_all();
+      fence_proxy_async();
+      mbar_arrive(bars + 8 * (A_FULL0 + buf));
+    }
+  } else if (warp == 10) {
+    // ================================================================ MMA issuer
+    if (tmem != 0) { printf("conv1_pool: unexpected TMEM base %u\n", tmem); __trap(); }
+    constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
+    constexpr uint32_t kI32 = make_idesc_f16(128, 32);
+    const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
+    uint32_t j = 0, slot = 0, sph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+      const uint32_t buf = j & 1, ph = (j >> 1) & 1;
+      const uint32_t a_lo = ((sbase + S_A + buf * ABYTES) >> 4) | (uint32_t(CH >> 4) << 16);
+      mbar_wait(bars + 8 * (A_FULL0 + buf), ph, 82);
+#pragma unroll 1
+      for (int hd = 0; hd < 6; ++hd) {                         // sub-stage = (channel half h, tap row dy)
+        const int h = hd / 3, dy = hd - h * 3;
+        mbar_wait(bars + 8 * (S_EMPTY0 + slot), sph ^ 1, 83);
+        tc_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t d = slot * SUBCOLS + dx * 32;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t a = a_lo + uint32_t(dy * TP + dx) + uint32_t(ks * 2 * CH / 16);
+              const uint32_t bb = w_lo + uint32_t((dx * kWDx + ks * 2 * kWLbo) / 16) + uint32_t((2 - dy) * 64 + h * 32);
+              umma_f16(d, kHi | uint64_t(a), kHi | uint64_t(bb), kI32, ks ? 1u : 0u);
+            }
+          }
+          umma_commit(bars + 8 * (S_FULL0 + slot));
+          if (hd == 5) umma_commit(bars + 8 * (A_EMPTY0 + buf));
+        }
+        __syncwarp();
+        if (++slot == NSUB) { slot = 0; sph ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 0-7)
+    const int ty = warp & 3, tx = lane, chsel = warp >> 2;
+    const uint32_t lane_addr = uint32_t(ty * 32) << 16;
+    const int nb = ty < 3 ? tid + 32 : tid;                   // exchange slot of the position one row below
+    uint32_t j = 0, slot = 0, sph = 0, xpar = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+      const uint32_t buf = j & 1;
+      const int tr = t / tiles_c, tc = t - tr * tiles_c;
+      const int pr = tr * OH + ty, pc = tc * OW + tx - 1;
+      const bool inplane = ty < OH && tx >= 1 && tx <= OW && (pr >> 1) < PR2 && (pc >> 1) < PC2;
+      const bool cell = inplane && pr < PR - 1 && pc < PC - 1;
+      const int64_t opos = inplane ? (int64_t((pr & 1) * 2 + (pc & 1)) * 8 * psz + int64_t(pr >> 1) * PC2 + (pc >> 1)) : 0;
+      mbar_wait(bars + 8 * (A_FULL0 + buf), (j >> 1) & 1, 84);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t sl[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          sl[k] = slot;
+          mbar_wait(bars + 8 * (S_FULL0 + slot), sph, 85);
+          if (++slot == NSUB) { slot = 0; sph ^= 1; }
+        }
+        tc_fence_after();
+#pragma unroll 1
+        for (int pp = 0; pp < 2; ++pp, xpar ^= 1) {
+          const int chunk = h * 4 + pp * 2 + chsel;
+          const uint32_t col = uint32_t(pp * 16 + chsel * 8);
+          float T[3][3][8];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) tmem_ld8(lane_addr + sl[dy] * SUBCOLS + dx * 32 + col, T[dy][dx]);
+          tmem_ld_wait();
+          if (pp == 1) {
+            tc_fence_before();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) mbar_arrive(bars + 8 * (S_EMPTY0 + sl[k]));
+          }
+          float base[8];
+          {
+            const uint4 rv = *reinterpret_cast<const uint4*>(smem + S_A + buf * ABYTES + chunk * CH + (1 + (ty + 1) * TP + tx) * 16);
+            const __half2* hr = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(hr[e]);
+              base[2 * e] = f.x + sbias[chunk * 8 + 2 * e];
+              base[2 * e + 1] = f.y + sbias[chunk * 8 + 2 * e + 1];
+            }
+          }
+          // G[a][b] = relu(b1 + F0 + sum of the taps the (row class a, column class b) border keeps)
+          float G[3][3][8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float R[3][3];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const float s12 = T[dy][1][c] + T[dy][2][c];
+              R[dy][0] = s12; R[dy][1] = T[dy][0][c] + s12; R[dy][2] = T[dy][0][c] + T[dy][1][c];
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              const float top = R[1][b] + R[2][b];
+              G[0][b][c] = fmaxf(top + base[c], 0.f);
+              G[1][b][c] = fmaxf((R[0][b] + top) + base[c], 0.f);
+              G[2][b][c] = fmaxf((R[0][b] + R[1][b]) + base[c], 0.f);
+            }
+          }
+          // vertical partner through shared memory: this thread publishes its mid / bot variants
+          float4* xb = reinterpret_cast<float4*>(smem + S_X + xpar * XBYTES);
+#pragma unroll
+          for (int a = 1; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                xb[(((a - 1) * 3 + b) * 2 + q) * kEpi + tid] =
+                    make_float4(G[a][b][4 * q], G[a][b][4 * q + 1], G[a][b][4 * q + 2], G[a][b][4 * q + 3]);
+          named_bar_sync(1, kEpi);
+          float V[3][3][8];                                    // [A][b]
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float4 m = xb[((0 * 3 + b) * 2 + q) * kEpi + nb];
+              const float4 o = xb[((1 * 3 + b) * 2 + q) * kEpi + nb];
+              const float mm[4] = {m.x, m.y, m.z, m.w}, oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = 4 * q + e;
+                V[0][b][c] = G[0][b][c] + mm[e];
+                V[1][b][c] = G[1][b][c] + mm[e];
+                V[2][b][c] = G[1][b][c] + oo[e];
+              }
+            }
+          // horizontal partner (tx+1) by shuffle, scale, round, store
+#pragma unroll
+          for (int A = 0; A < 3; ++A) {
+            __half2 o0[4], o1[4], o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float r[3][2];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int c = 2 * e + k;
+                const float n1 = __shfl_down_sync(0xffffffffu, V[A][1][c], 1);
+                const float n2 = __shfl_down_sync(0xffffffffu, V[A][2][c], 1);
+                r[0][k] = cell ? (V[A][0][c] + n1) * 0.25f : 0.f;
+                r[1][k] = cell ? (V[A][1][c] + n1) * 0.25f : 0.f;
+                r[2][k] = cell ? (V[A][1][c] + n2) * 0.25f : 0.f;
+              }
+              o0[e] = __floats2half2_rn(r[0][0], r[0][1]);
+              o1[e] = __floats2half2_rn(r[1][0], r[1][1]);
+              o2[e] = __floats2half2_rn(r[2][0], r[2][1]);
+            }
+            if (inplane) {
+              __half* dst = pmq + (int64_t(A * 3) * 32 * psz + opos + int64_t(chunk) * psz) * 8;
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(o0);
+              *reinterpret_cast<uint4*>(dst + int64_t(32) * psz * 8) = *reinterpret_cast<uint4*>(o1);
+              *reinterpret_cast<uint4*>(dst + int64_t(64) * psz * 8) = *reinterpret_cast<uint4*>(o2);
+            }
+          }
+        }
+      }
+      mbar_arrive(bars + 8 * (A_EMPTY0 + buf));               // residual reads (and the MMAs, by their commit) done with A
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 }  // namespace cmlpl
 
 using namespace cmlpl;
@@ -264,5 +520,23 @@ extern "C" int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int ban
   int64_t pg = (total + 255) / 256; const int64_t cap = int64_t(sm_count()) * 16; if (pg > cap) pg = cap;
   pool1_scene_kernel<<<int(pg), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, PR, PC, static_cast<__half*>(pm));
   CMLPL_CHECK_LAUNCH("pool1_scene");
+  return CMLPL_OK;
+}
+
+// conv1 variants + pooling fused (conv1_pool_kernel): f0pad -> pooled parity planes, no fp32 scratch
+extern "C" int cmlpl_conv1_pool_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed,
+                                           void* pmq, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(f0pad && packed && pmq, "conv1_pool_planes: null pointer");
+  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "conv1_pool_planes: bad dims (w must be 20)");
+  const int PR = band_rows + w - 1, PC = cols + w - 1, PR2 = (PR + 1) / 2, PC2 = (PC + 1) / 2;
+  const PackedLayout L = packed_layout(1, 1, w);
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  CMLPL_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1p::SMEM));
+  const int ntiles = ((2 * PR2 + c1p::OH - 1) / c1p::OH) * ((2 * PC2 + c1p::OW - 1) / c1p::OW);
+  int grid = sm_count(); if (grid > ntiles) grid = ntiles;
+  conv1_pool_kernel<<<grid, c1p::kThreads, c1p::SMEM, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(f0pad), PR, PC, PR2, PC2, pk + L.w1, reinterpret_cast<const float*>(pk + L.b1),
+      static_cast<__half*>(pmq));
+  CMLPL_CHECK_LAUNCH("conv1_pool");
   return CMLPL_OK;
 }

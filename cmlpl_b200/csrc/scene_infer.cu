@@ -188,9 +188,8 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   if (s.tc) {
     s.x16 = o; o = align256(o + size_t(mtiles) * (((B + 15) / 16) * 2) * 2048);
     s.h16 = o; o = align256(o + size_t(mtiles) * 128 * 2048);
-    const size_t ppos = size_t(band_rows + w - 1) * (cols + w - 1);
     const size_t qpos = size_t(4) * ((band_rows + w) / 2) * ((cols + w) / 2);     // positions of the 4 parity planes
-    s.g = o; o = align256(o + ppos * 9 * 64 * 4);          // conv1 border-class variants, fp32
+    s.g = o;                                               // (fp32 conv1 variants: not materialised any more)
     s.pm = o; o = align256(o + qpos * 9 * 64 * 2);         // pooled variants, f16 parity planes [9][4][8][PR2][PC2][8]
     s.yq = o; o = align256(o + qpos * 25 * 64 * 2);        // conv2 variants, f16 [25][4][8][PR2][PC2][8]
     s.lmap = o; o = align256(o + qpos * 25 * 16 * 4);      // class partials, f32 [4][25][4][PR2][PC2][4]
@@ -226,8 +225,7 @@ extern "C" int cmlpl_scene_workspace_layout(int band_rows, int cols, int num_fea
 // spectral classifier columns + gathered conv partials + argmax: everything after conv0 / the spectral GEMM
 static int dense_tail(unsigned char* wsb, const SceneWs& ws, int cols, int w, int band_rows, int num_features,
                       int num_classes, const void* packed, uint8_t* labels, float* logits, cmlpl_stream_t stream) {
-  int rc = cmlpl_conv1_scene_planes_f16(wsb + ws.f0pad, cols, w, band_rows, packed, reinterpret_cast<float*>(wsb + ws.g),
-                                        wsb + ws.pm, stream);
+  int rc = cmlpl_conv1_pool_planes_f16(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.pm, stream);
   if (rc != CMLPL_OK) return rc;
   rc = cmlpl_conv2_scene_f16(wsb + ws.pm, cols, w, band_rows, packed, wsb + ws.yq, stream);
   if (rc != CMLPL_OK) return rc;

@@ -194,6 +194,10 @@ int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_
                                    cmlpl_stream_t stream);
 int cmlpl_conv1_scene_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
                                  void* pmq, cmlpl_stream_t stream);
+/* cmlpl_conv1_pool_planes_f16: the same pooled planes from ONE kernel (conv1 variants pooled in the epilogue through a
+ * shared-memory / shuffle exchange; no fp32 scratch in HBM) -- what cmlpl_scene_infer runs. */
+int cmlpl_conv1_pool_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* pmq,
+                                cmlpl_stream_t stream);
 int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_rows, const void* packed, void* yq,
                           cmlpl_stream_t stream);
 int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_rows, int num_features, int num_classes,

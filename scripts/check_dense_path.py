@@ -49,6 +49,15 @@ def run(R, C, B, K, seed, time_it=False):
             sub = pm4[:, p:PR - 1:2, q:PC - 1:2, :]                    # pooled cells exist for pr < PR-1, pc < PC-1
             pmq_ref[:, p * 2 + q, :, :sub.shape[1], :sub.shape[2], :] = sub.reshape(9, sub.shape[1], sub.shape[2], 8, 8).permute(0, 3, 1, 2, 4)
     print(f"[{R}x{C}] planes vs pooled maps: equal={torch.equal(pmq, pmq_ref)} nan={int(torch.isnan(pmq.float()).sum())}")
+    # fused conv1+pool kernel (what scene_infer runs): same planes up to the fp32 summation order of the 2x2 pool
+    pmq_f = torch.full((9, 4, 8, PR2, PC2, 8), float("nan"), dtype=torch.float16, device=dev)
+    _lib.call("cmlpl_conv1_pool_planes_f16", f0.data_ptr(), C, w, R, packed.data_ptr(), pmq_f.data_ptr(), st)
+    torch.cuda.synchronize()
+    d = (pmq_f.float() - pmq.float()).abs()
+    ulp = (pmq.float().abs() * 2.0 ** -10).clamp_min(2.0 ** -24)
+    print(f"   fused conv1+pool planes: nan={int(torch.isnan(pmq_f.float()).sum())} bit-equal {float((pmq_f == pmq).float().mean()):.5f} "
+          f"max diff in ulps {float((d / ulp).max()):.2f} max abs {float(d.max()):.3e}")
+    pmq = pmq_f
     # dense planes [9][4][64][PR2][PC2] f32
     PMd = pmq_ref.permute(0, 1, 2, 5, 3, 4).reshape(9, 4, 64, PR2, PC2).float()
     # ---- stage 2: conv2 variants
@@ -134,7 +143,7 @@ def run(R, C, B, K, seed, time_it=False):
         tot = np.zeros(4)
         for it in range(8):
             ev[0].record()
-            _lib.call("cmlpl_conv1_scene_planes_f16", base + off[0], C, w, R, packed.data_ptr(), base + off[3], base + off[4], st)
+            _lib.call("cmlpl_conv1_pool_planes_f16", base + off[0], C, w, R, packed.data_ptr(), base + off[4], st)
             ev[1].record()
             _lib.call("cmlpl_conv2_scene_f16", base + off[4], C, w, R, packed.data_ptr(), base + off[5], st)
             ev[2].record()
