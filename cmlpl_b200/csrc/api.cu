@@ -2,7 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cmlpl {
 
@@ -25,6 +28,36 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+
+int make_scene_tmap(CUtensorMap* out, const void* base, int outer, int rows, int cols, int box_rows, int box_cols) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return CMLPL_ERR_CUDA;
+    }
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const cuuint64_t psz = cuuint64_t(rows) * cols;
+  // a row of the plane is contiguous (cols x 16 B), so (8 halves, cols) is ONE dimension of cols*8 halves: the box's
+  // innermost extent is box_cols*16 bytes (512 B for 32 columns) instead of 16 B, which is what the TMA unit likes
+  const cuuint64_t dims[4] = {cuuint64_t(cols) * 8, cuuint64_t(rows), 8, cuuint64_t(outer)};
+  const cuuint64_t strides[3] = {cuuint64_t(cols) * 16, psz * 16, psz * 128};       // bytes, dims 1..3
+  const cuuint32_t box[4] = {cuuint32_t(box_cols) * 8, cuuint32_t(box_rows), 8, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d][8][%d][%d][8] box %dx%d", int(r), outer, rows, cols, box_rows, box_cols);
+    return CMLPL_ERR_CUDA;
+  }
+  return CMLPL_OK;
 }
 
 }  // namespace cmlpl

@@ -22,6 +22,7 @@
 // Identical math up to fp32 summation order; per PaviaU scene conv2 executes 0.32 TFLOP instead of 1.53.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tma.cuh"
 
 namespace cmlpl {
 
@@ -289,24 +290,26 @@ conv2_scene_kernel(const __half* __restrict__ pmq, int PR2, int PC2, const unsig
 // accumulating into the block's TMEM columns; the (u,v) shift is an A-descriptor offset in the tile.
 namespace p2c {
 constexpr int TH = 4, TP = 32, TW = 31;              // outputs valid for tx = 0..30 (tx+1 must be in the tile)
-constexpr int ENT = (TH + 1) * TP + 2;               // 162 entries per chunk plane
-constexpr int CH = ENT * 16 + 16;
-constexpr int TBYTES = 8 * CH;                       // 20 864
-constexpr int NSLOT = 4, NSTAGE = 2;
+constexpr int CH = (TH + 1) * TP * 16;               // 2 560: one chunk plane of a tile, dense (written by TMA)
+constexpr int TBYTES = 8 * CH;                       // 20 480: one Y variant tile
+constexpr int NSLOT = 8;                             // ring of variant tiles (164 KB in flight per SM)
 constexpr int WBYTES = 400 * 128;                    // 25 maps x 16 classes x 64 channels, f16
-constexpr int S_W = 0, S_T = WBYTES, S_BAR = S_T + NSTAGE * NSLOT * TBYTES, S_TMEM = S_BAR + 128;
+constexpr int S_W = 0, S_T = WBYTES, S_BAR = S_T + NSLOT * TBYTES + 128, S_TMEM = S_BAR + 256;   // +128: shifted A rows of the last slot
 constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
-constexpr int kEpi = 256, kLoad = 128, kThreads = kEpi + kLoad + 32;
-constexpr int kMmaWarp = (kEpi + kLoad) / 32;
-constexpr int kTileItems = (TH + 1) * TP * 8;        // 16-byte copies per Y variant tile
-enum { F0 = 0, E0 = NSTAGE, DFULL = 2 * NSTAGE, DEMPTY };
+constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader, warp 9 MMA issuer
+constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
+enum { F0 = 0, E0 = NSLOT, DFULL = 2 * NSLOT, DEMPTY };
 static_assert(SMEM <= 232448, "pool2_cls: shared memory over the 227 KB limit");
+static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "pool2_cls: TMA destinations must be 128-byte aligned");
 }  // namespace p2c
 
 // yq f16 [25][4][8][PR2][PC2][8];  wcq f16 per block [8 kchunks][N rows = map*16 + cls][8];
 // lmap f32 [4][25][4][PR2][PC2][4]
+// The kernel streams 3.2 KB of Y per position once: every Y variant tile ((TH+1) rows x 32 entries x 8 chunks,
+// 20 KB) is ONE cp.async.bulk.tensor (TMA, 4-D tile mode, zero fill outside the plane) into a ring of 8 slots,
+// each with its own full / empty mbarrier, so a single loader thread runs up to 8 variants ahead of the MMAs.
 __global__ void __launch_bounds__(p2c::kThreads, 1)
-pool2_cls_kernel(const __half* __restrict__ yq, int PR2, int PC2, const unsigned char* __restrict__ wcq,
+pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, const unsigned char* __restrict__ wcq,
                  float* __restrict__ lmap) {
   using namespace p2c;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -322,10 +325,10 @@ pool2_cls_kernel(const __half* __restrict__ yq, int PR2, int PC2, const unsigned
     uint4* sw = reinterpret_cast<uint4*>(smem + S_W);
     for (int i = tid; i < WBYTES / 16; i += kThreads) sw[i] = __ldg(gw + i);
     uint4* z = reinterpret_cast<uint4*>(smem + S_T);
-    for (int i = tid; i < NSTAGE * NSLOT * TBYTES / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (NSLOT * TBYTES + 128) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bars + 8 * (F0 + s), kLoad); mbar_init(bars + 8 * (E0 + s), 1); }
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(bars + 8 * (F0 + s), 1); mbar_init(bars + 8 * (E0 + s), 1); }
     mbar_init(bars + 8 * DFULL, 1); mbar_init(bars + 8 * DEMPTY, kEpi);
     fence_barrier_init();
   }
@@ -336,72 +339,73 @@ pool2_cls_kernel(const __half* __restrict__ yq, int PR2, int PC2, const unsigned
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
 
-  if (warp >= 8 && warp < kMmaWarp) {
-    // ================================================================ loaders
-    const int lt = tid - kEpi;
-    uint32_t bc = 0;                                           // block stages filled so far
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int pl = t / tiles_p, tt = t - pl * tiles_p;
-      const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
-      const int y0 = tr * TH, x0 = tc * TW;
+  if (warp == kLoadWarp) {
+    // ================================================================ loader: one TMA per variant tile
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_y);
+      uint32_t slot = 0, ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int pl = t / tiles_p, tt = t - pl * tiles_p;
+        const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
 #pragma unroll 1
-      for (int b = 0; b < 9; ++b, ++bc) {
-        const int Al = b / 3, Be = b - Al * 3;
-        const int nr = Al == 1 ? 1 : 2, nk = Be == 1 ? 1 : 2;
-        const uint32_t stage = bc & 1;
-        mbar_wait(bars + 8 * (E0 + stage), ((bc >> 1) & 1) ^ 1, 71);
-        for (int it = lt; it < nr * nk * kTileItems; it += kLoad) {
-          const int q = it / kTileItems, e = it - q * kTileItems;
-          const int su = q / nk, sv = q - su * nk;
-          const int rx = e & 31, ch = (e >> 5) & 7, ry = e >> 8;
-          const int var = ycls(Al, su) * 5 + ycls(Be, sv);
-          const int y = y0 + ry, x = x0 + rx;
-          const bool in = y < PR2 && x < PC2;
-          const __half* src = yq + ((int64_t(var * 4 + pl) * 8 + ch) * psz + (in ? int64_t(y) * PC2 + x : 0)) * 8;
-          cp_async16_zfill(sbase + S_T + (stage * NSLOT + su * 2 + sv) * TBYTES + ch * CH + (ry * TP + rx) * 16, src,
-                           in ? 16u : 0u);
+        for (int b = 0; b < 9; ++b) {
+          const int Al = b / 3, Be = b - Al * 3;
+          const int nr = Al == 1 ? 1 : 2, nk = Be == 1 ? 1 : 2;
+#pragma unroll 1
+          for (int q = 0; q < nr * nk; ++q) {
+            const int su = q / nk, sv = q - su * nk;
+            const int var = ycls(Al, su) * 5 + ycls(Be, sv);
+            mbar_wait(bars + 8 * (E0 + slot), ph ^ 1, 71);
+            mbar_arrive_expect_tx(bars + 8 * (F0 + slot), TBYTES);
+            tma_load_tile(sbase + S_T + slot * TBYTES, &tm_y, tc * TW, tr * TH, var * 4 + pl, bars + 8 * (F0 + slot));
+            if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+          }
         }
-        cp_async_wait_all();
-        fence_proxy_async();
-        mbar_arrive(bars + 8 * (F0 + stage));
       }
     }
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     if (tmem != 0) { printf("pool2_cls: unexpected TMEM base %u\n", tmem); __trap(); }
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
-    uint32_t bc = 0, tj = 0;
+    uint32_t slot = 0, ph = 0, tj = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tj) {
       mbar_wait(bars + 8 * DEMPTY, (tj & 1) ^ 1, 72);          // epilogue of the previous tile has drained TMEM
       tc_fence_after();
 #pragma unroll
-      for (int b = 0; b < 9; ++b, ++bc) {
+      for (int b = 0; b < 9; ++b) {
         const int Al = b / 3, Be = b % 3;
         const int N = blk_n(Al) * blk_n(Be) * 16;
-        const uint32_t stage = bc & 1;
-        mbar_wait(bars + 8 * (F0 + stage), (bc >> 1) & 1, 73);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t idesc = make_idesc_f16(128, N);
-          const uint32_t t_lo = ((sbase + S_T + stage * NSLOT * TBYTES) >> 4) | (uint32_t(CH >> 4) << 16);
-          const uint32_t w_lo = ((sbase + S_W + blk_start(b) * 16 * 128) >> 4) | (uint32_t((N * 16) >> 4) << 16);
+        const int nr = Al == 1 ? 1 : 2, nk = Be == 1 ? 1 : 2;
+        const uint32_t idesc = make_idesc_f16(128, N);
+        const uint32_t w_lo = ((sbase + S_W + blk_start(b) * 16 * 128) >> 4) | (uint32_t((N * 16) >> 4) << 16);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+        for (int q = 0; q < nr * nk; ++q) {
+          const int su = q / nk, sv = q % nk;
+          mbar_wait(bars + 8 * (F0 + slot), ph, 73);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t t_lo = ((sbase + S_T + slot * TBYTES) >> 4) | (uint32_t(CH >> 4) << 16);
 #pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              const int slot = (Al == 1 ? 0 : u) * 2 + (Be == 1 ? 0 : v);
+            for (int u = 0; u < 2; ++u) {
+              if (Al != 1 && u != su) continue;                // a border row class has one variant per u
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t a = t_lo + uint32_t((slot * TBYTES + (u * TP + v) * 16 + ks * 2 * CH) / 16);
-                const uint32_t bw = w_lo + uint32_t((ks * 2 * N * 16) / 16);
-                umma_f16(uint32_t(blk_start(b) * 16), kHi | uint64_t(a), kHi | uint64_t(bw), idesc, (u | v | ks) ? 1u : 0u);
+              for (int v = 0; v < 2; ++v) {
+                if (Be != 1 && v != sv) continue;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint32_t a = t_lo + uint32_t(((u * TP + v) * 16 + ks * 2 * CH) / 16);
+                  const uint32_t bw = w_lo + uint32_t((ks * 2 * N * 16) / 16);
+                  const bool first = q == 0 && ks == 0 && u == (Al != 1 ? su : 0) && v == (Be != 1 ? sv : 0);
+                  umma_f16(uint32_t(blk_start(b) * 16), kHi | uint64_t(a), kHi | uint64_t(bw), idesc, first ? 0u : 1u);
+                }
               }
             }
+            umma_commit(bars + 8 * (E0 + slot));
+            if (b == 8 && q == nr * nk - 1) umma_commit(bars + 8 * DFULL);
           }
-          umma_commit(bars + 8 * (E0 + stage));
-          if (b == 8) umma_commit(bars + 8 * DFULL);
+          __syncwarp();
+          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         }
-        __syncwarp();
       }
     }
   } else {
@@ -483,8 +487,10 @@ extern "C" int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_row
   CMLPL_CUDA(cudaFuncSetAttribute(pool2_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2c::SMEM));
   const int ntiles = 4 * ((PR2 + p2c::TH - 1) / p2c::TH) * ((PC2 + p2c::TW - 1) / p2c::TW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
-  pool2_cls_kernel<<<grid, p2c::kThreads, p2c::SMEM, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(yq), PR2, PC2, pk + L.wcq, lmap);
+  CUtensorMap tm_y;
+  const int trc = make_scene_tmap(&tm_y, yq, 100, PR2, PC2, p2c::TH + 1, p2c::TP);
+  if (trc != CMLPL_OK) return trc;
+  pool2_cls_kernel<<<grid, p2c::kThreads, p2c::SMEM, static_cast<cudaStream_t>(stream)>>>(tm_y, PR2, PC2, pk + L.wcq, lmap);
   CMLPL_CHECK_LAUNCH("pool2_cls");
   return CMLPL_OK;
 }
