@@ -17,6 +17,7 @@
 // class b; the epilogue forms top = R1+R2, mid = R0+R1+R2, bot = R0+R1 in the same lane.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tma.cuh"
 
 namespace cmlpl {
 
@@ -251,11 +252,11 @@ __global__ void pool1_scene_kernel(const float* __restrict__ g, int PR, int PC, 
 //   PM[A][B] = 1/4 (V[A][b0(B)](x) + V[A][b1(B)](x+1))               (b0,b1 = left,mid | mid,mid | mid,right)
 namespace c1p {
 constexpr int TH = 4, TP = 32, OH = 3, OW = 29;      // conv rows, row pitch; pooled rows / columns per tile
-constexpr int ENT = 1 + (TH + 2) * TP + 1;
-constexpr int CH = ENT * 16 + 16;
+constexpr int CH = (TH + 2) * TP * 16;               // 3 072: one chunk plane of the conv0 tile, dense (written by TMA)
 constexpr int ABYTES = 8 * CH;
 constexpr int WBYTES = 3 * 8 * 192 * 16;
-constexpr int kEpi = 256, kLoad = 64, kThreads = kEpi + kLoad + 32;
+constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader (one thread, TMA), warp 9 MMA issuer
+constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int XBYTES = 12 * kEpi * 16;               // exchange: 12 float4 (G[mid|bot][3 b][8 ch]) per epilogue thread
 constexpr int S_W = 0, S_A = WBYTES, S_X = S_A + 2 * ABYTES, S_BIAS = S_X + 2 * XBYTES, S_BAR = S_BIAS + 256,
               S_TMEM = S_BAR + 128;
@@ -265,12 +266,13 @@ constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
 enum { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, S_FULL0 = 4, S_EMPTY0 = 4 + NSUB };
 static_assert(SMEM <= 232448, "conv1_pool: shared memory over the 227 KB limit");
 static_assert(S_EMPTY0 + NSUB <= 16, "conv1_pool: barrier area too small");
+static_assert(S_A % 128 == 0 && ABYTES % 128 == 0, "conv1_pool: TMA destinations must be 128-byte aligned");
 }  // namespace c1p
 
 // f0: f16 chunk-planar [8][PR][PC][8];  pmq f16 [9 = A*3+B][4 planes][8 chunks][PR2][PC2][8]
 __global__ void __launch_bounds__(c1p::kThreads, 1)
-conv1_pool_kernel(const __half* __restrict__ f0, int PR, int PC, int PR2, int PC2, const unsigned char* __restrict__ w1p,
-                  const float* __restrict__ b1g, __half* __restrict__ pmq) {
+conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int PR2, int PC2,
+                  const unsigned char* __restrict__ w1p, const float* __restrict__ b1g, __half* __restrict__ pmq) {
   using namespace c1p;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -290,40 +292,32 @@ conv1_pool_kernel(const __half* __restrict__ f0, int PR, int PC, int PR2, int PC
   }
   if (tid < 64) sbias[tid] = b1g[tid];
   if (tid == 0) {
-    mbar_init(bars + 8 * A_FULL0, kLoad); mbar_init(bars + 8 * A_FULL1, kLoad);
+    mbar_init(bars + 8 * A_FULL0, 1); mbar_init(bars + 8 * A_FULL1, 1);
     mbar_init(bars + 8 * A_EMPTY0, 1 + kEpi); mbar_init(bars + 8 * A_EMPTY1, 1 + kEpi);
     for (int s = 0; s < NSUB; ++s) { mbar_init(bars + 8 * (S_FULL0 + s), 1); mbar_init(bars + 8 * (S_EMPTY0 + s), kEpi); }
     fence_barrier_init();
   }
-  if (warp == 10) tmem_alloc(sbase + S_TMEM, 512);
+  if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
 
-  if (warp >= 8 && warp < 10) {
-    // ================================================================ loaders: (TH+2) x TP entries, zero outside the map
-    const int lt = tid - kEpi;
-    uint32_t j = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
-      const uint32_t buf = j & 1, ph = (j >> 1) & 1;
-      const int tr = t / tiles_c, tc = t - tr * tiles_c;
-      const int pr0 = tr * OH - 1, pc0 = tc * OW - 1;          // map coords of entry (ry=0, rx=0)
-      mbar_wait(bars + 8 * (A_EMPTY0 + buf), ph ^ 1, 81);
-      for (int it = lt; it < (TH + 2) * TP * 8; it += kLoad) {
-        const int ch = it & 7, e = it >> 3;
-        const int ry = e / TP, rx = e - ry * TP;
-        const int pr = pr0 + ry, pc = pc0 + rx;
-        const bool in = pr >= 0 && pr < PR && pc >= 0 && pc < PC;
-        const __half* src = f0 + ((int64_t(ch) * PR + (in ? pr : 0)) * PC + (in ? pc : 0)) * 8;
-        cp_async16_zfill(sbase + S_A + buf * ABYTES + ch * CH + (1 + e) * 16, src, in ? 16u : 0u);
+  if (warp == kLoadWarp) {
+    // ================================================================ loader: one TMA box per tile ((TH+2) x TP entries, zero outside the map)
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_f0);
+      uint32_t j = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+        const uint32_t buf = j & 1, ph = (j >> 1) & 1;
+        const int tr = t / tiles_c, tc = t - tr * tiles_c;
+        mbar_wait(bars + 8 * (A_EMPTY0 + buf), ph ^ 1, 81);
+        mbar_arrive_expect_tx(bars + 8 * (A_FULL0 + buf), ABYTES);
+        tma_load_tile(sbase + S_A + buf * ABYTES, &tm_f0, tc * OW - 1, tr * OH - 1, 0, bars + 8 * (A_FULL0 + buf));
       }
-      cp_async_wait_all();
-      fence_proxy_async();
-      mbar_arrive(bars + 8 * (A_FULL0 + buf));
     }
-  } else if (warp == 10) {
+  } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     if (tmem != 0) { printf("conv1_pool: unexpected TMEM base %u\n", tmem); __trap(); }
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
@@ -332,7 +326,8 @@ conv1_pool_kernel(const __half* __restrict__ f0, int PR, int PC, int PR2, int PC
     uint32_t j = 0, slot = 0, sph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const uint32_t buf = j & 1, ph = (j >> 1) & 1;
-      const uint32_t a_lo = ((sbase + S_A + buf * ABYTES) >> 4) | (uint32_t(CH >> 4) << 16);
+      // MMA row m of tap (dy,dx) reads tile entry m + dy*TP + dx - 1: descriptors start 16 B before the tile
+      const uint32_t a_lo = ((sbase + S_A + buf * ABYTES - 16) >> 4) | (uint32_t(CH >> 4) << 16);
       mbar_wait(bars + 8 * (A_FULL0 + buf), ph, 82);
 #pragma unroll 1
       for (int hd = 0; hd < 6; ++hd) {                         // sub-stage = (channel half h, tap row dy)
@@ -398,7 +393,7 @@ conv1_pool_kernel(const __half* __restrict__ f0, int PR, int PC, int PR2, int PC
           }
           float base[8];
           {
-            const uint4 rv = *reinterpret_cast<const uint4*>(smem + S_A + buf * ABYTES + chunk * CH + (1 + (ty + 1) * TP + tx) * 16);
+            const uint4 rv = *reinterpret_cast<const uint4*>(smem + S_A + buf * ABYTES + chunk * CH + ((ty + 1) * TP + tx) * 16);
             const __half2* hr = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -486,7 +481,7 @@ conv1_pool_kernel(const __half* __restrict__ f0, int PR, int PC, int PR2, int PC
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 }  // namespace cmlpl
@@ -534,9 +529,11 @@ extern "C" int cmlpl_conv1_pool_planes_f16(const void* f0pad, int cols, int w, i
   CMLPL_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1p::SMEM));
   const int ntiles = ((2 * PR2 + c1p::OH - 1) / c1p::OH) * ((2 * PC2 + c1p::OW - 1) / c1p::OW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
+  CUtensorMap tm_f0;
+  const int trc = make_scene_tmap(&tm_f0, f0pad, 1, PR, PC, c1p::TH + 2, c1p::TP);
+  if (trc != CMLPL_OK) return trc;
   conv1_pool_kernel<<<grid, c1p::kThreads, c1p::SMEM, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(f0pad), PR, PC, PR2, PC2, pk + L.w1, reinterpret_cast<const float*>(pk + L.b1),
-      static_cast<__half*>(pmq));
+      tm_f0, PR, PC, PR2, PC2, pk + L.w1, reinterpret_cast<const float*>(pk + L.b1), static_cast<__half*>(pmq));
   CMLPL_CHECK_LAUNCH("conv1_pool");
   return CMLPL_OK;
 }

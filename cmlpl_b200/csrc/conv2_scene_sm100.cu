@@ -77,7 +77,8 @@ __global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC,
 // conv2_scene_kernel: persistent, warp-specialised tcgen05 implicit GEMM over 4x30-position tiles of a
 // parity plane (M = 128 rows = 4 rows x 32 columns incl. one halo column each side; taps = A-descriptor
 // offsets in zero-haloed row-major tiles, exactly like conv1_scene_kernel).  Per tile the nine PM
-// variant tiles are loaded once, as three "slabs" of 3 row classes x one column class:
+// variant tiles are loaded once by TMA (one 24 KB box each, zero fill outside the plane), as three "slabs" of
+// 3 row classes x one column class:
 //     slab X <- left, slab M <- mid   : column classes kap = 0, 1
 //                        (mid only)    : kap = 2
 //     slab X <- right                  : kap = 3, 4
@@ -85,18 +86,17 @@ __global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC,
 // the epilogue (bias + residual + ReLU -> fp16) of one variant overlaps the MMAs of the next ones.
 namespace c2s {
 constexpr int TH = 4, TP = 32, TW = 30;
-constexpr int ENT = 1 + (TH + 2) * TP + 1;           // 194 entries per 16-byte chunk plane
-constexpr int CH = ENT * 16 + 16;                    // bytes between chunk planes (+16: bank spread)
-constexpr int TBYTES = 8 * CH;                       // one PM variant tile
+constexpr int CH = (TH + 2) * TP * 16;               // 3 072: one chunk plane of a tile, dense (written by TMA)
+constexpr int TBYTES = 8 * CH;                       // 24 576: one PM variant tile
 constexpr int WBYTES = 3 * 8 * 192 * 16;             // 73 728
 constexpr int S_W = 0, S_T = WBYTES, S_BIAS = S_T + 6 * TBYTES, S_BAR = S_BIAS + 256, S_TMEM = S_BAR + 256;
 constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
-constexpr int kEpi = 256, kLoad = 128, kThreads = kEpi + kLoad + 32;
-constexpr int kMmaWarp = (kEpi + kLoad) / 32;
+constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader (one thread, TMA), warp 9 MMA issuer
+constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
-constexpr int kSlabItems = 3 * (TH + 2) * TP * 8;    // 16-byte copies per slab
 enum { XF = 0, MF, XE, ME, DF0 = 4, DE0 = 12 };
 static_assert(SMEM <= 232448, "conv2_scene: shared memory over the 227 KB limit");
+static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "conv2_scene: TMA destinations must be 128-byte aligned");
 
 // all taps of variant (RHO, KAP) into TMEM columns [d, d+64); t_lo / w_lo = low descriptor words of tile 0 /
 // the weight block of dx = 0.  Every offset is an immediate.
@@ -116,7 +116,7 @@ __device__ __forceinline__ void issue_variant(uint32_t d, uint32_t t_lo, uint32_
       const int tile = (cls_of(j2) == 1 ? 3 : 0) + cls_of(i2);     // slab M holds the mid column class
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t a = t_lo + uint32_t((tile * TBYTES + (dy * TP + dx) * 16 + ks * 2 * CH) / 16);
+        const uint32_t a = t_lo + uint32_t((tile * TBYTES + (dy * TP + dx) * 16 + ks * 2 * CH) / 16);   // t_lo = tile 0 - 16 B
         const uint32_t b = w_lo + uint32_t((dx * kWDx + ks * 2 * kWLbo) / 16) + uint32_t((2 - dy) * 64);
         umma_f16(d, kHi | uint64_t(a), kHi | uint64_t(b), kI64, acc);
         acc = 1;
@@ -128,8 +128,8 @@ __device__ __forceinline__ void issue_variant(uint32_t d, uint32_t t_lo, uint32_
 
 // pmq f16 [9][4][8][PR2][PC2][8];  yq f16 [25 = rho*5+kap][4][8][PR2][PC2][8]
 __global__ void __launch_bounds__(c2s::kThreads, 1)
-conv2_scene_kernel(const __half* __restrict__ pmq, int PR2, int PC2, const unsigned char* __restrict__ w2p,
-                   const float* __restrict__ b2g, __half* __restrict__ yq) {
+conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __restrict__ pmq, int PR2, int PC2,
+                   const unsigned char* __restrict__ w2p, const float* __restrict__ b2g, __half* __restrict__ yq) {
   using namespace c2s;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -149,7 +149,7 @@ conv2_scene_kernel(const __half* __restrict__ pmq, int PR2, int PC2, const unsig
   }
   if (tid < 64) sbias[tid] = b2g[tid];
   if (tid == 0) {
-    mbar_init(bars + 8 * XF, kLoad); mbar_init(bars + 8 * MF, kLoad);
+    mbar_init(bars + 8 * XF, 1); mbar_init(bars + 8 * MF, 1);
     mbar_init(bars + 8 * XE, 1); mbar_init(bars + 8 * ME, 1);
     for (int s = 0; s < 8; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi); }
     fence_barrier_init();
@@ -161,37 +161,33 @@ conv2_scene_kernel(const __half* __restrict__ pmq, int PR2, int PC2, const unsig
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
 
-  if (warp >= 8 && warp < kMmaWarp) {
-    // ================================================================ loaders
-    const int lt = tid - kEpi;
-    uint32_t fx = 0, fm = 0;                                   // fills of slab X / slab M so far
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int pl = t / tiles_p, tt = t - pl * tiles_p;
-      const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
-      const int y0 = tr * TH - 1, x0 = tc * TW - 1;            // plane coords of entry (ry=0, rx=0)
+  if (warp == kLoadWarp) {
+    // ================================================================ loader: one thread, three TMA boxes per slab
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_pm);
+      uint32_t fx = 0, fm = 0;                                 // fills of slab X / slab M so far
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int pl = t / tiles_p, tt = t - pl * tiles_p;
+        const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
+        const int y0 = tr * TH - 1, x0 = tc * TW - 1;          // plane coords of entry (ry=0, rx=0); borders zero-filled
 #pragma unroll 1
-      for (int step = 0; step < 3; ++step) {                   // left -> X, mid -> M, right -> X
-        const int slab = step == 1 ? 1 : 0, bcls = step;
-        const uint32_t k = slab ? fm : fx;
-        mbar_wait(bars + 8 * (slab ? ME : XE), (k & 1) ^ 1, 61);
-        for (int it = lt; it < kSlabItems; it += kLoad) {
-          const int rx = it & 31, ch = (it >> 5) & 7, q = it >> 8;
-          const int a = q / (TH + 2), ry = q - a * (TH + 2);
-          const int y = y0 + ry, x = x0 + rx;
-          const bool in = y >= 0 && y < PR2 && x >= 0 && x < PC2;
-          const __half* src = pmq + ((int64_t((a * 3 + bcls) * 4 + pl) * 8 + ch) * psz + (in ? int64_t(y) * PC2 + x : 0)) * 8;
-          cp_async16_zfill(sbase + S_T + (slab * 3 + a) * TBYTES + ch * CH + (1 + ry * TP + rx) * 16, src, in ? 16u : 0u);
+        for (int step = 0; step < 3; ++step) {                 // left -> X, mid -> M, right -> X
+          const int slab = step == 1 ? 1 : 0, bcls = step;
+          const uint32_t k = slab ? fm : fx;
+          const uint32_t full = bars + 8 * (slab ? MF : XF);
+          mbar_wait(bars + 8 * (slab ? ME : XE), (k & 1) ^ 1, 61);
+          mbar_arrive_expect_tx(full, 3 * TBYTES);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            tma_load_tile(sbase + S_T + (slab * 3 + a) * TBYTES, &tm_pm, x0, y0, (a * 3 + bcls) * 4 + pl, full);
+          if (slab) ++fm; else ++fx;
         }
-        cp_async_wait_all();
-        fence_proxy_async();
-        mbar_arrive(bars + 8 * (slab ? MF : XF));
-        if (slab) ++fm; else ++fx;
       }
     }
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     if (tmem != 0) { printf("conv2_scene: unexpected TMEM base %u\n", tmem); __trap(); }
-    const uint32_t t_lo = ((sbase + S_T) >> 4) | (uint32_t(CH >> 4) << 16);
+    const uint32_t t_lo = ((sbase + S_T - 16) >> 4) | (uint32_t(CH >> 4) << 16);
     const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
     uint32_t fx = 0, fm = 0, vc = 0;                           // slab fills consumed, variants issued
 #define C2S_VARIANT(RHO, KAP)                                                        \
@@ -470,8 +466,12 @@ extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_
   CMLPL_CUDA(cudaFuncSetAttribute(conv2_scene_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c2s::SMEM));
   const int ntiles = 4 * ((PR2 + c2s::TH - 1) / c2s::TH) * ((PC2 + c2s::TW - 1) / c2s::TW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
+  CUtensorMap tm_pm;
+  const int trc = make_scene_tmap(&tm_pm, pmq, 36, PR2, PC2, c2s::TH + 2, c2s::TP);
+  if (trc != CMLPL_OK) return trc;
   conv2_scene_kernel<<<grid, c2s::kThreads, c2s::SMEM, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(pmq), PR2, PC2, pk + L.w2, reinterpret_cast<const float*>(pk + L.b2), static_cast<__half*>(yq));
+      tm_pm, static_cast<const __half*>(pmq), PR2, PC2, pk + L.w2, reinterpret_cast<const float*>(pk + L.b2),
+      static_cast<__half*>(yq));
   CMLPL_CHECK_LAUNCH("conv2_scene");
   return CMLPL_OK;
 }
