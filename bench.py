@@ -290,7 +290,7 @@ def main():
     assert off[10] == ws.numel() and off[11] == 1, "bench expects the tensor-core scene path"
     o_f0, o_x16, o_h16, o_g, o_pmq, o_yq, o_lmap = (ws.data_ptr() + off[i] for i in range(7))
     pk = packed.data_ptr()
-    names = ["conv0_map", "spectral_hidden", "conv1_scene", "conv2_scene", "pool2_cls", "head"]
+    names = ["conv0_map", "spectral_logits", "conv1_pool", "conv2_scene", "pool2_cls", "head_sum"]
     NS = len(names)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(NS + 1)] for _ in range(args.steps)]
     for it in range(args.warmup + args.steps):
@@ -298,7 +298,7 @@ def main():
         if e[0]: e[0].record()
         _lib.call("cmlpl_conv0_map_f16", slab.data_ptr(), scene_rows, C0, s0, s1 - s0, W0, r0, nb, pk, o_f0, st)
         if e[1]: e[1].record()
-        _lib.call("cmlpl_spectral_hidden_tc", spec.data_ptr(), n_band, B0, K0, W0, pk, o_x16, o_h16, st)
+        _lib.call("cmlpl_spectral_logits_tc", spec.data_ptr(), n_band, B0, K0, W0, pk, o_x16, o_h16, st)
         if e[2]: e[2].record()
         _lib.call("cmlpl_conv1_pool_planes_f16", o_f0, C0, W0, nb, pk, o_pmq, st)
         if e[3]: e[3].record()
@@ -306,7 +306,7 @@ def main():
         if e[4]: e[4].record()
         _lib.call("cmlpl_pool2_cls_f16", o_yq, C0, W0, nb, B0, K0, pk, o_lmap, st)
         if e[5]: e[5].record()
-        _lib.call("cmlpl_head_lmap_tc", o_h16, o_lmap, C0, nb, B0, K0, W0, pk, labels.data_ptr(), None, st)
+        _lib.call("cmlpl_head_sum_lmap", o_h16, o_lmap, C0, nb, B0, K0, W0, pk, labels.data_ptr(), None, st)
         if e[6]: e[6].record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -424,7 +424,7 @@ def main():
                              "at half the N=128 rate); in the reference's per-patch arithmetic (7.37 MFLOP/pixel for conv2, "
                              "40.2 for the net) the same launch / step is reference_arithmetic_tflops / "
                              "whole_step_algorithmic_tflops, above the hardware peak by the sharing factor",
-                     "conv1_scene_executed_tflops": conv1_exec_flop / (stage_ms["conv1_scene"] / 1e3) / 1e12,
+                     "conv1_scene_executed_tflops": conv1_exec_flop / (stage_ms["conv1_pool"] / 1e3) / 1e12,
                      "kernel_ms": cnn_ms, "stage_ms": stage_ms,
                      "whole_step_algorithmic_tflops": px_step / world * FLOP_PER_PX_ALL / (ms_dev / 1e3) / 1e12},
         "host_prep_s": t_data,

@@ -290,17 +290,252 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
   if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 32); }
 }
 
+
+// ------------------------------------------------------------------ spectral logits: Wc_spe . relu(Wspe . x + b), hidden never in HBM
+// spectral_logits_kernel fuses the two GEMMs of the spectral branch (models.py:142-143 and the spectral columns of
+// models.py:150): a CTA owns one quarter (256) of the 1024 hidden features and walks pixel tiles of 128.
+//   MMA1 (M=128, N=128, K=B)  hidden half-tile -> TMEM (ring of 3)
+//   epilogue                   bias + ReLU -> fp16 -> shared memory in the UMMA K-major layout (ring of nH half-tiles)
+//   MMA2 (M=128, N=16, K=128)  classifier columns of those hidden features, accumulated over both halves -> TMEM
+//   readout                    part[quarter][pixel][16] f32: the head adds the 4 quarter partials (53 MB instead of the
+//                              425 MB hidden tensor written and read back)
+namespace spl {
+constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader, warp 9 MMA issuer
+constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
+constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
+constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, logits accumulators at 384/400
+enum { A_FULL0 = 0, A_EMPTY0 = 2, D1_FULL0 = 4, D1_EMPTY0 = 7, H_FULL0 = 10, H_EMPTY0 = 12, L_FULL0 = 14, L_EMPTY0 = 16 };
+}  // namespace spl
+
+__global__ void __launch_bounds__(spl::kThreads, 1)
+spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, int nA, int nH,
+                       const __half* __restrict__ w1t, const float* __restrict__ bspe,
+                       const __half* __restrict__ wc_spe16, float* __restrict__ part) {
+  using namespace spl;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t wbytes = uint32_t(KC) * 4096, abytes = uint32_t(KC) * 2048;
+  const uint32_t S_W = 0, S_A = wbytes, S_H = S_A + uint32_t(nA) * abytes, S_WC = S_H + uint32_t(nH) * HBYTES,
+                 S_BIAS = S_WC + WCBYTES, S_BAR = S_BIAS + 1024, S_TMEM = S_BAR + 256;
+  const uint32_t bars = sbase + S_BAR;
+  const int ntile = blockIdx.x & 3;
+  const int64_t mt0 = blockIdx.x >> 2, mstep = gridDim.x >> 2;
+  const int64_t my_tiles = mt0 < mtiles ? (mtiles - mt0 + mstep - 1) / mstep : 0;
+  const uint32_t U = uint32_t(2 * my_tiles);           // units = (tile, hidden half)
+
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(w1t) + size_t(ntile) * (wbytes / 16);
+    uint4* sd = reinterpret_cast<uint4*>(smem + S_W);
+    for (uint32_t i = tid; i < wbytes / 16; i += kThreads) sd[i] = __ldg(g + i);
+    const uint4* gc = reinterpret_cast<const uint4*>(wc_spe16) + size_t(ntile) * (WCBYTES / 16);
+    uint4* sc = reinterpret_cast<uint4*>(smem + S_WC);
+    for (uint32_t i = tid; i < WCBYTES / 16; i += kThreads) sc[i] = __ldg(gc + i);
+    float* sb = reinterpret_cast<float*>(smem + S_BIAS);
+    if (tid < 256) sb[tid] = bspe[ntile * 256 + tid];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + 8 * (H_FULL0 + i), kEpi); mbar_init(bars + 8 * (H_EMPTY0 + i), 1);
+      mbar_init(bars + 8 * (L_FULL0 + i), 1); mbar_init(bars + 8 * (L_EMPTY0 + i), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(sbase + S_TMEM, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
+
+  if (warp == 8) {
+    // ================================================================ loader: one bulk copy per pixel tile
+    if (lane == 0) {
+      for (uint32_t j = 0; j < uint32_t(my_tiles); ++j) {
+        const uint32_t s = j % uint32_t(nA), ph = (j / uint32_t(nA)) & 1;
+        mbar_wait(bars + 8 * (A_EMPTY0 + s), ph ^ 1, 91);
+        mbar_arrive_expect_tx(bars + 8 * (A_FULL0 + s), abytes);
+        bulk_g2s(sbase + S_A + s * abytes, x16 + (mt0 + int64_t(j) * mstep) * int64_t(KC) * 1024, abytes, bars + 8 * (A_FULL0 + s));
+      }
+    }
+  } else if (warp == 9) {
+    // ================================================================ MMA issuer
+    if (tmem != 0) { printf("spectral_logits: unexpected TMEM base %u\n", tmem); __trap(); }
+    constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
+    constexpr uint32_t idesc1 = make_idesc_f16(128, 128), idesc2 = make_idesc_f16(128, 16);
+    auto issue1 = [&](uint32_t u) {                    // hidden half-tile of unit u
+      const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, s = ti % uint32_t(nA);
+      if (hh == 0) mbar_wait(bars + 8 * (A_FULL0 + s), (ti / uint32_t(nA)) & 1, 92);
+      mbar_wait(bars + 8 * (D1_EMPTY0 + d), ((u / 3) & 1) ^ 1, 93);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        uint32_t a_lo = ((sbase + S_A + s * abytes) >> 4) | (uint32_t(2048 >> 4) << 16);
+        uint32_t b_lo = ((sbase + S_W + hh * 2048) >> 4) | (uint32_t(4096 >> 4) << 16);
+        for (int ks = 0; ks < KC / 2; ++ks) {
+          umma_f16(d * 128, kHi | a_lo, kHi | b_lo, idesc1, ks ? 1u : 0u);
+          a_lo += 4096 >> 4; b_lo += 8192 >> 4;
+        }
+        umma_commit(bars + 8 * (D1_FULL0 + d));
+        if (hh == 1) umma_commit(bars + 8 * (A_EMPTY0 + s));
+      }
+      __syncwarp();
+    };
+    auto issue2 = [&](uint32_t u) {                    // classifier columns over the hidden half-tile of unit u
+      const uint32_t ti = u >> 1, hh = u & 1, hs = u % uint32_t(nH), ls = ti & 1;
+      mbar_wait(bars + 8 * (H_FULL0 + hs), (u / uint32_t(nH)) & 1, 94);
+      if (hh == 0) mbar_wait(bars + 8 * (L_EMPTY0 + ls), ((ti >> 1) & 1) ^ 1, 95);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        uint32_t a_lo = ((sbase + S_H + hs * HBYTES) >> 4) | (uint32_t(2048 >> 4) << 16);
+        uint32_t b_lo = ((sbase + S_WC + hh * 16 * 256) >> 4) | (uint32_t(256 >> 4) << 16);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          umma_f16(D2COL + ls * 16, kHi | a_lo, kHi | b_lo, idesc2, (hh | ks) ? 1u : 0u);
+          a_lo += 4096 >> 4; b_lo += 512 >> 4;
+        }
+        umma_commit(bars + 8 * (H_EMPTY0 + hs));
+        if (hh == 1) umma_commit(bars + 8 * (L_FULL0 + ls));
+      }
+      __syncwarp();
+    };
+    if (U > 0) issue1(0);
+    if (U > 1) issue1(1);
+    for (uint32_t u = 0; u < U; ++u) {
+      issue2(u);
+      if (u + 2 < U) issue1(u + 2);
+    }
+  } else {
+    // ================================================================ epilogue (warps 0-7)
+    const int q = warp & 3, ch = warp >> 2, L = q * 32 + lane;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const float* sb = reinterpret_cast<const float*>(smem + S_BIAS);
+    auto readout = [&](uint32_t ti) {                  // partial logits of tile ti (warps 0-3: one lane quarter each)
+      const uint32_t ls = ti & 1;
+      mbar_wait(bars + 8 * (L_FULL0 + ls), (ti >> 1) & 1, 96);
+      tc_fence_after();
+      float v[16];
+      tmem_ld16(lane_addr + D2COL + ls * 16, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bars + 8 * (L_EMPTY0 + ls));
+      float4* dst = reinterpret_cast<float4*>(part) + ((int64_t(ntile) * mtiles + (mt0 + int64_t(ti) * mstep)) * 128 + L) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    };
+    for (uint32_t u = 0; u < U; ++u) {
+      const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, hs = u % uint32_t(nH);
+      if (ch == 0 && hh == 0 && ti > 0) readout(ti - 1);
+      mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
+      mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
+      tc_fence_after();
+      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * 8) * 2048 + L * 16;
+      const float* bb = sb + hh * 128 + ch * 64;
+#pragma unroll
+      for (int g = 0; g < 4; g += 2) {
+        float v0[16], v1[16];
+        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 16, v0);
+        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 16 + 16, v1);
+        tmem_ld_wait();
+        if (g == 2) { tc_fence_before(); mbar_arrive(bars + 8 * (D1_EMPTY0 + d)); }
+        __half2 h[16];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          h[e] = __floats2half2_rn(fmaxf(v0[2 * e] + bb[g * 16 + 2 * e], 0.f), fmaxf(v0[2 * e + 1] + bb[g * 16 + 2 * e + 1], 0.f));
+          h[8 + e] = __floats2half2_rn(fmaxf(v1[2 * e] + bb[g * 16 + 16 + 2 * e], 0.f),
+                                        fmaxf(v1[2 * e + 1] + bb[g * 16 + 16 + 2 * e + 1], 0.f));
+        }
+        const uint4* hv = reinterpret_cast<const uint4*>(h);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(hdst + (g * 2 + k) * 2048) = hv[k];
+      }
+      fence_proxy_async();                             // generic-proxy writes of H -> visible to the tensor core
+      mbar_arrive(bars + 8 * (H_FULL0 + hs));
+    }
+    if (ch == 0 && my_tiles > 0) readout(uint32_t(my_tiles - 1));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------ head of the dense path: sums + argmax
+// logits(p) = bc + sum over the 4 hidden quarters of part[q][p] + the 25 gathered conv partials of pixel p
+// (class-partial maps of pool2_cls_kernel); first index wins ties (hyper_tools.py:426).  One thread per pixel:
+// adjacent lanes read adjacent 16-byte quads of the two parity planes of a row.
+__global__ void __launch_bounds__(256)
+head_sum_kernel(const float* __restrict__ part, int64_t mtiles, const float* __restrict__ lmap, int cols, int PR2, int PC2,
+                int64_t n, int C, const float* __restrict__ bc, uint8_t* __restrict__ labels, float* __restrict__ logits) {
+  const int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (p >= n) return;
+  const int nq = (C + 3) >> 2;                         // class quads that hold real classes
+  float v[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = 0.f;
+  const int r = int(p / cols), c0 = int(p - int64_t(r) * cols);
+  const int64_t psz = int64_t(PR2) * PC2;
+  const float4* base = reinterpret_cast<const float4*>(lmap) + int64_t((r & 1) * 2 + (c0 & 1)) * 100 * psz +
+                       int64_t(r >> 1) * PC2 + (c0 >> 1);
+#pragma unroll
+  for (int I = 0; I < 5; ++I) {
+#pragma unroll
+    for (int J = 0; J < 5; ++J) {
+      const float4* q = base + int64_t(lmap_index(I, J) * 4) * psz + (2 * I) * PC2 + 2 * J;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < nq) {
+          const float4 t = __ldg(q + int64_t(k) * psz);
+          v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    const float4* s = reinterpret_cast<const float4*>(part) + (int64_t(qd) * mtiles * 128 + p) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nq) {
+        const float4 t = __ldg(s + k);
+        v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
+      }
+    }
+  }
+  float best = -INFINITY; int arg = 0;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    if (c < C) {
+      const float z = v[c] + __ldg(bc + c);
+      if (logits) logits[p * C + c] = z;
+      if (z > best) { best = z; arg = c; }
+    }
+  }
+  labels[p] = uint8_t(arg);
+}
+
 }  // namespace cmlpl
 
 using namespace cmlpl;
 
+// shared-memory plan of spectral_logits_kernel for KC input k-chunks: prefers 2 input stages + 2 hidden half-tiles
+static bool spectral_logits_plan(int KC, int* nA, int* nH, size_t* smem) {
+  const int opts[3][2] = {{2, 2}, {2, 1}, {1, 1}};
+  for (int i = 0; i < 3; ++i) {
+    const size_t b = size_t(KC) * 4096 + size_t(opts[i][0]) * KC * 2048 + size_t(opts[i][1]) * spl::HBYTES + spl::WCBYTES +
+                     1024 + 256 + 64;
+    if (b <= 232448) { *nA = opts[i][0]; *nH = opts[i][1]; *smem = b; return true; }
+  }
+  return false;
+}
+
 static int spectral_hidden_impl(const void* x, int dtype /* -1 = preprocessed f32 spectra */, int64_t n, int num_features,
                                 int num_classes, int w, const float* mu, const float* inv_sigma, const void* packed,
-                                void* x16, void* h16, cmlpl_stream_t stream) {
+                                void* x16, void* h16, cmlpl_stream_t stream, bool fused_logits = false) {
   CMLPL_CHECK_ARG(x && packed && x16 && h16, "spectral_hidden_tc: null pointer");
   CMLPL_CHECK_ARG(n > 0 && num_features > 0, "spectral_hidden_tc: bad dims");
   const PackedLayout L = packed_layout(num_features, num_classes, w);
-  CMLPL_CHECK_ARG(L.kc_spe_in <= 26, "spectral_hidden_tc: %d bands exceed the 208 the tensor-core tile supports",
+  CMLPL_CHECK_ARG(L.kc_spe_in <= (fused_logits ? 28 : 26), "spectral_hidden_tc: %d bands exceed what the tensor-core tile supports",
                   num_features);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int KC = L.kc_spe_in;
@@ -313,6 +548,21 @@ static int spectral_hidden_impl(const void* x, int dtype /* -1 = preprocessed f3
   else
     x16_tile_raw_kernel<float><<<int(g), 256, 0, s>>>(static_cast<const float*>(x), n, num_features, KC, total, mu, inv_sigma, static_cast<__half*>(x16));
   CMLPL_CHECK_LAUNCH("x16_tile");
+  if (fused_logits) {
+    int nA = 0, nH = 0; size_t fsmem = 0;
+    CMLPL_CHECK_ARG(spectral_logits_plan(KC, &nA, &nH, &fsmem), "spectral_logits_tc: %d bands do not fit shared memory", num_features);
+    CMLPL_CHECK_ARG(num_classes <= 16, "spectral_logits_tc: needs <= 16 classes, got %d", num_classes);
+    CMLPL_CUDA(cudaFuncSetAttribute(spectral_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsmem)));
+    int fgrid = sm_count() / 4 * 4;
+    if (fgrid > mtiles * 4) fgrid = int(mtiles * 4);
+    const unsigned char* fpk = static_cast<const unsigned char*>(packed);
+    spectral_logits_kernel<<<fgrid, spl::kThreads, fsmem, s>>>(
+        static_cast<const __half*>(x16), mtiles, KC, nA, nH, reinterpret_cast<const __half*>(fpk + L.w1s),
+        reinterpret_cast<const float*>(fpk + L.bspe),
+        reinterpret_cast<const __half*>(fpk + L.wc16 + size_t(L.conv_pos) * 8 * 256), static_cast<float*>(h16));
+    CMLPL_CHECK_LAUNCH("spectral_logits");
+    return CMLPL_OK;
+  }
   const size_t smem = size_t(KC) * 8192 + 1024 + 64 + 64;
   CMLPL_CUDA(cudaFuncSetAttribute(spectral_hidden_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int grid = sm_count() / 4 * 4;
@@ -383,5 +633,37 @@ extern "C" int cmlpl_head_lmap_tc(const void* h16, const float* lmap, int cols, 
       reinterpret_cast<const __half*>(pk + L.wc16 + size_t(kc_conv) * 256), reinterpret_cast<const float*>(pk + L.bc),
       labels, logits, lmap, cols, (band_rows + w) / 2, (cols + w) / 2);
   CMLPL_CHECK_LAUNCH("head_lmap");
+  return CMLPL_OK;
+}
+
+// Fused spectral branch of the dense path: part f32 [4 hidden quarters][ceil(n/128)*128][16] partial spectral logits
+// (spectral_logits_kernel; the 1024 hidden features stay in shared memory).  x16 is scratch for the fp16 input tiles.
+extern "C" int cmlpl_spectral_logits_tc(const float* spectra, int64_t n, int num_features, int num_classes, int w,
+                                        const void* packed, void* x16, float* part, cmlpl_stream_t stream) {
+  return spectral_hidden_impl(spectra, -1, n, num_features, num_classes, w, nullptr, nullptr, packed, x16, part, stream, true);
+}
+
+extern "C" int cmlpl_spectral_logits_raw_tc(const void* raw, int dtype, int64_t n, int num_features, int num_classes, int w,
+                                            const float* mu, const float* inv_sigma, const void* packed, void* x16,
+                                            float* part, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG((dtype == 0 || dtype == 1) && mu && inv_sigma, "spectral_logits_raw_tc: bad args");
+  return spectral_hidden_impl(raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed, x16, part, stream, true);
+}
+
+// Head of the dense path without a GEMM: quarter partials of cmlpl_spectral_logits_tc + the 25 gathered conv partials
+// per pixel from lmap (cmlpl_pool2_cls_f16) + bias, argmax.  Pixels are the band's raster order.
+extern "C" int cmlpl_head_sum_lmap(const float* part, const float* lmap, int cols, int band_rows, int num_features,
+                                   int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
+                                   cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(part && lmap && packed && labels, "head_sum_lmap: null pointer");
+  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "head_sum_lmap: bad dims (w must be 20)");
+  CMLPL_CHECK_ARG(num_classes > 0 && num_classes <= 16, "head_sum_lmap: needs 1..16 classes, got %d", num_classes);
+  const PackedLayout L = packed_layout(num_features, num_classes, w);
+  const int64_t n = int64_t(band_rows) * cols, mtiles = (n + 127) / 128;
+  const unsigned char* pk = static_cast<const unsigned char*>(packed);
+  head_sum_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      part, mtiles, lmap, cols, (band_rows + w) / 2, (cols + w) / 2, n, num_classes,
+      reinterpret_cast<const float*>(pk + L.bc), labels, logits);
+  CMLPL_CHECK_LAUNCH("head_sum");
   return CMLPL_OK;
 }

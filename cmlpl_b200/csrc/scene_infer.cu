@@ -10,7 +10,7 @@
 //                    classifier -> 25 class-partial maps (conv2_scene_sm100.cu)
 //   4. head          spectral columns of the classifier (models.py:150) + the pixel's 25 gathered conv
 //                    partials + bias, argmax (hyper_tools.py:426, first index wins ties)
-//   (> 16 classes / > 208 bands: the all-per-pixel patch_cnn_sm100.cu kernel + CUDA-core classify instead)
+//   (> 16 classes / > 224 bands: the all-per-pixel patch_cnn_sm100.cu kernel + CUDA-core classify instead)
 #include "common.cuh"
 #include "gemm_core.cuh"
 
@@ -165,14 +165,14 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int64_t n, int C
 
 // Tensor-core head (head_sm100.cu) applies for <= 16 classes and <= 208 bands; otherwise the
 // CUDA-core spectral_head + classify kernels above run (same C ABI, same results contract).
-static bool use_tc_head(int B, int C) { return C <= 16 && ((B + 15) / 16) * 2 <= 26; }
+static bool use_tc_head(int B, int C) { return C <= 16 && ((B + 15) / 16) * 2 <= 28; }   // <= 224 bands (spectral_logits_kernel)
 
 struct SceneWs {
   size_t f0pad, p2, spe, hidden, x16, h16, g, pm, yq, lmap, total;
   int64_t chunk;
   bool tc;
 };
-// tensor-core path (<= 16 classes, <= 208 bands): conv0 map, spectral tiles, conv1 variants (fp32 scratch), pooled
+// tensor-core path (<= 16 classes, <= 224 bands): conv0 map, spectral tiles, conv1 variants (fp32 scratch), pooled
 // parity planes, the 25 conv2 variants, the 25 class-partial maps.  CUDA-core path: conv0 map, per-pixel pooled
 // features, spectral logits, hidden chunk.
 static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
@@ -187,7 +187,7 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   s.chunk = n < 16384 ? n : 16384;
   if (s.tc) {
     s.x16 = o; o = align256(o + size_t(mtiles) * (((B + 15) / 16) * 2) * 2048);
-    s.h16 = o; o = align256(o + size_t(mtiles) * 128 * 2048);
+    s.h16 = o; o = align256(o + size_t(4) * mtiles * 128 * 64);   // partial spectral logits f32 [4 quarters][mtiles*128][16]
     const size_t qpos = size_t(4) * ((band_rows + w) / 2) * ((cols + w) / 2);     // positions of the 4 parity planes
     s.g = o;                                               // (fp32 conv1 variants: not materialised any more)
     s.pm = o; o = align256(o + qpos * 9 * 64 * 2);         // pooled variants, f16 parity planes [9][4][8][PR2][PC2][8]
@@ -232,8 +232,8 @@ static int dense_tail(unsigned char* wsb, const SceneWs& ws, int cols, int w, in
   rc = cmlpl_pool2_cls_f16(wsb + ws.yq, cols, w, band_rows, num_features, num_classes, packed,
                            reinterpret_cast<float*>(wsb + ws.lmap), stream);
   if (rc != CMLPL_OK) return rc;
-  return cmlpl_head_lmap_tc(wsb + ws.h16, reinterpret_cast<const float*>(wsb + ws.lmap), cols, band_rows, num_features,
-                            num_classes, w, packed, labels, logits, stream);
+  return cmlpl_head_sum_lmap(reinterpret_cast<const float*>(wsb + ws.h16), reinterpret_cast<const float*>(wsb + ws.lmap), cols,
+                             band_rows, num_features, num_classes, w, packed, labels, logits, stream);
 }
 
 extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, int slab_row0, int slab_rows, int w,
@@ -347,7 +347,8 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
                                wsb + ws.f0pad, stream);
   if (rc != CMLPL_OK) return rc;
   if (ws.tc) {
-    rc = cmlpl_spectral_hidden_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16, wsb + ws.h16, stream);
+    rc = cmlpl_spectral_logits_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16,
+                                  reinterpret_cast<float*>(wsb + ws.h16), stream);
     if (rc != CMLPL_OK) return rc;
     return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
   }
@@ -377,7 +378,7 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
   CMLPL_CHECK_ARG(dtype == 0 || dtype == 1, "scene_infer_raw: dtype must be 0 (uint16) or 1 (float32)");
   CMLPL_CHECK_ARG(w == 20, "scene_infer_raw: w=%d unsupported (tools/models.py:127 fixes w=20)", w);
   CMLPL_CHECK_ARG(band_rows > 0 && cols > 0 && num_classes > 0 && num_features > 0, "scene_infer_raw: bad dims");
-  CMLPL_CHECK_ARG(use_tc_head(num_features, num_classes), "scene_infer_raw: needs <= 16 classes and <= 208 bands");
+  CMLPL_CHECK_ARG(use_tc_head(num_features, num_classes), "scene_infer_raw: needs <= 16 classes and <= 224 bands");
   CMLPL_CHECK_ARG(w / 2 <= scene_rows && w / 2 <= cols, "scene_infer_raw: window larger than the scene");
   CMLPL_CHECK_ARG(band_row0 >= 0 && band_row0 + band_rows <= scene_rows, "scene_infer_raw: band outside the scene");
   const int a = band_row0 + window_lo(w), b = band_row0 + band_rows - 1 + window_lo(w) + w - 1;
@@ -410,8 +411,8 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
   }
   const size_t esz = dtype == 0 ? 2 : 4;
   const void* band_raw = static_cast<const unsigned char*>(raw) + size_t(band_row0 - slab_row0) * cols * num_features * esz;
-  int rc = cmlpl_spectral_hidden_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
-                                        wsb + ws.x16, wsb + ws.h16, stream);
+  int rc = cmlpl_spectral_logits_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
+                                        wsb + ws.x16, reinterpret_cast<float*>(wsb + ws.h16), stream);
   if (rc != CMLPL_OK) return rc;
   return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
 }

@@ -202,6 +202,19 @@ int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_rows, const
                           cmlpl_stream_t stream);
 int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_rows, int num_features, int num_classes,
                         const void* packed, float* lmap, cmlpl_stream_t stream);
+/* Fused spectral branch + sum head (what cmlpl_scene_infer runs since the hidden features stopped going through HBM):
+ *   cmlpl_spectral_logits_tc     : part f32 [4 hidden quarters][ceil(n/128)*128][16] = Wc_spe . relu(Wspe . x + b) per
+ *                                  quarter of the 1024 hidden features (tools/models.py:142-143,150), <= 224 bands
+ *   cmlpl_spectral_logits_raw_tc : the same from the raw cube (z-score folded into the fp16 conversion)
+ *   cmlpl_head_sum_lmap          : 4 quarter partials + the 25 gathered conv partials + bias, argmax */
+int cmlpl_spectral_logits_tc(const float* spectra, int64_t n, int num_features, int num_classes, int w,
+                             const void* packed, void* x16, float* part, cmlpl_stream_t stream);
+int cmlpl_spectral_logits_raw_tc(const void* raw, int dtype, int64_t n, int num_features, int num_classes, int w,
+                                 const float* mu, const float* inv_sigma, const void* packed, void* x16, float* part,
+                                 cmlpl_stream_t stream);
+int cmlpl_head_sum_lmap(const float* part, const float* lmap, int cols, int band_rows, int num_features,
+                        int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
+                        cmlpl_stream_t stream);
 int cmlpl_head_lmap_tc(const void* h16, const float* lmap, int cols, int band_rows, int num_features,
                        int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
                        cmlpl_stream_t stream);

@@ -136,12 +136,14 @@ def run(R, C, B, K, seed, time_it=False):
         off = (ctypes.c_size_t * 12)()
         _lib.call("cmlpl_scene_workspace_layout", R, C, B, K, w, off)
         base = ws.data_ptr()
-        names = ["conv1_scene+pool", "conv2_scene", "pool2_cls", "head_lmap"]
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        _lib.call("cmlpl_conv0_map_f16", cube.data_ptr(), R, C, 0, R, w, 0, R, packed.data_ptr(), base + off[0], st)
-        _lib.call("cmlpl_spectral_hidden_tc", spectra.data_ptr(), n, B, K, w, packed.data_ptr(), base + off[1], base + off[2], st)
-        tot = np.zeros(4)
+        names = ["conv0_map", "spectral_logits", "conv1_pool", "conv2_scene", "pool2_cls", "head_sum"]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        tot = np.zeros(6)
         for it in range(8):
+            ev[5].record()
+            _lib.call("cmlpl_conv0_map_f16", cube.data_ptr(), R, C, 0, R, w, 0, R, packed.data_ptr(), base + off[0], st)
+            ev[6].record()
+            _lib.call("cmlpl_spectral_logits_tc", spectra.data_ptr(), n, B, K, w, packed.data_ptr(), base + off[1], base + off[2], st)
             ev[0].record()
             _lib.call("cmlpl_conv1_pool_planes_f16", base + off[0], C, w, R, packed.data_ptr(), base + off[4], st)
             ev[1].record()
@@ -149,11 +151,11 @@ def run(R, C, B, K, seed, time_it=False):
             ev[2].record()
             _lib.call("cmlpl_pool2_cls_f16", base + off[5], C, w, R, B, K, packed.data_ptr(), base + off[6], st)
             ev[3].record()
-            _lib.call("cmlpl_head_lmap_tc", base + off[2], base + off[6], C, R, B, K, w, packed.data_ptr(), lab2.data_ptr(), None, st)
+            _lib.call("cmlpl_head_sum_lmap", base + off[2], base + off[6], C, R, B, K, w, packed.data_ptr(), lab2.data_ptr(), None, st)
             ev[4].record()
             torch.cuda.synchronize()
             if it >= 3:
-                tot += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
+                tot += np.array([ev[5].elapsed_time(ev[6]), ev[6].elapsed_time(ev[0])] + [ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
         print("   stage ms: " + ", ".join(f"{nm} {t / 5:.3f}" for nm, t in zip(names, tot)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3): ops.scene_infer(cube, spectra, packed, K, w, workspace=ws, labels=lab2)
