@@ -304,7 +304,7 @@ constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp
 constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
 constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
 constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, logits accumulators at 384/400
-enum { A_FULL0 = 0, A_EMPTY0 = 2, D1_FULL0 = 4, D1_EMPTY0 = 7, H_FULL0 = 10, H_EMPTY0 = 12, L_FULL0 = 14, L_EMPTY0 = 16 };
+enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 16, L_FULL0 = 18, L_EMPTY0 = 20 };   // nA <= 4
 }  // namespace spl
 
 __global__ void __launch_bounds__(spl::kThreads, 1)
@@ -335,7 +335,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     if (tid < 256) sb[tid] = bspe[ntile * 256 + tid];
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
     for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bars + 8 * (H_FULL0 + i), kEpi); mbar_init(bars + 8 * (H_EMPTY0 + i), 1);
@@ -426,7 +426,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     };
     for (uint32_t u = 0; u < U; ++u) {
       const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, hs = u % uint32_t(nH);
-      if (ch == 0 && hh == 0 && ti > 0) readout(ti - 1);
+      if (ch == 0 && hh == 1 && ti > 0) readout(ti - 1);      // deferred by a unit: its MMA2 has long completed
       mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
       mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
       tc_fence_after();
@@ -518,10 +518,10 @@ head_sum_kernel(const float* __restrict__ part, int64_t mtiles, const float* __r
 
 using namespace cmlpl;
 
-// shared-memory plan of spectral_logits_kernel for KC input k-chunks: prefers 2 input stages + 2 hidden half-tiles
+// shared-memory plan of spectral_logits_kernel for KC input k-chunks: prefers 3 input stages + 2 hidden half-tiles
 static bool spectral_logits_plan(int KC, int* nA, int* nH, size_t* smem) {
-  const int opts[3][2] = {{2, 2}, {2, 1}, {1, 1}};
-  for (int i = 0; i < 3; ++i) {
+  const int opts[5][2] = {{3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 1}};   // input tiles in flight hide the L2 latency
+  for (int i = 0; i < 5; ++i) {
     const size_t b = size_t(KC) * 4096 + size_t(opts[i][0]) * KC * 2048 + size_t(opts[i][1]) * spl::HBYTES + spl::WCBYTES +
                      1024 + 256 + 64;
     if (b <= 232448) { *nA = opts[i][0]; *nH = opts[i][1]; *smem = b; return true; }

@@ -17,92 +17,104 @@
 namespace cmlpl {
 
 // ------------------------------------------------------------------ conv0 map
-// thread = (padded pixel, 8 output channels); weights [ci][n] in shared memory.
-__global__ void __launch_bounds__(256)
-conv0_map_kernel(const float* __restrict__ cube, int scene_rows, int cols, int slab_row0,
-                 int w, int band_row0, int prow_n, int pcol_n,
-                 const float* __restrict__ w0t, const float* __restrict__ b0, __half* __restrict__ f0pad) {
-  __shared__ __align__(16) float ws[60 * 64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 60 * 64; i += blockDim.x) ws[i] = w0t[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = b0[threadIdx.x];
+// conv0 (1x1) once per PADDED scene position, fp32 FFMA, register-tiled: a thread owns 4 consecutive padded
+// positions x 16 output channels (64 accumulators; per input channel 4 loaded inputs + 4 broadcast LDS.128 of
+// weights feed 64 FMAs), the 4 warps of a half-block share the same 128 positions (inputs hit L1), weights
+// [K][64] live in shared memory.  T = float with K = 60 (PCA cube) or the RAW cube (uint16 / float, K = B bands):
+// PCA projection, both z-scores and conv0 are per-pixel affine maps, so they fold into one
+// F0 = Wf . (x - mu) + bf with Wf = W0 . (U/s)^T [64 x B].  Output: mirrored halo baked in,
+// chunk-planar fp16 [8 chunks][prow_n][pcol_n][8].
+template <typename T, bool kVec4>
+__global__ void __launch_bounds__(256, 2)
+conv0_tiled_kernel(const T* __restrict__ in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0,
+                   int prow_n, int pcol_n, const float* __restrict__ wt, const float* __restrict__ bias,
+                   const float* __restrict__ mu, __half* __restrict__ f0pad) {
+  extern __shared__ __align__(16) float sm0[];              // wt [K][64] | mu [K] | bias [64]
+  float* ws = sm0; float* mus = sm0 + K * 64; float* bs = mus + K;
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) ws[i] = wt[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) mus[i] = mu ? mu[i] : 0.f;
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = warp & 3;                                  // 16 output channels = chunks 2cg, 2cg+1
   const int lo = window_lo(w);
-  const int64_t total = int64_t(prow_n) * pcol_n * 8;
   const int64_t plane = int64_t(prow_n) * pcol_n;
-  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    // consecutive threads -> consecutive pixels of the same 8-channel group (coalesced 16-B stores
-    // into the chunk-planar map [8][prow_n][pcol_n][8])
-    const int g = int(t / plane);
-    const int64_t pp = t - int64_t(g) * plane;
-    const int pr = int(pp / pcol_n), pc = int(pp - int64_t(pr) * pcol_n);
-    const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0;
-    const int sc = mirror_index(pc + lo, cols);
-    const float4* src = reinterpret_cast<const float4*>(cube + (int64_t(sr) * cols + sc) * 60);
-    float acc[8];
+  const int64_t ngroups = (plane + 3) >> 2;
+  for (int64_t g = (int64_t(blockIdx.x) * 2 + (warp >> 2)) * 32 + lane; g < ngroups; g += int64_t(gridDim.x) * 64) {
+    const T* src[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
-#pragma unroll 5
-    for (int c4 = 0; c4 < 15; ++c4) {
-      const float4 v = __ldg(src + c4);
-      const float xv[4] = {v.x, v.y, v.z, v.w};
+    for (int j = 0; j < 4; ++j) {
+      int64_t pp = g * 4 + j; if (pp >= plane) pp = plane - 1;
+      const int pr = int(pp / pcol_n), pc = int(pp - int64_t(pr) * pcol_n);
+      const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0;
+      const int sc = mirror_index(pc + lo, cols);
+      src[j] = in + (int64_t(sr) * cols + sc) * K;
+    }
+    float acc[4][16];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4 wa = *reinterpret_cast<const float4*>(&ws[(c4 * 4 + e) * 64 + g * 8]);
-        const float4 wb = *reinterpret_cast<const float4*>(&ws[(c4 * 4 + e) * 64 + g * 8 + 4]);
-        acc[0] = fmaf(xv[e], wa.x, acc[0]); acc[1] = fmaf(xv[e], wa.y, acc[1]);
-        acc[2] = fmaf(xv[e], wa.z, acc[2]); acc[3] = fmaf(xv[e], wa.w, acc[3]);
-        acc[4] = fmaf(xv[e], wb.x, acc[4]); acc[5] = fmaf(xv[e], wb.y, acc[5]);
-        acc[6] = fmaf(xv[e], wb.z, acc[6]); acc[7] = fmaf(xv[e], wb.w, acc[7]);
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[j][c] = bs[cg * 16 + c];
+    auto fma_k = [&](int k, const float (&x)[4]) {
+      float wv[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(&ws[k * 64 + cg * 16 + 4 * q]);
+        wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[j][c] = fmaf(x[j], wv[c], acc[j][c]);
+    };
+    if constexpr (kVec4) {                                  // float rows, 16-byte aligned, K % 4 == 0
+#pragma unroll 1
+      for (int k4 = 0; k4 < K; k4 += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(src[j] + k4));
+        { const float x[4] = {v[0].x - mus[k4], v[1].x - mus[k4], v[2].x - mus[k4], v[3].x - mus[k4]}; fma_k(k4, x); }
+        { const float x[4] = {v[0].y - mus[k4 + 1], v[1].y - mus[k4 + 1], v[2].y - mus[k4 + 1], v[3].y - mus[k4 + 1]}; fma_k(k4 + 1, x); }
+        { const float x[4] = {v[0].z - mus[k4 + 2], v[1].z - mus[k4 + 2], v[2].z - mus[k4 + 2], v[3].z - mus[k4 + 2]}; fma_k(k4 + 2, x); }
+        { const float x[4] = {v[0].w - mus[k4 + 3], v[1].w - mus[k4 + 3], v[2].w - mus[k4 + 3], v[3].w - mus[k4 + 3]}; fma_k(k4 + 3, x); }
+      }
+    } else {
+#pragma unroll 2
+      for (int k = 0; k < K; ++k) {
+        const float m = mus[k];
+        const float x[4] = {float(src[0][k]) - m, float(src[1][k]) - m, float(src[2][k]) - m, float(src[3][k]) - m};
+        fma_k(k, x);
       }
     }
-    __half2 h[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-    *reinterpret_cast<uint4*>(f0pad + (int64_t(g) * plane + pp) * 8) = *reinterpret_cast<uint4*>(h);
+    for (int j = 0; j < 4; ++j) {
+      const int64_t pp = g * 4 + j;
+      if (pp < plane) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          __half2 h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[j][q * 8 + 2 * e], acc[j][q * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(f0pad + (int64_t(cg * 2 + q) * plane + pp) * 8) = *reinterpret_cast<uint4*>(h);
+        }
+      }
+    }
   }
 }
 
-// conv0 map straight from the RAW cube: PCA projection, both z-scores and conv0 are per-pixel affine
-// maps, so they fold into one  F0 = Wf . (x - mu) + bf  with Wf = W0 . (U/s)^T  [64 x B].
-// thread = (padded pixel, 8 output channels); folded weights [B][64] in shared memory.
-template <typename T>
-__global__ void __launch_bounds__(256)
-conv0_map_raw_kernel(const T* __restrict__ raw, int B, int scene_rows, int cols, int slab_row0, int w, int band_row0,
-                     int prow_n, int pcol_n, const float* __restrict__ wf, const float* __restrict__ bf,
-                     const float* __restrict__ mu, __half* __restrict__ f0pad) {
-  extern __shared__ __align__(16) float sm0[];              // wf [B][64] | mu [B] | bf [64]
-  float* ws = sm0; float* mus = sm0 + B * 64; float* bs = mus + B;
-  for (int i = threadIdx.x; i < B * 64; i += blockDim.x) ws[i] = wf[i];
-  for (int i = threadIdx.x; i < B; i += blockDim.x) mus[i] = mu[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = bf[threadIdx.x];
-  __syncthreads();
-  const int lo = window_lo(w);
-  const int64_t plane = int64_t(prow_n) * pcol_n;
-  const int64_t total = plane * 8;
-  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    // consecutive threads -> the 8 channel groups of one pixel (they share the raw spectrum through L1)
-    const int g = int(t & 7);
-    const int64_t pp = t >> 3;
-    const int pr = int(pp / pcol_n), pc = int(pp - int64_t(pr) * pcol_n);
-    const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0;
-    const int sc = mirror_index(pc + lo, cols);
-    const T* src = raw + (int64_t(sr) * cols + sc) * B;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
-    for (int b = 0; b < B; ++b) {
-      const float xv = float(src[b]) - mus[b];
-      const float4 wa = *reinterpret_cast<const float4*>(&ws[b * 64 + g * 8]);
-      const float4 wb = *reinterpret_cast<const float4*>(&ws[b * 64 + g * 8 + 4]);
-      acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]); acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
-      acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]); acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
-    }
-    __half2 h[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-    *reinterpret_cast<uint4*>(f0pad + (int64_t(g) * plane + pp) * 8) = *reinterpret_cast<uint4*>(h);
-  }
+template <typename T, bool kVec4>
+static int launch_conv0(const T* in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0, int prow_n,
+                        int pcol_n, const float* wt, const float* bias, const float* mu, __half* f0pad, cudaStream_t s) {
+  const int64_t ngroups = (int64_t(prow_n) * pcol_n + 3) / 4;
+  int64_t grid = (ngroups + 63) / 64;
+  const int64_t cap = int64_t(sm_count()) * 2;
+  if (grid > cap) grid = cap;
+  const size_t smem = sizeof(float) * (size_t(K) * 64 + K + 64);
+  CMLPL_CUDA(cudaFuncSetAttribute(conv0_tiled_kernel<T, kVec4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  conv0_tiled_kernel<T, kVec4><<<int(grid), 256, smem, s>>>(in, K, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n, wt,
+                                                            bias, mu, f0pad);
+  CMLPL_CHECK_LAUNCH("conv0_map");
+  return CMLPL_OK;
 }
 
 // ------------------------------------------------------------------ classifier + argmax
@@ -255,16 +267,9 @@ extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, 
   const PackedLayout L = packed_layout(1, 1, w);  // w0/b0 offsets do not depend on B, C
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
   const int prow_n = band_rows + w - 1, pcol_n = cols + w - 1;
-  const int64_t total = int64_t(prow_n) * pcol_n * 8;
-  int64_t grid = (total + 255) / 256;
-  const int64_t cap = int64_t(sm_count()) * 8;
-  if (grid > cap) grid = cap;
-  conv0_map_kernel<<<int(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      cube, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n,
-      reinterpret_cast<const float*>(pk + L.w0), reinterpret_cast<const float*>(pk + L.b0),
-      static_cast<__half*>(f0pad));
-  CMLPL_CHECK_LAUNCH("conv0_map");
-  return CMLPL_OK;
+  return launch_conv0<float, true>(cube, 60, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n,
+                                   reinterpret_cast<const float*>(pk + L.w0), reinterpret_cast<const float*>(pk + L.b0), nullptr,
+                                   static_cast<__half*>(f0pad), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_features, int num_classes, int w,
@@ -395,19 +400,13 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
   const int64_t n = int64_t(band_rows) * cols;
   const int prow_n = band_rows + w - 1, pcol_n = cols + w - 1;
   {
-    const int64_t total = int64_t(prow_n) * pcol_n * 8;
-    int64_t grid = (total + 255) / 256; const int64_t cap = int64_t(sm_count()) * 8; if (grid > cap) grid = cap;
-    const size_t smem = sizeof(float) * (size_t(num_features) * 64 + num_features + 64);
-    if (dtype == 0) {
-      CMLPL_CUDA(cudaFuncSetAttribute(conv0_map_raw_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      conv0_map_raw_kernel<uint16_t><<<int(grid), 256, smem, s>>>(static_cast<const uint16_t*>(raw), num_features, scene_rows, cols,
-          slab_row0, w, band_row0, prow_n, pcol_n, wf, bf, mu, reinterpret_cast<__half*>(wsb + ws.f0pad));
-    } else {
-      CMLPL_CUDA(cudaFuncSetAttribute(conv0_map_raw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      conv0_map_raw_kernel<float><<<int(grid), 256, smem, s>>>(static_cast<const float*>(raw), num_features, scene_rows, cols,
-          slab_row0, w, band_row0, prow_n, pcol_n, wf, bf, mu, reinterpret_cast<__half*>(wsb + ws.f0pad));
-    }
-    CMLPL_CHECK_LAUNCH("conv0_map_raw");
+    __half* f0 = reinterpret_cast<__half*>(wsb + ws.f0pad);
+    const int rc0 = dtype == 0
+        ? launch_conv0<uint16_t, false>(static_cast<const uint16_t*>(raw), num_features, scene_rows, cols, slab_row0, w, band_row0,
+                                        prow_n, pcol_n, wf, bf, mu, f0, s)
+        : launch_conv0<float, false>(static_cast<const float*>(raw), num_features, scene_rows, cols, slab_row0, w, band_row0,
+                                     prow_n, pcol_n, wf, bf, mu, f0, s);
+    if (rc0 != CMLPL_OK) return rc0;
   }
   const size_t esz = dtype == 0 ? 2 : 4;
   const void* band_raw = static_cast<const unsigned char*>(raw) + size_t(band_row0 - slab_row0) * cols * num_features * esz;
