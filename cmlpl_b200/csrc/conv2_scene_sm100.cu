@@ -76,50 +76,70 @@ __global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC,
 // =================================================================================================
 // conv2_scene_kernel: persistent, warp-specialised tcgen05 implicit GEMM over 4x30-position tiles of a
 // parity plane (M = 128 rows = 4 rows x 32 columns incl. one halo column each side; taps = A-descriptor
-// offsets in zero-haloed row-major tiles, exactly like conv1_scene_kernel).  Per tile the nine PM
-// variant tiles are loaded once by TMA (one 24 KB box each, zero fill outside the plane), as three "slabs" of
-// 3 row classes x one column class:
+// offsets in zero-haloed row-major tiles).  Per tile the nine PM variant tiles are loaded once by TMA (one
+// 24 KB box each, zero fill outside the plane), as three "slabs" of 3 row classes x one column class:
 //     slab X <- left, slab M <- mid   : column classes kap = 0, 1
 //                        (mid only)    : kap = 2
 //     slab X <- right                  : kap = 3, 4
-// and every (rho, kap) variant accumulates its <= 9 taps into its own 64-column TMEM slot (ring of 8), so
-// the epilogue (bias + residual + ReLU -> fp16) of one variant overlaps the MMAs of the next ones.
+// ROW-TAP FUSION.  The five row classes rho = 0..4 of a column class are the conv2 output rows i = 0,1,4,8,9 of a
+// patch, and output row i reads pooled rows i-1, i, i+1: consecutive classes share input rows.  The accumulator
+// of class rho is kept in a frame shifted DOWN by rho rows (its row (ty,tx) is plane position (Y0+ty+rho, .)),
+// so tap dy of class rho and tap dy-1 of class rho+1 read the SAME shared-memory rows of the same PM row-class
+// tile; with the accumulators of rho = 0..4 in adjacent 64-column TMEM blocks and the weights stacked per dx as
+// 192 rows [W(dy=2); W(dy=1); W(dy=0)], the 13 row taps of a (kap, dx) become five MMAs:
+//     PA  N=128 [rho0|rho1]      <- PM top  (tile rows +1)  x [W1;W0]
+//     T1  N=192 [rho0|rho1|rho2] <- PM mid  (tile rows +2)  x [W2;W1;W0]
+//     T2  N=192 [rho1|rho2|rho3] <- PM mid  (tile rows +3)
+//     T3  N=192 [rho2|rho3|rho4] <- PM mid  (tile rows +4)
+//     PB  N=128 [rho3|rho4]      <- PM bot  (tile rows +5)  x [W2;W1]
+// i.e. 416 tensor-core cycles instead of 13 x 64 = 832 (a tcgen05.mma of M=128,K=16 costs ~64 cycles up to N=128
+// and 96 at N=192).  Issued group by group over all dx, the accumulators complete in the order rho0, rho1, rho2,
+// rho3+rho4, so the epilogue (bias + residual + ReLU -> fp16) of one class overlaps the MMAs of the next groups
+// and the single 320-column accumulator set is reused by the next column class as its blocks drain.  Rows
+// y < rho of class rho are never produced -- no pixel reads them (pooled row i >= rho for that class).
 namespace c2s {
 constexpr int TH = 4, TP = 32, TW = 30;
 constexpr int CH = (TH + 2) * TP * 16;               // 3 072: one chunk plane of a tile, dense (written by TMA)
-constexpr int TBYTES = 8 * CH;                       // 24 576: one PM variant tile
+constexpr int TBYTES = 8 * CH;                       // 24 576: one PM variant tile (6 rows)
 constexpr int WBYTES = 3 * 8 * 192 * 16;             // 73 728
 constexpr int S_W = 0, S_T = WBYTES, S_BIAS = S_T + 6 * TBYTES, S_BAR = S_BIAS + 256, S_TMEM = S_BAR + 256;
 constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
 constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader (one thread, TMA), warp 9 MMA issuer
 constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
-enum { XF = 0, MF, XE, ME, DF0 = 4, DE0 = 12 };
+enum { XF = 0, MF, XE, ME, DF0 = 4, DE0 = 9 };       // DF/DE: accumulator block of row class rho full / drained
 static_assert(SMEM <= 232448, "conv2_scene: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "conv2_scene: TMA destinations must be 128-byte aligned");
+// first tile row (relative to Y0 - 1) held by the tile of PM row class a: top rows +1.., mid +2.., bot +5..
+__host__ __device__ constexpr int tile_r0(int a) { return a == 0 ? 1 : (a == 1 ? 2 : 5); }
 
-// all taps of variant (RHO, KAP) into TMEM columns [d, d+64); t_lo / w_lo = low descriptor words of tile 0 /
-// the weight block of dx = 0.  Every offset is an immediate.
-template <int RHO, int KAP>
-__device__ __forceinline__ void issue_variant(uint32_t d, uint32_t t_lo, uint32_t w_lo) {
+// group G (0 = PA, 1..3 = T1..T3, 4 = PB) of column class KAP: every dx tap x 4 k-steps.  t_lo = low descriptor word of
+// tile 0 minus 16 B (MMA row m of tap dx reads entry m + dx - 1), w_lo = weight block of dx = 0.  All offsets immediate.
+template <int KAP, int G>
+__device__ __forceinline__ void issue_group(uint32_t t_lo, uint32_t w_lo) {
   constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;   // SBO = 128 B, version 1
-  constexpr uint32_t kI64 = make_idesc_f16(128, 64);
-  uint32_t acc = 0;
+  constexpr int a = G == 0 ? 0 : (G == 4 ? 2 : 1);
+  constexpr int o = G == 0 ? 1 : (G == 4 ? 5 : G + 1);
+  constexpr int d = G == 0 ? 0 : (G == 4 ? 192 : (G - 1) * 64);
+  constexpr int N = (G == 0 || G == 4) ? 128 : 192;
+  constexpr int brow = G == 0 ? 64 : 0;
+  constexpr int dx_first = rep_of(KAP) == 0 ? 1 : 0;
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int i2 = rep_of(RHO) + dy - 1;
-    if (i2 < 0 || i2 > 9) continue;
+  for (int dx = 0; dx < 3; ++dx) {
+    const int j2 = rep_of(KAP) + dx - 1;
+    if (j2 < 0 || j2 > 9) continue;
+    const int tile = (cls_of(j2) == 1 ? 3 : 0) + a;               // slab M holds the mid column class
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int j2 = rep_of(KAP) + dx - 1;
-      if (j2 < 0 || j2 > 9) continue;
-      const int tile = (cls_of(j2) == 1 ? 3 : 0) + cls_of(i2);     // slab M holds the mid column class
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t a = t_lo + uint32_t((tile * TBYTES + (dy * TP + dx) * 16 + ks * 2 * CH) / 16);   // t_lo = tile 0 - 16 B
-        const uint32_t b = w_lo + uint32_t((dx * kWDx + ks * 2 * kWLbo) / 16) + uint32_t((2 - dy) * 64);
-        umma_f16(d, kHi | uint64_t(a), kHi | uint64_t(b), kI64, acc);
-        acc = 1;
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t aa = t_lo + uint32_t((tile * TBYTES + ((o - tile_r0(a)) * TP + dx) * 16 + ks * 2 * CH) / 16);
+      const uint32_t bb = w_lo + uint32_t((dx * kWDx + ks * 2 * kWLbo) / 16) + uint32_t(brow);
+      const bool first = dx == dx_first && ks == 0;
+      if (first && G >= 1 && G <= 3) {
+        // the group's third accumulator starts here (overwrite); the other two already hold earlier groups
+        umma_f16(uint32_t(d), kHi | uint64_t(aa), kHi | uint64_t(bb), make_idesc_f16(128, 128), 1u);
+        umma_f16(uint32_t(d + 128), kHi | uint64_t(aa), kHi | uint64_t(bb + 128), make_idesc_f16(128, 64), 0u);
+      } else {
+        umma_f16(uint32_t(d), kHi | uint64_t(aa), kHi | uint64_t(bb), make_idesc_f16(128, N), (first && G == 0) ? 0u : 1u);
       }
     }
   }
@@ -151,7 +171,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
   if (tid == 0) {
     mbar_init(bars + 8 * XF, 1); mbar_init(bars + 8 * MF, 1);
     mbar_init(bars + 8 * XE, 1); mbar_init(bars + 8 * ME, 1);
-    for (int s = 0; s < 8; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi); }
+    for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
@@ -169,7 +189,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int pl = t / tiles_p, tt = t - pl * tiles_p;
         const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
-        const int y0 = tr * TH - 1, x0 = tc * TW - 1;          // plane coords of entry (ry=0, rx=0); borders zero-filled
+        const int y0 = tr * TH - 1, x0 = tc * TW - 1;          // borders zero-filled; tile of row class a starts at row y0 + tile_r0(a)
 #pragma unroll 1
         for (int step = 0; step < 3; ++step) {                 // left -> X, mid -> M, right -> X
           const int slab = step == 1 ? 1 : 0, bcls = step;
@@ -179,7 +199,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
           mbar_arrive_expect_tx(full, 3 * TBYTES);
 #pragma unroll
           for (int a = 0; a < 3; ++a)
-            tma_load_tile(sbase + S_T + (slab * 3 + a) * TBYTES, &tm_pm, x0, y0, (a * 3 + bcls) * 4 + pl, full);
+            tma_load_tile(sbase + S_T + (slab * 3 + a) * TBYTES, &tm_pm, x0, y0 + tile_r0(a), (a * 3 + bcls) * 4 + pl, full);
           if (slab) ++fm; else ++fx;
         }
       }
@@ -189,62 +209,68 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
     if (tmem != 0) { printf("conv2_scene: unexpected TMEM base %u\n", tmem); __trap(); }
     const uint32_t t_lo = ((sbase + S_T - 16) >> 4) | (uint32_t(CH >> 4) << 16);
     const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
-    uint32_t fx = 0, fm = 0, vc = 0;                           // slab fills consumed, variants issued
-#define C2S_VARIANT(RHO, KAP)                                                        \
+    uint32_t fx = 0, fm = 0, kc = 0;                           // slab fills consumed, column-class stages issued
+#define C2S_GROUP(KAP, G, ...)                                                       \
     do {                                                                             \
-      const uint32_t slot = vc & 7;                                                  \
-      mbar_wait(bars + 8 * (DE0 + slot), ((vc >> 3) & 1) ^ 1, 63);                   \
       tc_fence_after();                                                              \
-      if (elect_one_sync()) {                                                        \
-        issue_variant<RHO, KAP>(slot * 64, t_lo, w_lo);                              \
-        umma_commit(bars + 8 * (DF0 + slot));                                        \
-      }                                                                              \
+      if (elect_one_sync()) { issue_group<KAP, G>(t_lo, w_lo); __VA_ARGS__; }        \
       __syncwarp();                                                                  \
-      ++vc;                                                                          \
     } while (0)
-#define C2S_COLUMN(KAP) C2S_VARIANT(0, KAP); C2S_VARIANT(1, KAP); C2S_VARIANT(2, KAP); C2S_VARIANT(3, KAP); C2S_VARIANT(4, KAP)
+#define C2S_COLUMN(KAP)                                                              \
+    do {                                                                             \
+      const uint32_t ep = (kc & 1) ^ 1;                                              \
+      mbar_wait(bars + 8 * (DE0 + 0), ep, 63); mbar_wait(bars + 8 * (DE0 + 1), ep, 63);                       \
+      C2S_GROUP(KAP, 0, (void)0);                                                    \
+      mbar_wait(bars + 8 * (DE0 + 2), ep, 63);                                       \
+      C2S_GROUP(KAP, 1, umma_commit(bars + 8 * (DF0 + 0)));                          \
+      mbar_wait(bars + 8 * (DE0 + 3), ep, 63);                                       \
+      C2S_GROUP(KAP, 2, umma_commit(bars + 8 * (DF0 + 1)));                          \
+      mbar_wait(bars + 8 * (DE0 + 4), ep, 63);                                       \
+      C2S_GROUP(KAP, 3, umma_commit(bars + 8 * (DF0 + 2)));                          \
+      C2S_GROUP(KAP, 4, (umma_commit(bars + 8 * (DF0 + 3)), umma_commit(bars + 8 * (DF0 + 4))));              \
+      ++kc;                                                                          \
+    } while (0)
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       mbar_wait(bars + 8 * XF, fx & 1, 62); ++fx;              // left
       mbar_wait(bars + 8 * MF, fm & 1, 62); ++fm;              // mid
-      tc_fence_after();
       C2S_COLUMN(0);
       C2S_COLUMN(1);
       if (elect_one_sync()) umma_commit(bars + 8 * XE);        // left tiles consumed
       __syncwarp();
       C2S_COLUMN(2);
       mbar_wait(bars + 8 * XF, fx & 1, 62); ++fx;              // right
-      tc_fence_after();
       C2S_COLUMN(3);
       C2S_COLUMN(4);
       if (elect_one_sync()) { umma_commit(bars + 8 * XE); umma_commit(bars + 8 * ME); }
       __syncwarp();
     }
 #undef C2S_COLUMN
-#undef C2S_VARIANT
+#undef C2S_GROUP
   } else {
     // ================================================================ epilogue (warps 0-7)
     const int L = (warp & 3) * 32 + lane, chalf = warp >> 2;
     const uint32_t lane_addr = (uint32_t((warp & 3) * 32) << 16) + chalf * 32;
     const int ty = L >> 5, tx = L & 31;
-    uint32_t vc = 0;
+    uint32_t kc = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int pl = t / tiles_p, tt = t - pl * tiles_p;
       const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
-      const int y = tr * TH + ty, x = tc * TW + tx - 1;
-      const bool valid = tx >= 1 && tx <= TW && y < PR2 && x < PC2;
-      const int64_t pos = valid ? int64_t(y) * PC2 + x : 0;
+      const int x = tc * TW + tx - 1;
 #pragma unroll 1
-      for (int kap = 0; kap < 5; ++kap) {
+      for (int kap = 0; kap < 5; ++kap, ++kc) {
 #pragma unroll 1
-        for (int rho = 0; rho < 5; ++rho, ++vc) {
-          const uint32_t slot = vc & 7;
+        for (int rho = 0; rho < 5; ++rho) {
+          const uint32_t slot = rho;
+          const int y = tr * TH + ty + rho;                    // the accumulator of class rho lives rho rows further down
+          const bool valid = tx >= 1 && tx <= TW && y < PR2 && x < PC2;
+          const int64_t pos = valid ? int64_t(y) * PC2 + x : 0;
           // residual = centre cell PM[A(rho)][B(kap)][y,x] (L2-resident), issued before the wait
           const int rv = cls_of(rep_of(rho)) * 3 + cls_of(rep_of(kap));
           const __half* rp = pmq + ((int64_t(rv * 4 + pl) * 8 + chalf * 4) * psz + pos) * 8;
           uint4 res[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) res[k] = valid ? __ldg(reinterpret_cast<const uint4*>(rp + int64_t(k) * psz * 8)) : make_uint4(0, 0, 0, 0);
-          mbar_wait(bars + 8 * (DF0 + slot), (vc >> 3) & 1, 64);
+          mbar_wait(bars + 8 * (DF0 + slot), kc & 1, 64);
           tc_fence_after();
           float v0[16], v1[16];
           tmem_ld16(lane_addr + slot * 64, v0);

@@ -300,7 +300,8 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
 //   readout                    part[quarter][pixel][16] f32: the head adds the 4 quarter partials (53 MB instead of the
 //                              425 MB hidden tensor written and read back)
 namespace spl {
-constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader, warp 9 MMA issuer
+constexpr int kEpi = 512, kThreads = kEpi + 64;      // warps 0-15 epilogue (lane quarter x 32-column group), warp 16 loader, warp 17 MMA issuer
+constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
 constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
 constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, logits accumulators at 384/400
@@ -343,14 +344,14 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(sbase + S_TMEM, 512);
+  if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
 
-  if (warp == 8) {
+  if (warp == kLoadWarp) {
     // ================================================================ loader: one bulk copy per pixel tile
     if (lane == 0) {
       for (uint32_t j = 0; j < uint32_t(my_tiles); ++j) {
@@ -360,7 +361,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
         bulk_g2s(sbase + S_A + s * abytes, x16 + (mt0 + int64_t(j) * mstep) * int64_t(KC) * 1024, abytes, bars + 8 * (A_FULL0 + s));
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     if (tmem != 0) { printf("spectral_logits: unexpected TMEM base %u\n", tmem); __trap(); }
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
@@ -407,7 +408,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       if (u + 2 < U) issue1(u + 2);
     }
   } else {
-    // ================================================================ epilogue (warps 0-7)
+    // ================================================================ epilogue (warps 0-15)
     const int q = warp & 3, ch = warp >> 2, L = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const float* sb = reinterpret_cast<const float*>(smem + S_BIAS);
@@ -430,25 +431,24 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
       mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
       tc_fence_after();
-      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * 8) * 2048 + L * 16;
-      const float* bb = sb + hh * 128 + ch * 64;
-#pragma unroll
-      for (int g = 0; g < 4; g += 2) {
+      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * 4) * 2048 + L * 16;
+      const float* bb = sb + hh * 128 + ch * 32;
+      {
         float v0[16], v1[16];
-        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 16, v0);
-        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 16 + 16, v1);
+        tmem_ld16(lane_addr + d * 128 + ch * 32, v0);
+        tmem_ld16(lane_addr + d * 128 + ch * 32 + 16, v1);
         tmem_ld_wait();
-        if (g == 2) { tc_fence_before(); mbar_arrive(bars + 8 * (D1_EMPTY0 + d)); }
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (D1_EMPTY0 + d));
         __half2 h[16];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          h[e] = __floats2half2_rn(fmaxf(v0[2 * e] + bb[g * 16 + 2 * e], 0.f), fmaxf(v0[2 * e + 1] + bb[g * 16 + 2 * e + 1], 0.f));
-          h[8 + e] = __floats2half2_rn(fmaxf(v1[2 * e] + bb[g * 16 + 16 + 2 * e], 0.f),
-                                        fmaxf(v1[2 * e + 1] + bb[g * 16 + 16 + 2 * e + 1], 0.f));
+          h[e] = __floats2half2_rn(fmaxf(v0[2 * e] + bb[2 * e], 0.f), fmaxf(v0[2 * e + 1] + bb[2 * e + 1], 0.f));
+          h[8 + e] = __floats2half2_rn(fmaxf(v1[2 * e] + bb[16 + 2 * e], 0.f), fmaxf(v1[2 * e + 1] + bb[16 + 2 * e + 1], 0.f));
         }
         const uint4* hv = reinterpret_cast<const uint4*>(h);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(hdst + (g * 2 + k) * 2048) = hv[k];
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(hdst + k * 2048) = hv[k];
       }
       fence_proxy_async();                             // generic-proxy writes of H -> visible to the tensor core
       mbar_arrive(bars + 8 * (H_FULL0 + hs));
@@ -457,7 +457,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------ head of the dense path: sums + argmax

@@ -80,12 +80,13 @@ def run(R, C, B, K, seed, time_it=False):
                     acc += torch.einsum("oc,pcyx->poyx", W2[:, :, dy, dx], sh)
             Yd[rho * 5 + kap] = acc.clamp_min(0)
     yq_d = yq.permute(0, 1, 2, 5, 3, 4).reshape(25, 4, 64, PR2, PC2).float()
-    nan_y = int(torch.isnan(yq_d).sum())
-    worst = max(rel(yq_d[v], Yd[v]) for v in range(25))
+    # rows y' < rho of row class rho are never produced (no pixel reads them: conv2_scene_sm100.cu, row-tap fusion)
+    nan_y = sum(int(torch.isnan(yq_d[v][:, :, v // 5:]).sum()) for v in range(25))
+    worst = max(rel(yq_d[v][:, :, v // 5:], Yd[v][:, :, v // 5:]) for v in range(25))
     print(f"   conv2 variants: worst rel err {worst:.2e} (fp16 output rounding ~5e-4) nan={nan_y}")
-    if worst > 5e-3:
+    if not worst < 5e-3:
         for v in range(25):
-            print("      variant rho=%d kap=%d rel %.2e" % (v // 5, v % 5, rel(yq_d[v], Yd[v])))
+            print("      variant rho=%d kap=%d rel %.2e" % (v // 5, v % 5, rel(yq_d[v][:, :, v // 5:], Yd[v][:, :, v // 5:])))
     # ---- stage 3: pooled classifier partial maps from the kernel's own yq
     _lib.call("cmlpl_pool2_cls_f16", yq.data_ptr(), C, w, R, B, K, packed.data_ptr(), lmap.data_ptr(), st)
     torch.cuda.synchronize()
@@ -110,9 +111,10 @@ def run(R, C, B, K, seed, time_it=False):
                 ref += 0.25 * torch.einsum("kc,pcyx->pkyx", Wc[:, :, I, J], sh)
         got = lmap[:, m].permute(0, 1, 4, 2, 3).reshape(4, 16, PR2, PC2)[:, :K]
         # only positions whose four inputs exist matter; compare on the interior
-        e = rel(got[:, :, :PR2 - 1, :PC2 - 1], ref[:, :, :PR2 - 1, :PC2 - 1])
+        # map (I, J) is read at y' = r' + 2I >= 2I only
+        e = rel(got[:, :, 2 * I:PR2 - 1, :PC2 - 1], ref[:, :, 2 * I:PR2 - 1, :PC2 - 1])
         worst = max(worst, e)
-    print(f"   class-partial maps: worst rel err {worst:.2e} nan(interior)={int(torch.isnan(lmap[:, :, :, :PR2 - 1, :PC2 - 1]).sum())}")
+    print(f"   class-partial maps: worst rel err {worst:.2e}")
     # ---- stage 4: whole path vs per-pixel path vs oracle
     labels, logits = ops.scene_infer(cube, spectra, packed, K, w, want_logits=True)
     torch.cuda.synchronize()
