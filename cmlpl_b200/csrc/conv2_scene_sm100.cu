@@ -170,8 +170,8 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
   if (tid < 64) sbias[tid] = b2g[tid];
   if (tid == 0) {
     mbar_init(bars + 8 * XF, 1); mbar_init(bars + 8 * MF, 1);
-    mbar_init(bars + 8 * XE, 1); mbar_init(bars + 8 * ME, 1);
-    for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi); }
+    mbar_init(bars + 8 * XE, 1 + kEpi); mbar_init(bars + 8 * ME, 1 + kEpi);   // MMA commit + every epilogue thread's residual reads
+    for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi / 2); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
@@ -248,52 +248,60 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
 #undef C2S_GROUP
   } else {
     // ================================================================ epilogue (warps 0-7)
-    const int L = (warp & 3) * 32 + lane, chalf = warp >> 2;
-    const uint32_t lane_addr = (uint32_t((warp & 3) * 32) << 16) + chalf * 32;
+    // two groups of four warps take alternate variants, so the residual loads / TMEM reads / stores of one variant
+    // overlap the other group's; a thread owns one position (TMEM lane) and all 64 channels of it
+    const int L = (warp & 3) * 32 + lane, grp = warp >> 2;
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
     const int ty = L >> 5, tx = L & 31;
-    uint32_t kc = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int pl = t / tiles_p, tt = t - pl * tiles_p;
-      const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
-      const int x = tc * TW + tx - 1;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t nv = uint32_t(my_tiles) * 25;
 #pragma unroll 1
-      for (int kap = 0; kap < 5; ++kap, ++kc) {
-#pragma unroll 1
-        for (int rho = 0; rho < 5; ++rho) {
-          const uint32_t slot = rho;
-          const int y = tr * TH + ty + rho;                    // the accumulator of class rho lives rho rows further down
-          const bool valid = tx >= 1 && tx <= TW && y < PR2 && x < PC2;
-          const int64_t pos = valid ? int64_t(y) * PC2 + x : 0;
-          // residual = centre cell PM[A(rho)][B(kap)][y,x] (L2-resident), issued before the wait
-          const int rv = cls_of(rep_of(rho)) * 3 + cls_of(rep_of(kap));
-          const __half* rp = pmq + ((int64_t(rv * 4 + pl) * 8 + chalf * 4) * psz + pos) * 8;
-          uint4 res[4];
+    for (uint32_t vc = uint32_t(grp); vc < nv; vc += 2) {
+      // variant vc of this CTA -> tile, column class, row class
+      const uint32_t tl = vc / 25, r = vc - tl * 25;
+      const int kap = int(r / 5), rho = int(r - uint32_t(kap) * 5);
+      const int t = blockIdx.x + int(tl) * gridDim.x;
+      const int pl = t / tiles_p, tt = t - pl * tiles_p, tr = tt / tiles_c, tc = tt - tr * tiles_c;
+      const int y = tr * TH + ty + rho, x = tc * TW + tx - 1;   // the accumulator of class rho lives rho rows further down
+      const bool valid = tx >= 1 && tx <= TW && y < PR2 && x < PC2;
+      const int64_t pos = valid ? int64_t(y) * PC2 + x : 0;
+      const uint32_t kc = vc / 5;                              // column-class stage (phase of the DF barriers)
+      mbar_wait(bars + 8 * (DF0 + rho), kc & 1, 64);
+      tc_fence_after();
+      // residual = centre cell PM[A(rho)][B(kap)][y,x] = the (dy=1,dx=1) operand of this variant, still in its slab:
+      // tile row ty + rho + 1 - r0(A), entry tx (the slab is only released once every epilogue thread has read its share)
+      uint4 res[8];
+      {
+        const int a = cls_of(rep_of(rho)), b = cls_of(rep_of(kap));
+        const unsigned char* rp = smem + S_T + ((b == 1 ? 3 : 0) + a) * TBYTES + ((ty + rho + 1 - tile_r0(a)) * TP + tx) * 16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) res[k] = valid ? __ldg(reinterpret_cast<const uint4*>(rp + int64_t(k) * psz * 8)) : make_uint4(0, 0, 0, 0);
-          mbar_wait(bars + 8 * (DF0 + slot), kc & 1, 64);
-          tc_fence_after();
-          float v0[16], v1[16];
-          tmem_ld16(lane_addr + slot * 64, v0);
-          tmem_ld16(lane_addr + slot * 64 + 16, v1);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(bars + 8 * (DE0 + slot));
-          if (valid) {
-            __half* dst = yq + ((int64_t((rho * 5 + kap) * 4 + pl) * 8 + chalf * 4) * psz + pos) * 8;
-            const float* bb = sbias + chalf * 32;
+        for (int k = 0; k < 8; ++k) res[k] = *reinterpret_cast<const uint4*>(rp + k * CH);
+      }
+      if (r == 3 || r == 4) mbar_arrive(bars + 8 * XE);        // this thread's last read of the left slab (kap = 0)
+      if (r == 18 || r == 19) mbar_arrive(bars + 8 * ME);      // ... of the mid slab (kap = 1..3)
+      if (r == 23 || r == 24) mbar_arrive(bars + 8 * XE);      // ... of the right slab (kap = 4)
+      __half* dst = yq + (int64_t((rho * 5 + kap) * 4 + pl) * 8 * psz + pos) * 8;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half2* hr = reinterpret_cast<const __half2*>(&res[k]);
-              const float* v = k < 2 ? v0 + k * 8 : v1 + (k - 2) * 8;
-              __half2 h[4];
+      for (int hf = 0; hf < 2; ++hf) {                         // 32 channels at a time
+        float v0[16], v1[16];
+        tmem_ld16(lane_addr + rho * 64 + hf * 32, v0);
+        tmem_ld16(lane_addr + rho * 64 + hf * 32 + 16, v1);
+        tmem_ld_wait();
+        if (hf == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (DE0 + rho)); }
+        if (valid) {
+          const float* bb = sbias + hf * 32;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(hr[e]);
-                h[e] = __floats2half2_rn(fmaxf(v[2 * e] + (f.x + bb[k * 8 + 2 * e]), 0.f),
-                                         fmaxf(v[2 * e + 1] + (f.y + bb[k * 8 + 2 * e + 1]), 0.f));
-              }
-              *reinterpret_cast<uint4*>(dst + int64_t(k) * psz * 8) = *reinterpret_cast<uint4*>(h);
+          for (int k = 0; k < 4; ++k) {
+            const __half2* hr = reinterpret_cast<const __half2*>(&res[hf * 4 + k]);
+            const float* v = k < 2 ? v0 + k * 8 : v1 + (k - 2) * 8;
+            __half2 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(hr[e]);
+              h[e] = __floats2half2_rn(fmaxf(v[2 * e] + (f.x + bb[k * 8 + 2 * e]), 0.f),
+                                       fmaxf(v[2 * e + 1] + (f.y + bb[k * 8 + 2 * e + 1]), 0.f));
             }
+            *reinterpret_cast<uint4*>(dst + int64_t(hf * 4 + k) * psz * 8) = *reinterpret_cast<uint4*>(h);
           }
         }
       }
