@@ -304,7 +304,7 @@ constexpr int kEpi = 512, kThreads = kEpi + 64;      // warps 0-15 epilogue (lan
 constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
 constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
-constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, logits accumulators at 384/400
+constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, 2 stages x 4 logits accumulators at 384..511
 enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 16, L_FULL0 = 18, L_EMPTY0 = 20 };   // nA <= 4
 }  // namespace spl
 
@@ -393,7 +393,9 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
         uint32_t b_lo = ((sbase + S_WC + hh * 16 * 256) >> 4) | (uint32_t(256 >> 4) << 16);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          umma_f16(D2COL + ls * 16, kHi | a_lo, kHi | b_lo, idesc2, (hh | ks) ? 1u : 0u);
+          // four independent accumulators (k-step mod 4): back-to-back N=16 MMAs into ONE accumulator serialise on
+          // its ~190-cycle update latency; the readout adds the four
+          umma_f16(D2COL + ls * 64 + (ks & 3) * 16, kHi | a_lo, kHi | b_lo, idesc2, (hh | (ks >> 2)) ? 1u : 0u);
           a_lo += 4096 >> 4; b_lo += 512 >> 4;
         }
         umma_commit(bars + 8 * (H_EMPTY0 + hs));
@@ -401,11 +403,12 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       }
       __syncwarp();
     };
-    if (U > 0) issue1(0);
-    if (U > 1) issue1(1);
+    // MMA1 runs a full accumulator ring (3 units) ahead of the epilogue: it only needs a drained TMEM slot, never the
+    // hidden half-tile, so the epilogue -> MMA2 hand-over is the only dependency left on the critical path
+    for (uint32_t u = 0; u < 3 && u < U; ++u) issue1(u);
     for (uint32_t u = 0; u < U; ++u) {
       issue2(u);
-      if (u + 2 < U) issue1(u + 2);
+      if (u + 3 < U) issue1(u + 3);
     }
   } else {
     // ================================================================ epilogue (warps 0-15)
@@ -416,11 +419,16 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       const uint32_t ls = ti & 1;
       mbar_wait(bars + 8 * (L_FULL0 + ls), (ti >> 1) & 1, 96);
       tc_fence_after();
-      float v[16];
-      tmem_ld16(lane_addr + D2COL + ls * 16, v);
+      float v[16], w1[16], w2[16], w3[16];
+      tmem_ld16(lane_addr + D2COL + ls * 64, v);
+      tmem_ld16(lane_addr + D2COL + ls * 64 + 16, w1);
+      tmem_ld16(lane_addr + D2COL + ls * 64 + 32, w2);
+      tmem_ld16(lane_addr + D2COL + ls * 64 + 48, w3);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bars + 8 * (L_EMPTY0 + ls));
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = (v[c] + w1[c]) + (w2[c] + w3[c]);
       float4* dst = reinterpret_cast<float4*>(part) + ((int64_t(ntile) * mtiles + (mt0 + int64_t(ti) * mstep)) * 128 + L) * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
