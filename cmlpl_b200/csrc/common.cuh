@@ -37,6 +37,19 @@ void set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// opt a kernel into `bytes` of dynamic shared memory; the attribute call is made once per (call site, device) and
+// again only if a larger size is requested -- it costs microseconds of host time that a 1 ms step cannot hide
+#define CMLPL_MAX_DYN_SMEM(kernel, bytes)                                                             \
+  do {                                                                                                \
+    static int set__[64];                                                                             \
+    int dev__ = 0;                                                                                    \
+    if (cudaGetDevice(&dev__) != cudaSuccess || dev__ < 0 || dev__ >= 64) dev__ = 0;                  \
+    if (int(bytes) > set__[dev__]) {                                                                  \
+      CMLPL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); \
+      set__[dev__] = int(bytes);                                                                      \
+    }                                                                                                 \
+  } while (0)
+
 // number of SMs of the current device (cached)
 int sm_count();
 

@@ -496,7 +496,7 @@ extern "C" int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w
   const PackedLayout L = packed_layout(1, 1, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CMLPL_CUDA(cudaFuncSetAttribute(conv1_scene_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1s::SMEM));
+  CMLPL_MAX_DYN_SMEM(conv1_scene_kernel, c1s::SMEM);
   const int ntiles = ((PR + c1s::TH - 1) / c1s::TH) * ((PC + c1s::TW - 1) / c1s::TW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
   conv1_scene_kernel<<<grid, c1s::kThreads, c1s::SMEM, s>>>(static_cast<const __half*>(f0pad), PR, PC, pk + L.w1,
@@ -526,7 +526,7 @@ extern "C" int cmlpl_conv1_pool_planes_f16(const void* f0pad, int cols, int w, i
   const int PR = band_rows + w - 1, PC = cols + w - 1, PR2 = (PR + 1) / 2, PC2 = (PC + 1) / 2;
   const PackedLayout L = packed_layout(1, 1, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  CMLPL_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1p::SMEM));
+  CMLPL_MAX_DYN_SMEM(conv1_pool_kernel, c1p::SMEM);
   const int ntiles = ((2 * PR2 + c1p::OH - 1) / c1p::OH) * ((2 * PC2 + c1p::OW - 1) / c1p::OW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
   CUtensorMap tm_f0;

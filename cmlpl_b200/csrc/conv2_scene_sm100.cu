@@ -497,7 +497,7 @@ extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_
   const int PR2 = (band_rows + w) / 2, PC2 = (cols + w) / 2;
   const PackedLayout L = packed_layout(1, 1, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  CMLPL_CUDA(cudaFuncSetAttribute(conv2_scene_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c2s::SMEM));
+  CMLPL_MAX_DYN_SMEM(conv2_scene_kernel, c2s::SMEM);
   const int ntiles = 4 * ((PR2 + c2s::TH - 1) / c2s::TH) * ((PC2 + c2s::TW - 1) / c2s::TW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
   CUtensorMap tm_pm;
@@ -518,7 +518,7 @@ extern "C" int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_row
   const int PR2 = (band_rows + w) / 2, PC2 = (cols + w) / 2;
   const PackedLayout L = packed_layout(num_features, num_classes, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  CMLPL_CUDA(cudaFuncSetAttribute(pool2_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2c::SMEM));
+  CMLPL_MAX_DYN_SMEM(pool2_cls_kernel, p2c::SMEM);
   const int ntiles = 4 * ((PR2 + p2c::TH - 1) / p2c::TH) * ((PC2 + p2c::TW - 1) / p2c::TW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
   CUtensorMap tm_y;

@@ -560,7 +560,7 @@ static int spectral_hidden_impl(const void* x, int dtype /* -1 = preprocessed f3
     int nA = 0, nH = 0; size_t fsmem = 0;
     CMLPL_CHECK_ARG(spectral_logits_plan(KC, &nA, &nH, &fsmem), "spectral_logits_tc: %d bands do not fit shared memory", num_features);
     CMLPL_CHECK_ARG(num_classes <= 16, "spectral_logits_tc: needs <= 16 classes, got %d", num_classes);
-    CMLPL_CUDA(cudaFuncSetAttribute(spectral_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsmem)));
+    CMLPL_MAX_DYN_SMEM(spectral_logits_kernel, int(fsmem));
     int fgrid = sm_count() / 4 * 4;
     if (fgrid > mtiles * 4) fgrid = int(mtiles * 4);
     const unsigned char* fpk = static_cast<const unsigned char*>(packed);
@@ -572,7 +572,7 @@ static int spectral_hidden_impl(const void* x, int dtype /* -1 = preprocessed f3
     return CMLPL_OK;
   }
   const size_t smem = size_t(KC) * 8192 + 1024 + 64 + 64;
-  CMLPL_CUDA(cudaFuncSetAttribute(spectral_hidden_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  CMLPL_MAX_DYN_SMEM(spectral_hidden_kernel, int(smem));
   int grid = sm_count() / 4 * 4;
   if (grid > mtiles * 4) grid = int(mtiles * 4);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
@@ -606,7 +606,7 @@ extern "C" int cmlpl_head_tc(const void* p2t, const void* h16, int64_t n, int nu
   const size_t wbytes = size_t(kc_conv + kc_spe) * 256;
   const size_t smem = (wbytes + 127) / 128 * 128 + size_t(kHeadStages) * kHeadChunkBytes + 256 + 64;
   CMLPL_CHECK_ARG(smem <= 227 * 1024, "head_tc: shared memory %zu too large", smem);
-  CMLPL_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  CMLPL_MAX_DYN_SMEM(head_kernel, int(smem));
   const int64_t mtiles = (n + 127) / 128;
   int grid = sm_count(); if (grid > mtiles) grid = int(mtiles);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
@@ -630,7 +630,7 @@ extern "C" int cmlpl_head_lmap_tc(const void* h16, const float* lmap, int cols, 
   const int kc_conv = L.conv_pos * 8, kc_spe = 128;
   const size_t wbytes = size_t(kc_spe) * 256;
   const size_t smem = (wbytes + 127) / 128 * 128 + size_t(kHeadStages) * kHeadChunkBytes + 256 + 64;
-  CMLPL_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  CMLPL_MAX_DYN_SMEM(head_kernel, int(smem));
   const int64_t n = int64_t(band_rows) * cols;
   const int64_t mtiles = (n + 127) / 128;
   int grid = sm_count(); if (grid > mtiles) grid = int(mtiles);

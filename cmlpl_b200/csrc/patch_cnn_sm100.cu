@@ -388,7 +388,7 @@ static int launch_patch_cnn(const void* f0pad, int cols, int w, int band_rows, c
   const PackedLayout L = packed_layout(1, 1, w);   // conv offsets do not depend on B, C
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
   auto kern = trace ? patch_cnn_kernel<20, true> : patch_cnn_kernel<20, false>;
-  CMLPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  CMLPL_MAX_DYN_SMEM(kern, Cfg::SMEM);
   const int64_t npix = int64_t(band_rows) * cols;
   int64_t grid = grid_override > 0 ? grid_override : sm_count();
   if (grid > npix) grid = npix;

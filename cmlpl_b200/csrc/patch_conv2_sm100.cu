@@ -237,7 +237,7 @@ static int launch_patch_conv2(const void* pm, int cols, int w, int band_rows, co
   CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "patch_conv2: bad dims (w must be 20)");
   const PackedLayout L = packed_layout(1, 1, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  CMLPL_CUDA(cudaFuncSetAttribute(patch_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pc2::SMEM));
+  CMLPL_MAX_DYN_SMEM(patch_conv2_kernel, pc2::SMEM);
   const int64_t npix = int64_t(band_rows) * cols;
   int64_t grid = sm_count();
   if (grid > (npix + 1) / 2) grid = (npix + 1) / 2;

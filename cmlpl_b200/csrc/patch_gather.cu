@@ -207,7 +207,7 @@ extern "C" int cmlpl_patch_gather_f32(const float* cube, int scene_rows, int col
                                                        noise_scale, out);
   } else {
     auto kern = patch_gather_kernel<false>;
-    CMLPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CMLPL_MAX_DYN_SMEM(kern, int(smem));
     const int ctas_per_sm = smem * 2 <= 227 * 1024 ? 2 : 1;
     int64_t grid = int64_t(sm_count()) * ctas_per_sm * 4;
     if (grid > n) grid = n;

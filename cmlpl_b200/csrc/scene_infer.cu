@@ -110,7 +110,7 @@ static int launch_conv0(const T* in, int K, int scene_rows, int cols, int slab_r
   const int64_t cap = int64_t(sm_count()) * 2;
   if (grid > cap) grid = cap;
   const size_t smem = sizeof(float) * (size_t(K) * 64 + K + 64);
-  CMLPL_CUDA(cudaFuncSetAttribute(conv0_tiled_kernel<T, kVec4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  CMLPL_MAX_DYN_SMEM((conv0_tiled_kernel<T, kVec4>), int(smem));
   conv0_tiled_kernel<T, kVec4><<<int(grid), 256, smem, s>>>(in, K, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n, wt,
                                                             bias, mu, f0pad);
   CMLPL_CHECK_LAUNCH("conv0_map");
