@@ -135,7 +135,7 @@ int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, int slab_row0
                       void* workspace, size_t workspace_bytes,
                       uint8_t* labels, float* logits, cmlpl_stream_t stream);
 
-/* The same from the RAW cube (dtype 0 = uint16, 1 = float32; <= 16 classes, <= 208 bands): the PCA
+/* The same from the RAW cube (dtype 0 = uint16, 1 = float32; <= 16 classes, <= 224 bands): the PCA
  * projection and both z-scores of tools/hyper_tools.py:285-292 are folded into conv0
  * (wf f32 [B][64] = (W0 . (U/s)^T)^T, bf f32 [64] = b0 - W0 . m/s) and into the fp16 conversion of the
  * spectral branch (mu, inv_sigma f32 [B]); neither the PCA cube nor the z-scored spectra touch HBM.
