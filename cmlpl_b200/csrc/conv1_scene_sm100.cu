@@ -380,92 +380,79 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
         for (int pp = 0; pp < 2; ++pp, xpar ^= 1) {
           const int chunk = h * 4 + pp * 2 + chsel;
           const uint32_t col = uint32_t(pp * 16 + chsel * 8);
-          float T[3][3][8];
+          typedef unsigned long long f2;                       // two packed fp32 channels (FADD2 / FMUL2)
+          f2 T[3][3][4];
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) tmem_ld8(lane_addr + sl[dy] * SUBCOLS + dx * 32 + col, T[dy][dx]);
+            for (int dx = 0; dx < 3; ++dx) tmem_ld8_x2(lane_addr + sl[dy] * SUBCOLS + dx * 32 + col, T[dy][dx]);
           tmem_ld_wait();
           if (pp == 1) {
             tc_fence_before();
 #pragma unroll
             for (int k = 0; k < 3; ++k) mbar_arrive(bars + 8 * (S_EMPTY0 + sl[k]));
           }
-          float base[8];
           {
+            // bias + residual (centre entry of the A tile) go into the centre tap, which every border class keeps
             const uint4 rv = *reinterpret_cast<const uint4*>(smem + S_A + buf * ABYTES + chunk * CH + ((ty + 1) * TP + tx) * 16);
             const __half2* hr = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 f = __half22float2(hr[e]);
-              base[2 * e] = f.x + sbias[chunk * 8 + 2 * e];
-              base[2 * e + 1] = f.y + sbias[chunk * 8 + 2 * e + 1];
+              T[1][1][e] = f2_add(T[1][1][e], f2_pack(f.x + sbias[chunk * 8 + 2 * e], f.y + sbias[chunk * 8 + 2 * e + 1]));
             }
           }
           // G[a][b] = relu(b1 + F0 + sum of the taps the (row class a, column class b) border keeps)
-          float G[3][3][8];
+          f2 G[3][3][4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float R[3][3];
+          for (int c = 0; c < 4; ++c) {
+            f2 R[3][3];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-              const float s12 = T[dy][1][c] + T[dy][2][c];
-              R[dy][0] = s12; R[dy][1] = T[dy][0][c] + s12; R[dy][2] = T[dy][0][c] + T[dy][1][c];
+              const f2 s12 = f2_add(T[dy][1][c], T[dy][2][c]);
+              R[dy][0] = s12; R[dy][1] = f2_add(T[dy][0][c], s12); R[dy][2] = f2_add(T[dy][0][c], T[dy][1][c]);
             }
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
-              const float top = R[1][b] + R[2][b];
-              G[0][b][c] = fmaxf(top + base[c], 0.f);
-              G[1][b][c] = fmaxf((R[0][b] + top) + base[c], 0.f);
-              G[2][b][c] = fmaxf((R[0][b] + R[1][b]) + base[c], 0.f);
+              const f2 top = f2_add(R[1][b], R[2][b]);
+              G[0][b][c] = f2_relu(top);
+              G[1][b][c] = f2_relu(f2_add(R[0][b], top));
+              G[2][b][c] = f2_relu(f2_add(R[0][b], R[1][b]));
             }
           }
           // vertical partner through shared memory: this thread publishes its mid / bot variants
-          float4* xb = reinterpret_cast<float4*>(smem + S_X + xpar * XBYTES);
+          ulonglong2* xb = reinterpret_cast<ulonglong2*>(smem + S_X + xpar * XBYTES);
 #pragma unroll
           for (int a = 1; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3; ++b)
 #pragma unroll
               for (int q = 0; q < 2; ++q)
-                xb[(((a - 1) * 3 + b) * 2 + q) * kEpi + tid] =
-                    make_float4(G[a][b][4 * q], G[a][b][4 * q + 1], G[a][b][4 * q + 2], G[a][b][4 * q + 3]);
+                xb[(((a - 1) * 3 + b) * 2 + q) * kEpi + tid] = make_ulonglong2(G[a][b][2 * q], G[a][b][2 * q + 1]);
           named_bar_sync(1, kEpi);
-          float V[3][3][8];                                    // [A][b]
+          f2 V[3][3][4];                                       // [A][b]
 #pragma unroll
           for (int b = 0; b < 3; ++b)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const float4 m = xb[((0 * 3 + b) * 2 + q) * kEpi + nb];
-              const float4 o = xb[((1 * 3 + b) * 2 + q) * kEpi + nb];
-              const float mm[4] = {m.x, m.y, m.z, m.w}, oo[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = 4 * q + e;
-                V[0][b][c] = G[0][b][c] + mm[e];
-                V[1][b][c] = G[1][b][c] + mm[e];
-                V[2][b][c] = G[1][b][c] + oo[e];
-              }
+              const ulonglong2 m = xb[((0 * 3 + b) * 2 + q) * kEpi + nb];
+              const ulonglong2 o = xb[((1 * 3 + b) * 2 + q) * kEpi + nb];
+              V[0][b][2 * q] = f2_add(G[0][b][2 * q], m.x); V[0][b][2 * q + 1] = f2_add(G[0][b][2 * q + 1], m.y);
+              V[1][b][2 * q] = f2_add(G[1][b][2 * q], m.x); V[1][b][2 * q + 1] = f2_add(G[1][b][2 * q + 1], m.y);
+              V[2][b][2 * q] = f2_add(G[1][b][2 * q], o.x); V[2][b][2 * q + 1] = f2_add(G[1][b][2 * q + 1], o.y);
             }
-          // horizontal partner (tx+1) by shuffle, scale, round, store
+          // horizontal partner (tx+1) by shuffle, scale (0 for plane cells without a pooled value), round, store
+          const f2 sc = f2_pack(cell ? 0.25f : 0.f, cell ? 0.25f : 0.f);
 #pragma unroll
           for (int A = 0; A < 3; ++A) {
             __half2 o0[4], o1[4], o2[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float r[3][2];
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const int c = 2 * e + k;
-                const float n1 = __shfl_down_sync(0xffffffffu, V[A][1][c], 1);
-                const float n2 = __shfl_down_sync(0xffffffffu, V[A][2][c], 1);
-                r[0][k] = cell ? (V[A][0][c] + n1) * 0.25f : 0.f;
-                r[1][k] = cell ? (V[A][1][c] + n1) * 0.25f : 0.f;
-                r[2][k] = cell ? (V[A][1][c] + n2) * 0.25f : 0.f;
-              }
-              o0[e] = __floats2half2_rn(r[0][0], r[0][1]);
-              o1[e] = __floats2half2_rn(r[1][0], r[1][1]);
-              o2[e] = __floats2half2_rn(r[2][0], r[2][1]);
+              const f2 n1 = f2_shfl_down1(V[A][1][e]), n2 = f2_shfl_down1(V[A][2][e]);
+              float lo, hi;
+              f2_unpack(f2_mul(f2_add(V[A][0][e], n1), sc), lo, hi); o0[e] = __floats2half2_rn(lo, hi);
+              f2_unpack(f2_mul(f2_add(V[A][1][e], n1), sc), lo, hi); o1[e] = __floats2half2_rn(lo, hi);
+              f2_unpack(f2_mul(f2_add(V[A][1][e], n2), sc), lo, hi); o2[e] = __floats2half2_rn(lo, hi);
             }
             if (inplane) {
               __half* dst = pmq + (int64_t(A * 3) * 32 * psz + opos + int64_t(chunk) * psz) * 8;

@@ -29,8 +29,8 @@ __global__ void __launch_bounds__(256, 2)
 conv0_tiled_kernel(const T* __restrict__ in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0,
                    int prow_n, int pcol_n, const float* __restrict__ wt, const float* __restrict__ bias,
                    const float* __restrict__ mu, __half* __restrict__ f0pad) {
-  extern __shared__ __align__(16) float sm0[];              // wt [K][64] | mu [K] | bias [64]
-  float* ws = sm0; float* mus = sm0 + K * 64; float* bs = mus + K;
+  extern __shared__ __align__(16) float sm0[];              // wt [K][64] | bias [64] | mu [K]
+  float* ws = sm0; float* bs = sm0 + K * 64; float* mus = bs + 64;                 // bias right after the weights: 8-byte aligned pairs
   for (int i = threadIdx.x; i < K * 64; i += blockDim.x) ws[i] = wt[i];
   for (int i = threadIdx.x; i < K; i += blockDim.x) mus[i] = mu ? mu[i] : 0.f;
   if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
@@ -50,22 +50,26 @@ conv0_tiled_kernel(const T* __restrict__ in, int K, int scene_rows, int cols, in
       const int sc = mirror_index(pc + lo, cols);
       src[j] = in + (int64_t(sr) * cols + sc) * K;
     }
-    float acc[4][16];
+    // accumulators as packed pairs: fma.rn.f32x2 (FFMA2) does two fp32 FMAs per issue slot, each rounded exactly like fmaf
+    unsigned long long acc2[4][8];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc[j][c] = bs[cg * 16 + c];
+      for (int c = 0; c < 8; ++c) acc2[j][c] = *reinterpret_cast<const unsigned long long*>(&bs[cg * 16 + 2 * c]);
     auto fma_k = [&](int k, const float (&x)[4]) {
-      float wv[16];
+      unsigned long long wv[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 t = *reinterpret_cast<const float4*>(&ws[k * 64 + cg * 16 + 4 * q]);
-        wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(&ws[k * 64 + cg * 16 + 4 * q]);
+        wv[2 * q] = t.x; wv[2 * q + 1] = t.y;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 4; ++j) {
+        unsigned long long xx;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x[j]));
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[j][c] = fmaf(x[j], wv[c], acc[j][c]);
+        for (int c = 0; c < 8; ++c) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[j][c]) : "l"(xx), "l"(wv[c]));
+      }
     };
     if constexpr (kVec4) {                                  // float rows, 16-byte aligned, K % 4 == 0
 #pragma unroll 1
@@ -94,7 +98,11 @@ conv0_tiled_kernel(const T* __restrict__ in, int K, int scene_rows, int cols, in
         for (int q = 0; q < 2; ++q) {
           __half2 h[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[j][q * 8 + 2 * e], acc[j][q * 8 + 2 * e + 1]);
+          for (int e = 0; e < 4; ++e) {
+            float lo_, hi_;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo_), "=f"(hi_) : "l"(acc2[j][q * 4 + e]));
+            h[e] = __floats2half2_rn(lo_, hi_);
+          }
           *reinterpret_cast<uint4*>(f0pad + (int64_t(cg * 2 + q) * plane + pp) * 8) = *reinterpret_cast<uint4*>(h);
         }
       }

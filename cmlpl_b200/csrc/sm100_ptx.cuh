@@ -91,6 +91,35 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tcgen05.ld of 8 columns as four packed fp32 pairs (register pairs are adjacent, the packing is free)
+__device__ __forceinline__ void tmem_ld8_x2(uint32_t taddr, unsigned long long* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v[i]) : "r"(r[2 * i]), "r"(r[2 * i + 1]));
+}
+// packed fp32 pairs (sm_100 FADD2 / FMUL2: two IEEE fp32 operations per issue slot, same rounding as the scalar ops)
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long a, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+__device__ __forceinline__ unsigned long long f2_relu(unsigned long long a) {
+  float lo, hi; f2_unpack(a, lo, hi); return f2_pack(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+}
+__device__ __forceinline__ unsigned long long f2_shfl_down1(unsigned long long a) {
+  float lo, hi; f2_unpack(a, lo, hi);
+  return f2_pack(__shfl_down_sync(0xffffffffu, lo, 1), __shfl_down_sync(0xffffffffu, hi, 1));
+}
 // named barrier among `count` threads (epilogue warps only; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
