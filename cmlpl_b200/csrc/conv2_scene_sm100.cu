@@ -339,7 +339,7 @@ static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "pool2_cls: TMA destinations 
 // 20 KB) is ONE cp.async.bulk.tensor (TMA, 4-D tile mode, zero fill outside the plane) into a ring of 8 slots,
 // each with its own full / empty mbarrier, so a single loader thread runs up to 8 variants ahead of the MMAs.
 __global__ void __launch_bounds__(p2c::kThreads, 1)
-pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, const unsigned char* __restrict__ wcq,
+pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int nq, const unsigned char* __restrict__ wcq,
                  float* __restrict__ lmap) {
   using namespace p2c;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -462,7 +462,8 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, con
         if (m == m1 - 1) { tc_fence_before(); mbar_arrive(bars + 8 * DEMPTY); }
         if (valid) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[int64_t(m * 4 + q) * psz] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; ++q)                         // class quads beyond the real classes are never read (head_sum_kernel)
+            if (q < nq) dst[int64_t(m * 4 + q) * psz] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
     }
@@ -524,7 +525,8 @@ extern "C" int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_row
   CUtensorMap tm_y;
   const int trc = make_scene_tmap(&tm_y, yq, 100, PR2, PC2, p2c::TH + 1, p2c::TP);
   if (trc != CMLPL_OK) return trc;
-  pool2_cls_kernel<<<grid, p2c::kThreads, p2c::SMEM, static_cast<cudaStream_t>(stream)>>>(tm_y, PR2, PC2, pk + L.wcq, lmap);
+  pool2_cls_kernel<<<grid, p2c::kThreads, p2c::SMEM, static_cast<cudaStream_t>(stream)>>>(tm_y, PR2, PC2, (num_classes + 3) / 4,
+                                                                                          pk + L.wcq, lmap);
   CMLPL_CHECK_LAUNCH("pool2_cls");
   return CMLPL_OK;
 }

@@ -337,9 +337,9 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
   }
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi); }
+    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / 2); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bars + 8 * (H_FULL0 + i), kEpi); mbar_init(bars + 8 * (H_EMPTY0 + i), 1);
+      mbar_init(bars + 8 * (H_FULL0 + i), kEpi / 2); mbar_init(bars + 8 * (H_EMPTY0 + i), 1);
       mbar_init(bars + 8 * (L_FULL0 + i), 1); mbar_init(bars + 8 * (L_EMPTY0 + i), 128);
     }
     fence_barrier_init();
@@ -358,7 +358,10 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
         const uint32_t s = j % uint32_t(nA), ph = (j / uint32_t(nA)) & 1;
         mbar_wait(bars + 8 * (A_EMPTY0 + s), ph ^ 1, 91);
         mbar_arrive_expect_tx(bars + 8 * (A_FULL0 + s), abytes);
-        bulk_g2s(sbase + S_A + s * abytes, x16 + (mt0 + int64_t(j) * mstep) * int64_t(KC) * 1024, abytes, bars + 8 * (A_FULL0 + s));
+        // one bulk copy moves ~6-7 GB/s however large it is: the tile goes as KC/2 copies of 4 KB in flight together
+        const __half* src = x16 + (mt0 + int64_t(j) * mstep) * int64_t(KC) * 1024;
+        for (int c = 0; c < KC / 2; ++c)
+          bulk_g2s(sbase + S_A + s * abytes + c * 4096, src + c * 2048, 4096, bars + 8 * (A_FULL0 + s));
       }
     }
   } else if (warp == kMmaWarp) {
@@ -412,7 +415,9 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     }
   } else {
     // ================================================================ epilogue (warps 0-15)
-    const int q = warp & 3, ch = warp >> 2, L = q * 32 + lane;
+    // two groups of eight warps: group 0 takes the first hidden halves (even units), group 1 the second halves, so two
+    // TMEM -> registers -> shared memory -> MMA2 hand-overs are in flight; a thread owns one pixel row and 64 columns
+    const int grp = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1, L = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const float* sb = reinterpret_cast<const float*>(smem + S_BIAS);
     auto readout = [&](uint32_t ti) {                  // partial logits of tile ti (warps 0-3: one lane quarter each)
@@ -433,35 +438,36 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
 #pragma unroll
       for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     };
-    for (uint32_t u = 0; u < U; ++u) {
+    for (uint32_t u = uint32_t(grp); u < U; u += 2) {
       const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, hs = u % uint32_t(nH);
-      if (ch == 0 && hh == 1 && ti > 0) readout(ti - 1);      // deferred by a unit: its MMA2 has long completed
+      if (grp == 1 && ch == 0 && ti > 0) readout(ti - 1);     // deferred by a tile: its MMA2 has long completed
       mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
       mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
       tc_fence_after();
-      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * 4) * 2048 + L * 16;
-      const float* bb = sb + hh * 128 + ch * 32;
-      {
+      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * 8) * 2048 + L * 16;
+      const float* bb = sb + hh * 128 + ch * 64;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
         float v0[16], v1[16];
-        tmem_ld16(lane_addr + d * 128 + ch * 32, v0);
-        tmem_ld16(lane_addr + d * 128 + ch * 32 + 16, v1);
+        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 32, v0);
+        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 32 + 16, v1);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bars + 8 * (D1_EMPTY0 + d));
+        if (g == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (D1_EMPTY0 + d)); }
         __half2 h[16];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          h[e] = __floats2half2_rn(fmaxf(v0[2 * e] + bb[2 * e], 0.f), fmaxf(v0[2 * e + 1] + bb[2 * e + 1], 0.f));
-          h[8 + e] = __floats2half2_rn(fmaxf(v1[2 * e] + bb[16 + 2 * e], 0.f), fmaxf(v1[2 * e + 1] + bb[16 + 2 * e + 1], 0.f));
+          h[e] = __floats2half2_rn(fmaxf(v0[2 * e] + bb[g * 32 + 2 * e], 0.f), fmaxf(v0[2 * e + 1] + bb[g * 32 + 2 * e + 1], 0.f));
+          h[8 + e] = __floats2half2_rn(fmaxf(v1[2 * e] + bb[g * 32 + 16 + 2 * e], 0.f),
+                                        fmaxf(v1[2 * e + 1] + bb[g * 32 + 16 + 2 * e + 1], 0.f));
         }
         const uint4* hv = reinterpret_cast<const uint4*>(h);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(hdst + k * 2048) = hv[k];
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(hdst + (g * 4 + k) * 2048) = hv[k];
       }
       fence_proxy_async();                             // generic-proxy writes of H -> visible to the tensor core
       mbar_arrive(bars + 8 * (H_FULL0 + hs));
     }
-    if (ch == 0 && my_tiles > 0) readout(uint32_t(my_tiles - 1));
+    if (grp == 1 && ch == 0 && my_tiles > 0) readout(uint32_t(my_tiles - 1));
   }
   tc_fence_before();
   __syncthreads();
