@@ -50,16 +50,16 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
     out[col] = t;
   }
 }
-// db[co] = sum_{b,pos} dy[b][co][pos]: one CTA per output channel, grid-stride over (b, pos), tree reduce
+// db[co] = sum_{b,pos} dy[b][co][pos]: grid (co, splits); a CTA sums the contiguous planes of every splits-th sample
+// and adds its partial to db (zeroed by the caller) -- 64 channels alone cannot fill 148 SMs
 __global__ void __launch_bounds__(256)
 conv_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int b, int co, int hw) {
   __shared__ float red[8];
   const int c = blockIdx.x;
   float s = 0.f;
-  const int total = b * hw;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int bi = i / hw, r = i - bi * hw;
-    s += dy[(int64_t(bi) * co + c) * hw + r];
+  for (int bi = blockIdx.y; bi < b; bi += gridDim.y) {
+    const float* p = dy + (int64_t(bi) * co + c) * hw;
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) s += __ldg(p + i);
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -67,7 +67,7 @@ conv_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int 
   if (threadIdx.x < 32) {
     float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) db[c] = v;
+    if (threadIdx.x == 0) atomicAdd(db + c, v);
   }
 }
 
@@ -156,7 +156,8 @@ extern "C" int cmlpl_conv2d_wgrad_f32(const float* x, const float* dy, float* dw
   else rc = launch_gemm(co, N, Kp, splits, WgradA{dy, co, h * w}, WgradB<3>{x, ci, h, w}, fc, s, "conv3x3_wgrad");
   if (rc != CMLPL_OK) return rc;
   if (db) {
-    conv_bias_grad_kernel<<<co, 256, 0, s>>>(dy, db, b, co, h * w);
+    CMLPL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * size_t(co), s));
+    conv_bias_grad_kernel<<<dim3(co, b < 32 ? b : 32), 256, 0, s>>>(dy, db, b, co, h * w);
     CMLPL_CHECK_LAUNCH("conv_bias_grad");
   }
   return rc;

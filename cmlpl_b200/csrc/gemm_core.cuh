@@ -120,11 +120,10 @@ gemm_tile_kernel(int M, int N, int K, int kper, FA fa, FB fb, FC fc) {
   if (am_ok) fa.prep(am);
   // compute mapping: 16x16 threads, 4x4 outputs each
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  // accumulators as packed fp32 pairs along n: fma.rn.f32x2 (FFMA2) = two fp32 FMAs per issue slot, each rounded like fmaf
+  unsigned long long acc2[4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < 4; ++i) acc2[i][0] = acc2[i][1] = 0ull;
 
   float ra[4], rb[4];
   auto gload = [&](int k0) {
@@ -153,12 +152,15 @@ gemm_tile_kernel(int M, int N, int K, int kper, FA fa, FB fb, FC fc) {
 #pragma unroll
       for (int k = 0; k < TK; ++k) {
         const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(&Bs[buf][k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int i = 0; i < 4; ++i) {
+          unsigned long long aa;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(av[i]));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][0]) : "l"(aa), "l"(b.x));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][1]) : "l"(aa), "l"(b.y));
+        }
       }
       if (more) {
         sstore(buf ^ 1);
@@ -167,6 +169,11 @@ gemm_tile_kernel(int M, int N, int K, int kper, FA fa, FB fb, FC fc) {
       }
     }
   }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2 * j]), "=f"(acc[i][2 * j + 1]) : "l"(acc2[i][j]));
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
