@@ -99,9 +99,12 @@ int cmlpl_l2norm_bwd_f32(const float* y, const float* norm, const float* dy, flo
 /* ------------------------------------------------------------ scene inference --
  * tools/hyper_tools.py:416-437 (test_whole) over a whole scene / row band without ever
  * materialising patches: conv0 is evaluated once per scene pixel into a mirrored,
- * halo-padded fp16 map; a persistent tcgen05 kernel runs conv1/conv2 (+residual, ReLU,
- * 2x2 avg-pool) per pixel with the patch window staged in shared memory; the classifier
- * (+ spectral branch) and argmax finish in a head kernel.
+ * halo-padded fp16 map; conv1 (+residual, ReLU, 2x2 avg-pool), conv2 and the pool + conv columns of
+ * the classifier are evaluated ONCE PER SCENE POSITION in the 9 / 25 classes of how a patch border can
+ * cut them (exact compute sharing; persistent tcgen05 kernels fed by TMA tile loads); the spectral
+ * branch is one fused two-GEMM kernel; a sum head adds each pixel's 25 gathered conv partials to its
+ * spectral partials and takes the argmax.  > 16 classes or > 224 bands fall back to the all-per-pixel
+ * tcgen05 kernel (patch window staged in shared memory) and CUDA-core heads.
  *
  * Packed weights: cmlpl_pack_basenet2() converts the reference state_dict tensors
  * (models.py:102-127: conv0/1/2.{weight,bias}, feat_spe.*, classifier.*) into the
@@ -120,7 +123,8 @@ int cmlpl_pack_basenet2(const float* conv0_w, const float* conv0_b,
 size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w);
 
 /* Byte offsets of the workspace regions (for stage-level profiling): offsets[12] =
- * {f0pad, x16, h16, g, pmq, yq, lmap, p2, spe_logits, hidden, total, uses_tensor_core_path}. */
+ * {f0pad, x16, h16 (partial spectral logits f32 [4][ceil(n/128)*128][16] on the dense path), g (unused, zero-sized),
+ *  pmq, yq, lmap, p2, spe_logits, hidden, total, uses_tensor_core_path}. */
 int cmlpl_scene_workspace_layout(int band_rows, int cols, int num_features, int num_classes, int w,
                                  size_t* offsets);
 
