@@ -337,9 +337,10 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
   }
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / 2); }
+    // nH epilogue groups (one per hidden half-tile slot): each group's barriers see that group's threads only
+    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / nH); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bars + 8 * (H_FULL0 + i), kEpi / 2); mbar_init(bars + 8 * (H_EMPTY0 + i), 1);
+      mbar_init(bars + 8 * (H_FULL0 + i), kEpi / nH); mbar_init(bars + 8 * (H_EMPTY0 + i), 1);
       mbar_init(bars + 8 * (L_FULL0 + i), 1); mbar_init(bars + 8 * (L_EMPTY0 + i), 128);
     }
     fence_barrier_init();
@@ -415,9 +416,12 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     }
   } else {
     // ================================================================ epilogue (warps 0-15)
-    // two groups of eight warps: group 0 takes the first hidden halves (even units), group 1 the second halves, so two
-    // TMEM -> registers -> shared memory -> MMA2 hand-overs are in flight; a thread owns one pixel row and 64 columns
-    const int grp = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1, L = q * 32 + lane;
+    // nH = 2: two groups of eight warps, group 0 takes the first hidden halves (even units), group 1 the second halves,
+    // each with its own half-tile slot, so two TMEM -> registers -> shared memory -> MMA2 hand-overs are in flight and a
+    // thread owns one pixel row x 64 columns.  nH = 1 (wide spectra leave room for one slot): one group of sixteen warps
+    // on every unit, 32 columns per thread -- two groups on ONE slot could run two barrier phases apart.
+    const int G = nH, grp = G == 2 ? warp >> 3 : 0, q = warp & 3, ch = G == 2 ? (warp >> 2) & 1 : warp >> 2, L = q * 32 + lane;
+    const int cpt = 128 / (4 / G);                                // columns per thread: 64 or 32
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const float* sb = reinterpret_cast<const float*>(smem + S_BIAS);
     auto readout = [&](uint32_t ti) {                  // partial logits of tile ti (warps 0-3: one lane quarter each)
@@ -438,21 +442,21 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
 #pragma unroll
       for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     };
-    for (uint32_t u = uint32_t(grp); u < U; u += 2) {
+    for (uint32_t u = uint32_t(grp); u < U; u += uint32_t(G)) {
       const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, hs = u % uint32_t(nH);
-      if (grp == 1 && ch == 0 && ti > 0) readout(ti - 1);     // deferred by a tile: its MMA2 has long completed
+      if (hh == 1 && ch == 0 && ti > 0) readout(ti - 1);      // deferred by a tile: its MMA2 has long completed
       mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
       mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
       tc_fence_after();
-      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * 8) * 2048 + L * 16;
-      const float* bb = sb + hh * 128 + ch * 64;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * (cpt / 8)) * 2048 + L * 16;
+      const float* bb = sb + hh * 128 + ch * cpt;
+#pragma unroll 1
+      for (int g = 0; g < cpt / 32; ++g) {
         float v0[16], v1[16];
-        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 32, v0);
-        tmem_ld16(lane_addr + d * 128 + ch * 64 + g * 32 + 16, v1);
+        tmem_ld16(lane_addr + d * 128 + ch * cpt + g * 32, v0);
+        tmem_ld16(lane_addr + d * 128 + ch * cpt + g * 32 + 16, v1);
         tmem_ld_wait();
-        if (g == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (D1_EMPTY0 + d)); }
+        if (g == cpt / 32 - 1) { tc_fence_before(); mbar_arrive(bars + 8 * (D1_EMPTY0 + d)); }
         __half2 h[16];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -467,7 +471,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       fence_proxy_async();                             // generic-proxy writes of H -> visible to the tensor core
       mbar_arrive(bars + 8 * (H_FULL0 + hs));
     }
-    if (grp == 1 && ch == 0 && my_tiles > 0) readout(uint32_t(my_tiles - 1));
+    if ((G == 1 || grp == 1) && ch == 0 && my_tiles > 0) readout(uint32_t(my_tiles - 1));
   }
   tc_fence_before();
   __syncthreads();

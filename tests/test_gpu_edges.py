@@ -146,3 +146,49 @@ def test_dense_tail_matches_per_pixel_tail(dev, B, K):
     assert rel(logits.cpu().numpy(), log2.cpu().numpy()) < 5e-4
     assert torch.equal(labels.cpu(), logits.argmax(1).to(torch.uint8).cpu())
     assert float((labels == lab2).float().mean()) > 0.995
+
+
+def test_full_size_scene_properties(dev):
+    """BASELINE.json's headline shape (610 x 340 x 103, 9 classes) at full size, through size-independent properties:
+    labels are the argmax of the returned logits, an uneven 4-band walk with read-only halos reproduces the one-shot
+    label map bit for bit, a second run is bit-identical (no race in the persistent kernels), and a stride of sampled
+    pixels agrees with the CPU oracle."""
+    from cmlpl_b200 import ops
+    R, C, B, K, w = 610, 340, 103, 9, 20
+    gen = torch.Generator(device=dev); gen.manual_seed(7)
+    cube = torch.randn((R, C, 60), device=dev, generator=gen)
+    spectra = torch.randn((R * C, B), device=dev, generator=gen)
+    torch.manual_seed(7)
+    sd = O.basenet2_init(B, K)
+    packed = ops.pack_basenet2({k: v.to(dev) for k, v in sd.items()}, B, K, w)
+    lab, logits = ops.scene_infer(cube, spectra, packed, K, w, want_logits=True)
+    assert torch.equal(lab, logits.argmax(1).to(torch.uint8))
+    assert torch.equal(lab, ops.scene_infer(cube, spectra, packed, K, w))
+    parts, r0 = [], 0
+    for rows in (97, 200, 13, 300):
+        parts.append(ops.scene_infer(cube, spectra[r0 * C:(r0 + rows) * C], packed, K, w, band_row0=r0, band_rows=rows,
+                                     scene_rows=R))
+        r0 += rows
+    assert r0 == R and torch.equal(torch.cat(parts), lab)
+    idx = np.arange(0, R * C, 6007)
+    cube_h = cube.cpu().numpy()
+    with torch.no_grad():
+        ref, _ = O.basenet2_forward(sd, torch.from_numpy(O.extract_patches_at(cube_h, w, idx)), spectra[torch.from_numpy(idx).to(dev)].cpu())
+    assert rel(logits[torch.from_numpy(idx).to(dev)].cpu().numpy(), ref.numpy()) < 1e-3
+
+
+def test_wide_spectrum_scene_in_row_bands(dev):
+    """224 bands / 16 classes (the AVIRIS-NG-scale shape of BASELINE.json configs[4], reduced to 300 x 257 pixels): the
+    row-band walk an 8192 x 8192 scene needs gives the one-shot label map bit for bit."""
+    from cmlpl_b200 import ops
+    R, C, B, K, w = 300, 257, 224, 16, 20
+    gen = torch.Generator(device=dev); gen.manual_seed(9)
+    cube = torch.randn((R, C, 60), device=dev, generator=gen)
+    spectra = torch.randn((R * C, B), device=dev, generator=gen)
+    torch.manual_seed(9)
+    packed = ops.pack_basenet2({k: v.to(dev) for k, v in O.basenet2_init(B, K).items()}, B, K, w)
+    full = ops.scene_infer(cube, spectra, packed, K, w)
+    ws = ops.scene_workspace(64, C, B, K, w, dev)
+    parts = [ops.scene_infer(cube, spectra[a * C:min(a + 64, R) * C], packed, K, w, band_row0=a, band_rows=min(64, R - a),
+                             scene_rows=R, workspace=ws) for a in range(0, R, 64)]
+    assert torch.equal(torch.cat(parts), full)
