@@ -192,3 +192,33 @@ def test_wide_spectrum_scene_in_row_bands(dev):
     parts = [ops.scene_infer(cube, spectra[a * C:min(a + 64, R) * C], packed, K, w, band_row0=a, band_rows=min(64, R - a),
                              scene_rows=R, workspace=ws) for a in range(0, R, 64)]
     assert torch.equal(torch.cat(parts), full)
+
+
+@pytest.mark.parametrize("B,K,dtype", [(103, 9, "u16"), (200, 16, "f32")])
+def test_raw_path_mid_size_matches_preprocessed_path(dev, B, K, dtype):
+    """cmlpl_scene_infer_raw on a scene large enough that every persistent kernel walks several tiles per CTA
+    (220 x 180 pixels): logits within 2e-3 of the path that materialises the PCA cube / z-scored spectra first, the
+    same labels wherever the margin allows, band walk bit-identical."""
+    from cmlpl_b200 import ops, preprocess, synth
+    R, C = 220, 180
+    cube_u16, _ = synth.synth_scene(R, C, B, K, seed=12)
+    raw = torch.from_numpy(cube_u16.reshape(-1, B).copy()).to(dev)
+    pp = preprocess.fit(raw, 60)
+    cube, spec = preprocess.apply(raw, pp)
+    torch.manual_seed(12)
+    sd = {k: v.to(dev) for k, v in O.basenet2_init(B, K).items()}
+    packed = ops.pack_basenet2(sd, B, K, 20)
+    lab_a, log_a = ops.scene_infer(cube.view(R, C, 60), spec, packed, K, 20, want_logits=True)
+    folded = pp.folded_conv0(sd["conv0.weight"], sd["conv0.bias"], dev)
+    raw_in = raw if dtype == "u16" else raw.float()
+    lab_b, log_b = ops.scene_infer_raw(raw_in, folded, packed, K, C, 20, want_logits=True)
+    assert rel(log_b.cpu().numpy(), log_a.cpu().numpy()) < 2e-3
+    assert torch.equal(lab_b, log_b.argmax(1).to(torch.uint8))
+    assert float((lab_a == lab_b).float().mean()) > 0.99
+    parts = []
+    for a in range(0, R, 64):
+        b = min(a + 64, R)
+        s0, s1 = max(0, a - 10), min(R, b + 9)
+        parts.append(ops.scene_infer_raw(raw_in[s0 * C:s1 * C].contiguous(), folded, packed, K, C, 20, band_row0=a,
+                                         band_rows=b - a, scene_rows=R, slab_row0=s0))
+    assert torch.equal(torch.cat(parts), lab_b)
