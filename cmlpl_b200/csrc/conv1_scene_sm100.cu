@@ -263,9 +263,9 @@ constexpr int S_W = 0, S_A = WBYTES, S_X = S_A + 2 * ABYTES, S_BIAS = S_X + 2 * 
 constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
 constexpr int NSUB = 5, SUBCOLS = 96;
 constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
-enum { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, S_FULL0 = 4, S_EMPTY0 = 4 + NSUB };
+enum { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, S_FULL0 = 4, S_EMPTY0 = 4 + NSUB, W_FULL = 4 + 2 * NSUB };
 static_assert(SMEM <= 232448, "conv1_pool: shared memory over the 227 KB limit");
-static_assert(S_EMPTY0 + NSUB <= 16, "conv1_pool: barrier area too small");
+static_assert(W_FULL < 16, "conv1_pool: barrier area too small");
 static_assert(S_A % 128 == 0 && ABYTES % 128 == 0, "conv1_pool: TMA destinations must be 128-byte aligned");
 }  // namespace c1p
 
@@ -284,14 +284,14 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
   const int64_t psz = int64_t(PR2) * PC2;
 
   {
-    const uint4* gw = reinterpret_cast<const uint4*>(w1p);
-    uint4* sw = reinterpret_cast<uint4*>(smem + S_W);
-    for (int i = tid; i < WBYTES / 16; i += kThreads) sw[i] = __ldg(gw + i);
     uint4* z = reinterpret_cast<uint4*>(smem + S_A);
     for (int i = tid; i < 2 * ABYTES / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid < 64) sbias[tid] = b1g[tid];
   if (tid == 0) {
+    mbar_init(bars + 8 * W_FULL, 1);
+    fence_barrier_init();
+    bulk_weights_g2s(sbase + S_W, w1p, WBYTES, bars + 8 * W_FULL);
     mbar_init(bars + 8 * A_FULL0, 1); mbar_init(bars + 8 * A_FULL1, 1);
     mbar_init(bars + 8 * A_EMPTY0, 1 + kEpi); mbar_init(bars + 8 * A_EMPTY1, 1 + kEpi);
     for (int s = 0; s < NSUB; ++s) { mbar_init(bars + 8 * (S_FULL0 + s), 1); mbar_init(bars + 8 * (S_EMPTY0 + s), kEpi); }
@@ -324,6 +324,7 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
     constexpr uint32_t kI32 = make_idesc_f16(128, 32);
     const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
     uint32_t j = 0, slot = 0, sph = 0;
+    mbar_wait(bars + 8 * W_FULL, 0, 80);                       // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const uint32_t buf = j & 1, ph = (j >> 1) & 1;
       // MMA row m of tap (dy,dx) reads tile entry m + dy*TP + dx - 1: descriptors start 16 B before the tile

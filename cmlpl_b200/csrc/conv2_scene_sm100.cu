@@ -107,7 +107,7 @@ constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
 constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader (one thread, TMA), warp 9 MMA issuer
 constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
-enum { XF = 0, MF, XE, ME, DF0 = 4, DE0 = 9 };       // DF/DE: accumulator block of row class rho full / drained
+enum { XF = 0, MF, XE, ME, DF0 = 4, DE0 = 9, W_FULL = 14 };   // DF/DE: accumulator block of row class rho full / drained
 static_assert(SMEM <= 232448, "conv2_scene: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "conv2_scene: TMA destinations must be 128-byte aligned");
 // first tile row (relative to Y0 - 1) held by the tile of PM row class a: top rows +1.., mid +2.., bot +5..
@@ -161,14 +161,14 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
   const int64_t psz = int64_t(PR2) * PC2;
 
   {
-    const uint4* gw = reinterpret_cast<const uint4*>(w2p);
-    uint4* sw = reinterpret_cast<uint4*>(smem + S_W);
-    for (int i = tid; i < WBYTES / 16; i += kThreads) sw[i] = __ldg(gw + i);
     uint4* z = reinterpret_cast<uint4*>(smem + S_T);
     for (int i = tid; i < 6 * TBYTES / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid < 64) sbias[tid] = b2g[tid];
   if (tid == 0) {
+    mbar_init(bars + 8 * W_FULL, 1);
+    fence_barrier_init();
+    bulk_weights_g2s(sbase + S_W, w2p, WBYTES, bars + 8 * W_FULL);
     mbar_init(bars + 8 * XF, 1); mbar_init(bars + 8 * MF, 1);
     mbar_init(bars + 8 * XE, 1 + kEpi); mbar_init(bars + 8 * ME, 1 + kEpi);   // MMA commit + every epilogue thread's residual reads
     for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi / 2); }
@@ -230,6 +230,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
       C2S_GROUP(KAP, 4, (umma_commit(bars + 8 * (DF0 + 3)), umma_commit(bars + 8 * (DF0 + 4))));              \
       ++kc;                                                                          \
     } while (0)
+    mbar_wait(bars + 8 * c2s::W_FULL, 0, 60);                  // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       mbar_wait(bars + 8 * XF, fx & 1, 62); ++fx;              // left
       mbar_wait(bars + 8 * MF, fm & 1, 62); ++fm;              // mid
@@ -328,7 +329,7 @@ constexpr int S_W = 0, S_T = WBYTES, S_BAR = S_T + NSLOT * TBYTES + 128, S_TMEM 
 constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
 constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader, warp 9 MMA issuer
 constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
-enum { F0 = 0, E0 = NSLOT, DFULL = 2 * NSLOT, DEMPTY };
+enum { F0 = 0, E0 = NSLOT, DFULL = 2 * NSLOT, DEMPTY, W_FULL };
 static_assert(SMEM <= 232448, "pool2_cls: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "pool2_cls: TMA destinations must be 128-byte aligned");
 }  // namespace p2c
@@ -351,13 +352,13 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
   const int64_t psz = int64_t(PR2) * PC2;
 
   {
-    const uint4* gw = reinterpret_cast<const uint4*>(wcq);
-    uint4* sw = reinterpret_cast<uint4*>(smem + S_W);
-    for (int i = tid; i < WBYTES / 16; i += kThreads) sw[i] = __ldg(gw + i);
     uint4* z = reinterpret_cast<uint4*>(smem + S_T);
     for (int i = tid; i < (NSLOT * TBYTES + 128) / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) {
+    mbar_init(bars + 8 * W_FULL, 1);
+    fence_barrier_init();
+    bulk_weights_g2s(sbase + S_W, wcq, WBYTES, bars + 8 * W_FULL);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(bars + 8 * (F0 + s), 1); mbar_init(bars + 8 * (E0 + s), 1); }
     mbar_init(bars + 8 * DFULL, 1); mbar_init(bars + 8 * DEMPTY, kEpi);
     fence_barrier_init();
@@ -398,6 +399,7 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
     if (tmem != 0) { printf("pool2_cls: unexpected TMEM base %u\n", tmem); __trap(); }
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
     uint32_t slot = 0, ph = 0, tj = 0;
+    mbar_wait(bars + 8 * p2c::W_FULL, 0, 70);                  // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tj) {
       mbar_wait(bars + 8 * DEMPTY, (tj & 1) ^ 1, 72);          // epilogue of the previous tile has drained TMEM
       tc_fence_after();

@@ -305,7 +305,7 @@ constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
 constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
 constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, 2 stages x 4 logits accumulators at 384..511
-enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 16, L_FULL0 = 18, L_EMPTY0 = 20 };   // nA <= 4
+enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 16, L_FULL0 = 18, L_EMPTY0 = 20, W_FULL = 22 };   // nA <= 4
 }  // namespace spl
 
 __global__ void __launch_bounds__(spl::kThreads, 1)
@@ -326,16 +326,16 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
   const uint32_t U = uint32_t(2 * my_tiles);           // units = (tile, hidden half)
 
   {
-    const uint4* g = reinterpret_cast<const uint4*>(w1t) + size_t(ntile) * (wbytes / 16);
-    uint4* sd = reinterpret_cast<uint4*>(smem + S_W);
-    for (uint32_t i = tid; i < wbytes / 16; i += kThreads) sd[i] = __ldg(g + i);
-    const uint4* gc = reinterpret_cast<const uint4*>(wc_spe16) + size_t(ntile) * (WCBYTES / 16);
-    uint4* sc = reinterpret_cast<uint4*>(smem + S_WC);
-    for (uint32_t i = tid; i < WCBYTES / 16; i += kThreads) sc[i] = __ldg(gc + i);
     float* sb = reinterpret_cast<float*>(smem + S_BIAS);
     if (tid < 256) sb[tid] = bspe[ntile * 256 + tid];
   }
   if (tid == 0) {
+    mbar_init(bars + 8 * W_FULL, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bars + 8 * W_FULL, wbytes + WCBYTES);   // this quarter's feat_spe rows and classifier columns
+    const unsigned char* gw = reinterpret_cast<const unsigned char*>(w1t) + size_t(ntile) * wbytes;
+    for (uint32_t o = 0; o < wbytes; o += 8192) bulk_g2s(sbase + S_W + o, gw + o, wbytes - o < 8192 ? wbytes - o : 8192, bars + 8 * W_FULL);
+    bulk_g2s(sbase + S_WC, reinterpret_cast<const unsigned char*>(wc_spe16) + size_t(ntile) * WCBYTES, WCBYTES, bars + 8 * W_FULL);
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
     // nH epilogue groups (one per hidden half-tile slot): each group's barriers see that group's threads only
     for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / nH); }
@@ -409,6 +409,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     };
     // MMA1 runs a full accumulator ring (3 units) ahead of the epilogue: it only needs a drained TMEM slot, never the
     // hidden half-tile, so the epilogue -> MMA2 hand-over is the only dependency left on the critical path
+    mbar_wait(bars + 8 * W_FULL, 0, 90);                 // weights have landed
     for (uint32_t u = 0; u < 3 && u < U; ++u) issue1(u);
     for (uint32_t u = 0; u < U; ++u) {
       issue2(u);

@@ -39,6 +39,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// weights -> shared memory as a handful of bulk copies in flight together, all completing on one mbarrier (the MMA
+// issuer waits on it before its first tcgen05.mma); called by ONE thread right after it initialised the barrier.
+// Replaces an LDG -> STS loop whose dependent round trips cost ~15 us at the head of every persistent kernel.
+__device__ __forceinline__ void bulk_weights_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  mbar_arrive_expect_tx(bar, bytes);
+  const unsigned char* g = static_cast<const unsigned char*>(src);
+  for (uint32_t o = 0; o < bytes; o += 8192) {
+    const uint32_t n = bytes - o < 8192 ? bytes - o : 8192;
+    bulk_g2s(dst_smem + o, g + o, n, bar);
+  }
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
