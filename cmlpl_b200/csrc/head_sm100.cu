@@ -300,12 +300,12 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
 //   readout                    part[quarter][pixel][16] f32: the head adds the 4 quarter partials (53 MB instead of the
 //                              425 MB hidden tensor written and read back)
 namespace spl {
-constexpr int kEpi = 512, kThreads = kEpi + 64;      // warps 0-15 epilogue (lane quarter x 32-column group), warp 16 loader, warp 17 MMA issuer
-constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
+constexpr int kEpi = 512, kThreads = kEpi + 96;      // warps 0-15 epilogue, warp 16 loader, warp 17 MMA1 issuer (+ TMEM), warp 18 MMA2 issuer
+constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1, kMma2Warp = kLoadWarp + 2;
 constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
 constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
-constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, 2 stages x 4 logits accumulators at 384..511
-enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 16, L_FULL0 = 18, L_EMPTY0 = 20, W_FULL = 22 };   // nA <= 4
+constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, 4 stages x 2 logits accumulators at 384..511
+enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 16, L_FULL0 = 18, L_EMPTY0 = 22, W_FULL = 26 };   // nA <= 4, 4 logits stages
 }  // namespace spl
 
 __global__ void __launch_bounds__(spl::kThreads, 1)
@@ -339,10 +339,8 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
     // nH epilogue groups (one per hidden half-tile slot): each group's barriers see that group's threads only
     for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / nH); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bars + 8 * (H_FULL0 + i), kEpi / nH); mbar_init(bars + 8 * (H_EMPTY0 + i), 1);
-      mbar_init(bars + 8 * (L_FULL0 + i), 1); mbar_init(bars + 8 * (L_EMPTY0 + i), 128);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(bars + 8 * (H_FULL0 + i), kEpi / nH); mbar_init(bars + 8 * (H_EMPTY0 + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (L_FULL0 + i), 1); mbar_init(bars + 8 * (L_EMPTY0 + i), 128); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
@@ -369,8 +367,11 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     // ================================================================ MMA issuer
     if (tmem != 0) { printf("spectral_logits: unexpected TMEM base %u\n", tmem); __trap(); }
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
-    constexpr uint32_t idesc1 = make_idesc_f16(128, 128), idesc2 = make_idesc_f16(128, 16);
-    auto issue1 = [&](uint32_t u) {                    // hidden half-tile of unit u
+    constexpr uint32_t idesc1 = make_idesc_f16(128, 128);
+    // MMA1 only: gated by the input tile and a drained accumulator slot, never by the epilogue -> MMA2 hand-over, so it
+    // really runs the full ring (3 units) ahead; MMA2 is issued by its own warp below
+    mbar_wait(bars + 8 * W_FULL, 0, 90);                 // weights have landed
+    for (uint32_t u = 0; u < U; ++u) {
       const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, s = ti % uint32_t(nA);
       if (hh == 0) mbar_wait(bars + 8 * (A_FULL0 + s), (ti / uint32_t(nA)) & 1, 92);
       mbar_wait(bars + 8 * (D1_EMPTY0 + d), ((u / 3) & 1) ^ 1, 93);
@@ -386,34 +387,30 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
         if (hh == 1) umma_commit(bars + 8 * (A_EMPTY0 + s));
       }
       __syncwarp();
-    };
-    auto issue2 = [&](uint32_t u) {                    // classifier columns over the hidden half-tile of unit u
-      const uint32_t ti = u >> 1, hh = u & 1, hs = u % uint32_t(nH), ls = ti & 1;
+    }
+  } else if (warp == kMma2Warp) {
+    // ================================================================ MMA2 issuer: classifier columns over the hidden half-tiles
+    constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
+    constexpr uint32_t idesc2 = make_idesc_f16(128, 16);
+    mbar_wait(bars + 8 * W_FULL, 0, 90);
+    for (uint32_t u = 0; u < U; ++u) {
+      const uint32_t ti = u >> 1, hh = u & 1, hs = u % uint32_t(nH), ls = ti & 3;
       mbar_wait(bars + 8 * (H_FULL0 + hs), (u / uint32_t(nH)) & 1, 94);
-      if (hh == 0) mbar_wait(bars + 8 * (L_EMPTY0 + ls), ((ti >> 1) & 1) ^ 1, 95);
+      if (hh == 0) mbar_wait(bars + 8 * (L_EMPTY0 + ls), ((ti >> 2) & 1) ^ 1, 95);
       tc_fence_after();
       if (elect_one_sync()) {
         uint32_t a_lo = ((sbase + S_H + hs * HBYTES) >> 4) | (uint32_t(2048 >> 4) << 16);
         uint32_t b_lo = ((sbase + S_WC + hh * 16 * 256) >> 4) | (uint32_t(256 >> 4) << 16);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          // four independent accumulators (k-step mod 4): back-to-back N=16 MMAs into ONE accumulator serialise on
-          // its ~190-cycle update latency; the readout adds the four
-          umma_f16(D2COL + ls * 64 + (ks & 3) * 16, kHi | a_lo, kHi | b_lo, idesc2, (hh | (ks >> 2)) ? 1u : 0u);
+          // two independent accumulators (even / odd k-steps); the readout adds them
+          umma_f16(D2COL + ls * 32 + (ks & 1) * 16, kHi | a_lo, kHi | b_lo, idesc2, (hh | (ks >> 1)) ? 1u : 0u);
           a_lo += 4096 >> 4; b_lo += 512 >> 4;
         }
         umma_commit(bars + 8 * (H_EMPTY0 + hs));
         if (hh == 1) umma_commit(bars + 8 * (L_FULL0 + ls));
       }
       __syncwarp();
-    };
-    // MMA1 runs a full accumulator ring (3 units) ahead of the epilogue: it only needs a drained TMEM slot, never the
-    // hidden half-tile, so the epilogue -> MMA2 hand-over is the only dependency left on the critical path
-    mbar_wait(bars + 8 * W_FULL, 0, 90);                 // weights have landed
-    for (uint32_t u = 0; u < 3 && u < U; ++u) issue1(u);
-    for (uint32_t u = 0; u < U; ++u) {
-      issue2(u);
-      if (u + 3 < U) issue1(u + 3);
     }
   } else {
     // ================================================================ epilogue (warps 0-15)
@@ -425,27 +422,25 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     const int cpt = 128 / (4 / G);                                // columns per thread: 64 or 32
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const float* sb = reinterpret_cast<const float*>(smem + S_BIAS);
-    auto readout = [&](uint32_t ti) {                  // partial logits of tile ti (warps 0-3: one lane quarter each)
-      const uint32_t ls = ti & 1;
-      mbar_wait(bars + 8 * (L_FULL0 + ls), (ti >> 1) & 1, 96);
+    auto readout = [&](uint32_t ti) {                  // partial logits of tile ti (four warps: one lane quarter each)
+      const uint32_t ls = ti & 3;
+      mbar_wait(bars + 8 * (L_FULL0 + ls), (ti >> 2) & 1, 96);
       tc_fence_after();
-      float v[16], w1[16], w2[16], w3[16];
-      tmem_ld16(lane_addr + D2COL + ls * 64, v);
-      tmem_ld16(lane_addr + D2COL + ls * 64 + 16, w1);
-      tmem_ld16(lane_addr + D2COL + ls * 64 + 32, w2);
-      tmem_ld16(lane_addr + D2COL + ls * 64 + 48, w3);
+      float v[16], w1[16];
+      tmem_ld16(lane_addr + D2COL + ls * 32, v);
+      tmem_ld16(lane_addr + D2COL + ls * 32 + 16, w1);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bars + 8 * (L_EMPTY0 + ls));
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = (v[c] + w1[c]) + (w2[c] + w3[c]);
+      for (int c = 0; c < 16; ++c) v[c] += w1[c];
       float4* dst = reinterpret_cast<float4*>(part) + ((int64_t(ntile) * mtiles + (mt0 + int64_t(ti) * mstep)) * 128 + L) * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     };
     for (uint32_t u = uint32_t(grp); u < U; u += uint32_t(G)) {
       const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, hs = u % uint32_t(nH);
-      if (hh == 1 && ch == 0 && ti > 0) readout(ti - 1);      // deferred by a tile: its MMA2 has long completed
+      if (hh == 1 && ch == 0 && ti > 1) readout(ti - 2);      // deferred by two tiles (4 logits stages): its MMA2 has long completed
       mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
       mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
       tc_fence_after();
@@ -472,7 +467,10 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       fence_proxy_async();                             // generic-proxy writes of H -> visible to the tensor core
       mbar_arrive(bars + 8 * (H_FULL0 + hs));
     }
-    if ((G == 1 || grp == 1) && ch == 0 && my_tiles > 0) readout(uint32_t(my_tiles - 1));
+    if ((G == 1 || grp == 1) && ch == 0) {
+      if (my_tiles > 1) readout(uint32_t(my_tiles - 2));
+      if (my_tiles > 0) readout(uint32_t(my_tiles - 1));
+    }
   }
   tc_fence_before();
   __syncthreads();
