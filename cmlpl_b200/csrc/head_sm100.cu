@@ -305,7 +305,7 @@ constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1, kMma2Warp = kLoad
 constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
 constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
 constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, 4 stages x 2 logits accumulators at 384..511
-enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 16, L_FULL0 = 18, L_EMPTY0 = 22, W_FULL = 26 };   // nA <= 4, 4 logits stages
+enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 17, L_FULL0 = 20, L_EMPTY0 = 24, W_FULL = 28 };   // nA <= 4, nH <= 3, 4 logits stages
 }  // namespace spl
 
 __global__ void __launch_bounds__(spl::kThreads, 1)
@@ -337,9 +337,11 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     for (uint32_t o = 0; o < wbytes; o += 8192) bulk_g2s(sbase + S_W + o, gw + o, wbytes - o < 8192 ? wbytes - o : 8192, bars + 8 * W_FULL);
     bulk_g2s(sbase + S_WC, reinterpret_cast<const unsigned char*>(wc_spe16) + size_t(ntile) * WCBYTES, WCBYTES, bars + 8 * W_FULL);
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
-    // nH epilogue groups (one per hidden half-tile slot): each group's barriers see that group's threads only
-    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / nH); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bars + 8 * (H_FULL0 + i), kEpi / nH); mbar_init(bars + 8 * (H_EMPTY0 + i), 1); }
+    // one or two epilogue groups (two as soon as there are >= 2 hidden half-tile slots); a unit's barriers see the
+    // threads of the group that owns it only
+    const int ng = nH >= 2 ? 2 : 1;
+    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / ng); }
+    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (H_FULL0 + i), kEpi / ng); mbar_init(bars + 8 * (H_EMPTY0 + i), 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (L_FULL0 + i), 1); mbar_init(bars + 8 * (L_EMPTY0 + i), 128); }
     fence_barrier_init();
   }
@@ -414,11 +416,11 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     }
   } else {
     // ================================================================ epilogue (warps 0-15)
-    // nH = 2: two groups of eight warps, group 0 takes the first hidden halves (even units), group 1 the second halves,
-    // each with its own half-tile slot, so two TMEM -> registers -> shared memory -> MMA2 hand-overs are in flight and a
-    // thread owns one pixel row x 64 columns.  nH = 1 (wide spectra leave room for one slot): one group of sixteen warps
-    // on every unit, 32 columns per thread -- two groups on ONE slot could run two barrier phases apart.
-    const int G = nH, grp = G == 2 ? warp >> 3 : 0, q = warp & 3, ch = G == 2 ? (warp >> 2) & 1 : warp >> 2, L = q * 32 + lane;
+    // nH >= 2: two groups of eight warps, group 0 takes the first hidden halves (even units), group 1 the second halves;
+    // unit u writes half-tile slot u % nH, so with three slots a group never waits for the MMA2 of its own previous unit.
+    // A thread owns one pixel row x 64 columns.  nH = 1 (wide spectra leave room for one slot): one group of sixteen
+    // warps on every unit, 32 columns per thread -- two groups on ONE slot could run two barrier phases apart.
+    const int G = nH >= 2 ? 2 : 1, grp = G == 2 ? warp >> 3 : 0, q = warp & 3, ch = G == 2 ? (warp >> 2) & 1 : warp >> 2, L = q * 32 + lane;
     const int cpt = 128 / (4 / G);                                // columns per thread: 64 or 32
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const float* sb = reinterpret_cast<const float*>(smem + S_BIAS);
@@ -537,8 +539,8 @@ using namespace cmlpl;
 
 // shared-memory plan of spectral_logits_kernel for KC input k-chunks: prefers 3 input stages + 2 hidden half-tiles
 static bool spectral_logits_plan(int KC, int* nA, int* nH, size_t* smem) {
-  const int opts[5][2] = {{3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 1}};   // input tiles in flight hide the L2 latency
-  for (int i = 0; i < 5; ++i) {
+  const int opts[6][2] = {{2, 3}, {3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 1}};   // hidden half-tile slots first, then input tiles in flight
+  for (int i = 0; i < 6; ++i) {
     const size_t b = size_t(KC) * 4096 + size_t(opts[i][0]) * KC * 2048 + size_t(opts[i][1]) * spl::HBYTES + spl::WCBYTES +
                      1024 + 256 + 64;
     if (b <= 232448) { *nA = opts[i][0]; *nH = opts[i][1]; *smem = b; return true; }
