@@ -107,7 +107,10 @@ constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
 constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader (one thread, TMA), warp 9 MMA issuer
 constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
 constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
-enum { XF = 0, MF, XE, ME, DF0 = 4, DE0 = 9, W_FULL = 14 };   // DF/DE: accumulator block of row class rho full / drained
+// one full / empty mbarrier per resident class tile (slab X or M x row class a), so the next tile's loads start as each
+// tile is released (top tiles after the PA group of the last column class that reads them, ...) instead of after the
+// whole slab; DF/DE: accumulator block of row class rho full / drained
+enum { XF0 = 0, MF0 = 3, XE0 = 6, ME0 = 9, DF0 = 12, DE0 = 17, W_FULL = 22 };
 static_assert(SMEM <= 232448, "conv2_scene: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "conv2_scene: TMA destinations must be 128-byte aligned");
 // first tile row (relative to Y0 - 1) held by the tile of PM row class a: top rows +1.., mid +2.., bot +5..
@@ -169,8 +172,14 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
     mbar_init(bars + 8 * W_FULL, 1);
     fence_barrier_init();
     bulk_weights_g2s(sbase + S_W, w2p, WBYTES, bars + 8 * W_FULL);
-    mbar_init(bars + 8 * XF, 1); mbar_init(bars + 8 * MF, 1);
-    mbar_init(bars + 8 * XE, 1 + kEpi); mbar_init(bars + 8 * ME, 1 + kEpi);   // MMA commit + every epilogue thread's residual reads
+    for (int a = 0; a < 3; ++a) {
+      mbar_init(bars + 8 * (XF0 + a), 1); mbar_init(bars + 8 * (MF0 + a), 1);
+      // released by the MMA commit after the last group that reads this class tile + EVERY epilogue thread once it has
+      // done its last residual read of the whole slab (a finer per-tile accounting of the epilogue reads was ~3 %
+      // faster but produced one differing run in ~400 under scripts/stress_determinism.py)
+      const uint32_t cnt = 1 + kEpi;
+      mbar_init(bars + 8 * (XE0 + a), cnt); mbar_init(bars + 8 * (ME0 + a), cnt);
+    }
     for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi / 2); }
     fence_barrier_init();
   }
@@ -185,22 +194,22 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
     // ================================================================ loader: one thread, three TMA boxes per slab
     if (lane == 0) {
       tma_prefetch_desc(&tm_pm);
-      uint32_t fx = 0, fm = 0;                                 // fills of slab X / slab M so far
+      uint32_t fx[3] = {0, 0, 0}, fm[3] = {0, 0, 0};           // fills of each class tile of slab X / slab M so far
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int pl = t / tiles_p, tt = t - pl * tiles_p;
         const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
         const int y0 = tr * TH - 1, x0 = tc * TW - 1;          // borders zero-filled; tile of row class a starts at row y0 + tile_r0(a)
-#pragma unroll 1
-        for (int step = 0; step < 3; ++step) {                 // left -> X, mid -> M, right -> X
-          const int slab = step == 1 ? 1 : 0, bcls = step;
-          const uint32_t k = slab ? fm : fx;
-          const uint32_t full = bars + 8 * (slab ? MF : XF);
-          mbar_wait(bars + 8 * (slab ? ME : XE), (k & 1) ^ 1, 61);
-          mbar_arrive_expect_tx(full, 3 * TBYTES);
+        // left and mid tiles interleaved in the order the MMA groups need them (top, mid, bottom), then the right tiles
 #pragma unroll
-          for (int a = 0; a < 3; ++a)
-            tma_load_tile(sbase + S_T + (slab * 3 + a) * TBYTES, &tm_pm, x0, y0 + tile_r0(a), (a * 3 + bcls) * 4 + pl, full);
-          if (slab) ++fm; else ++fx;
+        for (int i = 0; i < 9; ++i) {
+          const int a = i < 6 ? i >> 1 : i - 6;
+          const int slab = i < 6 ? (i & 1) : 0, bcls = i < 6 ? (i & 1) : 2;
+          const uint32_t k = slab ? fm[a] : fx[a];
+          const uint32_t full = bars + 8 * ((slab ? MF0 : XF0) + a);
+          mbar_wait(bars + 8 * ((slab ? ME0 : XE0) + a), (k & 1) ^ 1, 61);
+          mbar_arrive_expect_tx(full, TBYTES);
+          tma_load_tile(sbase + S_T + (slab * 3 + a) * TBYTES, &tm_pm, x0, y0 + tile_r0(a), (a * 3 + bcls) * 4 + pl, full);
+          if (slab) ++fm[a]; else ++fx[a];
         }
       }
     }
@@ -209,43 +218,49 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
     if (tmem != 0) { printf("conv2_scene: unexpected TMEM base %u\n", tmem); __trap(); }
     const uint32_t t_lo = ((sbase + S_T - 16) >> 4) | (uint32_t(CH >> 4) << 16);
     const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
-    uint32_t fx = 0, fm = 0, kc = 0;                           // slab fills consumed, column-class stages issued
+    uint32_t cx[3] = {0, 0, 0}, cm[3] = {0, 0, 0}, kc = 0;     // class-tile fills consumed, column-class stages issued
 #define C2S_GROUP(KAP, G, ...)                                                       \
     do {                                                                             \
       tc_fence_after();                                                              \
       if (elect_one_sync()) { issue_group<KAP, G>(t_lo, w_lo); __VA_ARGS__; }        \
       __syncwarp();                                                                  \
     } while (0)
-#define C2S_COLUMN(KAP)                                                              \
+    // WX / WM: this column class is the first to read a fresh fill of slab X / M (wait per class tile, just before the
+    // first group that reads it); RX / RM: it is the last to read the resident fill (release per class tile)
+#define C2S_FILL(A, WX, WM)                                                          \
+    do {                                                                             \
+      if (WX) { mbar_wait(bars + 8 * (XF0 + A), cx[A] & 1, 62); ++cx[A]; }           \
+      if (WM) { mbar_wait(bars + 8 * (MF0 + A), cm[A] & 1, 62); ++cm[A]; }           \
+    } while (0)
+#define C2S_REL(A, RX, RM) ((RX) ? umma_commit(bars + 8 * (XE0 + A)) : (void)0, (RM) ? umma_commit(bars + 8 * (ME0 + A)) : (void)0)
+#define C2S_COLUMN(KAP, WX, WM, RX, RM)                                              \
     do {                                                                             \
       const uint32_t ep = (kc & 1) ^ 1;                                              \
+      C2S_FILL(0, WX, WM);                                                           \
       mbar_wait(bars + 8 * (DE0 + 0), ep, 63); mbar_wait(bars + 8 * (DE0 + 1), ep, 63);                       \
-      C2S_GROUP(KAP, 0, (void)0);                                                    \
+      C2S_GROUP(KAP, 0, C2S_REL(0, RX, RM));                                         \
+      C2S_FILL(1, WX, WM);                                                           \
       mbar_wait(bars + 8 * (DE0 + 2), ep, 63);                                       \
       C2S_GROUP(KAP, 1, umma_commit(bars + 8 * (DF0 + 0)));                          \
       mbar_wait(bars + 8 * (DE0 + 3), ep, 63);                                       \
       C2S_GROUP(KAP, 2, umma_commit(bars + 8 * (DF0 + 1)));                          \
       mbar_wait(bars + 8 * (DE0 + 4), ep, 63);                                       \
-      C2S_GROUP(KAP, 3, umma_commit(bars + 8 * (DF0 + 2)));                          \
-      C2S_GROUP(KAP, 4, (umma_commit(bars + 8 * (DF0 + 3)), umma_commit(bars + 8 * (DF0 + 4))));              \
+      C2S_GROUP(KAP, 3, (umma_commit(bars + 8 * (DF0 + 2)), C2S_REL(1, RX, RM)));    \
+      C2S_FILL(2, WX, WM);                                                           \
+      C2S_GROUP(KAP, 4, (umma_commit(bars + 8 * (DF0 + 3)), umma_commit(bars + 8 * (DF0 + 4)), C2S_REL(2, RX, RM)));   \
       ++kc;                                                                          \
     } while (0)
     mbar_wait(bars + 8 * c2s::W_FULL, 0, 60);                  // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      mbar_wait(bars + 8 * XF, fx & 1, 62); ++fx;              // left
-      mbar_wait(bars + 8 * MF, fm & 1, 62); ++fm;              // mid
-      C2S_COLUMN(0);
-      C2S_COLUMN(1);
-      if (elect_one_sync()) umma_commit(bars + 8 * XE);        // left tiles consumed
-      __syncwarp();
-      C2S_COLUMN(2);
-      mbar_wait(bars + 8 * XF, fx & 1, 62); ++fx;              // right
-      C2S_COLUMN(3);
-      C2S_COLUMN(4);
-      if (elect_one_sync()) { umma_commit(bars + 8 * XE); umma_commit(bars + 8 * ME); }
-      __syncwarp();
+      C2S_COLUMN(0, true, true, false, false);                 // left + mid arrive
+      C2S_COLUMN(1, false, false, true, false);                // last reader of the left tiles
+      C2S_COLUMN(2, false, false, false, false);
+      C2S_COLUMN(3, true, false, false, false);                // right tiles arrive
+      C2S_COLUMN(4, false, false, true, true);                 // last reader of the right and mid tiles
     }
 #undef C2S_COLUMN
+#undef C2S_REL
+#undef C2S_FILL
 #undef C2S_GROUP
   } else {
     // ================================================================ epilogue (warps 0-7)
@@ -278,9 +293,10 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
 #pragma unroll
         for (int k = 0; k < 8; ++k) res[k] = *reinterpret_cast<const uint4*>(rp + k * CH);
       }
-      if (r == 3 || r == 4) mbar_arrive(bars + 8 * XE);        // this thread's last read of the left slab (kap = 0)
-      if (r == 18 || r == 19) mbar_arrive(bars + 8 * ME);      // ... of the mid slab (kap = 1..3)
-      if (r == 23 || r == 24) mbar_arrive(bars + 8 * XE);      // ... of the right slab (kap = 4)
+      // this thread's last residual read of a slab releases its share of all three class tiles (r = kap*5 + rho; a thread
+      // sees one parity of r per tile): left tiles are read by kap = 0 only, mid tiles by kap = 1..3, right tiles by kap = 4
+      if (r == 3 || r == 4 || r == 23 || r == 24) { mbar_arrive(bars + 8 * (XE0 + 0)); mbar_arrive(bars + 8 * (XE0 + 1)); mbar_arrive(bars + 8 * (XE0 + 2)); }
+      else if (r == 18 || r == 19) { mbar_arrive(bars + 8 * (ME0 + 0)); mbar_arrive(bars + 8 * (ME0 + 1)); mbar_arrive(bars + 8 * (ME0 + 2)); }
       __half* dst = yq + (int64_t((rho * 5 + kap) * 4 + pl) * 8 * psz + pos) * 8;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {                         // 32 channels at a time
