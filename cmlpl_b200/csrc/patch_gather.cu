@@ -138,8 +138,11 @@ patch_gather_reg_kernel(const float* __restrict__ cube, int scene_rows, int cols
       for (int u = 0; u < U; ++u) {
         const int t = t0 + u * blockDim.x;
         const int gp = t / pair_items, rem = t - gp * pair_items;
-        f4s[u] = rem >> 1;
-        gs[u] = (t < items) ? gp * 2 + (rem & 1) : groups;
+        // groups come in pairs (adjacent lanes -> adjacent 16-byte stores); an odd group count (w*w/4 odd, i.e.
+        // w = 2 mod 4) leaves a last half-filled pair whose f4n items all belong to group `groups - 1`
+        const bool tail = (groups & 1) && gp == (groups >> 1);
+        f4s[u] = tail ? rem : rem >> 1;
+        gs[u] = (t < items) ? (tail ? groups - 1 : gp * 2 + (rem & 1)) : groups;
         if (gs[u] < groups) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {

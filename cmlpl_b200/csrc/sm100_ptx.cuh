@@ -23,11 +23,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug must trap (kernel error), never hang the GPU
+// bounded wait: a protocol bug must trap (kernel error), never hang the GPU.  The bound is wall clock (10 s of
+// %globaltimer, sampled every 4096 polls), not an iteration count: time slicing, a profiler replay, clock throttling
+// or a TMEM allocation waiting for a co-resident kernel can legitimately stretch a wait by orders of magnitude.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 26); ++it)
+  for (int it = 0; it < 4096; ++it)
     if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+#pragma unroll 1
+  for (;;) {
+#pragma unroll 1
+    for (int it = 0; it < 4096; ++it)
+      if (mbar_try_wait(bar, parity)) return;
+    if (global_timer_ns() - t0 > 10000000000ull) break;
+  }
   printf("cmlpl: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
   __trap();
 }

@@ -18,7 +18,7 @@ import os
 
 import numpy as np
 
-from .tools.hyper_tools import DATASETS, _MAT, PCANorm, featureNormalize
+from .tools.hyper_tools import DATASETS, _MAT, PCANorm, _loadmat, featureNormalize
 
 
 def split_indices(Y, num_label):
@@ -47,9 +47,8 @@ def load_scene(dataID, root="./dataset/", synthetic=False, seed=1088):
         shape = {1: synth.SHAPES["paviau"], 2: synth.SHAPES["salinas"], 3: synth.SHAPES["houston"],
                  4: synth.SHAPES["indian_pines"]}[dataID]
         return synth.synth_scene(*shape, seed=seed)
-    import scipy.io as sio
     fx, kx, fy, ky = _MAT[dataID]
-    return sio.loadmat(os.path.join(root, fx))[kx], sio.loadmat(os.path.join(root, fy))[ky]
+    return _loadmat(os.path.join(root, fx))[kx], _loadmat(os.path.join(root, fy))[ky]
 
 
 def main(args):

@@ -54,8 +54,15 @@ def _to_cube(X) -> torch.Tensor:
 
 def MirrowCut(X, hw):
     """hyper_tools.py:35-55 (== symmetric padding by hw).  Returned as float64 numpy like the reference.
-    Implemented as a w=1 gather of the padded coordinate grid through the same device index map."""
-    cube = _to_cube(X)
+    Implemented as a w=1 gather of the padded coordinate grid through the device index map of
+    cmlpl_patch_gather_f32.  float64 input keeps its bits: the cube is handed to the (pure copy) kernel as
+    2F float32 words per pixel and the result is viewed back as float64."""
+    as_f64 = isinstance(X, np.ndarray) and X.dtype == np.float64
+    if as_f64:
+        Xc = np.ascontiguousarray(X)
+        cube = torch.from_numpy(Xc).view(torch.float32).to(_device())          # [R, C, 2F] bit view
+    else:
+        cube = _to_cube(X)
     R, C, F = cube.shape
     if hw > R or hw > C:
         raise ValueError("MirrowCut: hw larger than the image")
@@ -66,10 +73,8 @@ def MirrowCut(X, hw):
     idx = (mr[:, None] * C + mc[None, :]).reshape(-1).contiguous()
     out = ops.patch_gather(cube, 1, idx=idx, odd_mode=True)          # [n, F, 1, 1]
     out = out.view(R + 2 * hw, C + 2 * hw, F)
-    if isinstance(X, np.ndarray) and X.dtype == np.float64:
-        # exact for float32-representable inputs; otherwise re-gather on host to keep float64 bits
-        res = np.asarray(X)[mr.cpu().numpy()[:, None], mc.cpu().numpy()[None, :], :]
-        return res.astype(np.float64)
+    if as_f64:
+        return out.cpu().contiguous().view(torch.float64).numpy()
     return out.cpu().numpy().astype(np.float64)
 
 
@@ -97,13 +102,33 @@ def _extract(X, w, idx, odd, as_numpy):
     return out.cpu().numpy() if as_numpy else out
 
 
+def _loadmat(path):
+    """scipy.io.loadmat, falling back to hdf5storage / h5py for MATLAB v7.3 (HDF5) files: the reference reads
+    indian_pines_corrected.mat with hdf5storage.loadmat (hyper_tools.py:271-276) because it ships in that format."""
+    import scipy.io as sio
+    try:
+        return sio.loadmat(path)
+    except NotImplementedError:
+        pass
+    try:
+        import hdf5storage
+        return hdf5storage.loadmat(path)
+    except ImportError:
+        pass
+    try:
+        import h5py
+    except ImportError as e:
+        raise ImportError(f"{path} is a MATLAB v7.3 (HDF5) file: install hdf5storage or h5py to read it") from e
+    with h5py.File(path, "r") as f:
+        # HDF5 stores MATLAB arrays column-major: reverse the axes to get MATLAB's index order
+        return {k: np.asarray(v).transpose() for k, v in f.items() if not k.startswith("#")}
+
+
 def SampleGen(dataID=1, w=16, n_PC=3, root="./dataset/", as_numpy=True):
     """hyper_tools.py:246-297: load the .mat scene, PCA + z-score -> (XP, X, Y)."""
-    import scipy.io as sio
-
     fx, kx, fy, ky = _MAT[dataID]
-    X = sio.loadmat(root + fx)[kx]
-    Y = sio.loadmat(root + fy)[ky]
+    X = _loadmat(root + fx)[kx]
+    Y = _loadmat(root + fy)[ky]
     row, col, n_feature = X.shape
     X = X.reshape(row * col, n_feature)
     X_PCA = featureNormalize(PCANorm(X, n_PC), 1).reshape(row, col, n_PC)
@@ -173,6 +198,7 @@ class StreamedScene:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.events = [torch.cuda.Event() for _ in self.bands]
         self.done = torch.cuda.Event()
+        self.d2h_done = torch.cuda.Event()
 
     def __call__(self, packed, cube_host, spectra_host, d2h=True):
         """cube_host f32 [s1-s0, C, 60] (pinned; slab rows s0..s1 of the scene), spectra_host f32
@@ -199,6 +225,13 @@ class StreamedScene:
         if not d2h:
             return self.labels
         self.labels_host.copy_(self.labels, non_blocking=True)
+        self.d2h_done.record(main)
+        return self.labels_host
+
+    def wait(self):
+        """Block the host until the labels of the last call have landed in ``labels_host`` (the D2H copy is
+        asynchronous: read the returned pinned tensor only after this, or after synchronising the stream)."""
+        self.d2h_done.synchronize()
         return self.labels_host
 
 
@@ -243,7 +276,8 @@ class StreamedRawScene:
 
     def __call__(self, packed, raw_host, d2h=True, folded=None):
         """raw_host [(s1-s0)*cols, B] pinned: raw rows s0..s1 of the scene.  Returns uint8 labels of the band
-        (the pinned host tensor of this call's buffer set when d2h, else the CUDA tensor)."""
+        (the pinned host tensor of this call's buffer set when d2h, else the CUDA tensor).  The D2H copy is
+        asynchronous: call ``wait()`` (or synchronise the stream) before reading the pinned tensor."""
         main = torch.cuda.current_stream()
         S, events = self.sets[self.calls & 1], self.events[self.calls & 1]
         self.calls += 1
@@ -278,8 +312,15 @@ class StreamedRawScene:
                             labels=S["labels"][qa:qb])
         if d2h:
             S["labels_host"].copy_(S["labels"], non_blocking=True)
-        S["done"].record(main)
+        S["done"].record(main)                                # after the D2H copy: also the "labels landed" event
         return S["labels_host"] if d2h else S["labels"]
+
+    def wait(self):
+        """Block the host until the last call's labels have landed in its pinned buffer and return it (the D2H
+        copy is asynchronous: read the tensor ``__call__`` returned only after this or a stream synchronise)."""
+        S = self.sets[(self.calls - 1) & 1]
+        S["done"].synchronize()
+        return S["labels_host"]
 
 
 def confusion_matrix(predict, label, num_classes):

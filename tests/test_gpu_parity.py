@@ -67,6 +67,30 @@ def test_patch_gather_random_idx_and_bands(dev, shape, w, odd):
         assert np.array_equal(np.concatenate(parts), full)
 
 
+@pytest.mark.parametrize("w", [2, 6, 10, 14, 18, 4, 8, 20])
+@pytest.mark.parametrize("feat", [60, 4])
+def test_patch_gather_vectorised_path_every_w(dev, w, feat):
+    """feat % 4 == 0 takes patch_gather_reg_kernel; w = 2 (mod 4) makes the group count odd (the last
+    half-filled pair used to be skipped, leaving torch.empty garbage).  Also with fused noise."""
+    from cmlpl_b200 import ops
+    rng = np.random.default_rng(100 + w)
+    X = rng.standard_normal((21, 19, feat)).astype(np.float32)
+    idx = rng.integers(0, 21 * 19, size=33)
+    Xd = torch.from_numpy(X).to(dev)
+    idx_d = torch.from_numpy(idx).to(dev)
+    # poison the caching allocator's free blocks so an unwritten element cannot pass by luck
+    poison = torch.full((33 * feat * w * w,), float("nan"), device=dev)
+    del poison
+    got = ops.patch_gather(Xd, w, idx=idx_d)
+    ref = O.extract_patches_at(X, w, idx, False)
+    assert np.array_equal(got.cpu().numpy(), ref)
+    noise = torch.randn(33, feat, w, w)
+    poison = torch.full((33 * feat * w * w,), float("nan"), device=dev)
+    del poison
+    got = ops.patch_gather(Xd, w, idx=idx_d, noise=noise.to(dev), noise_scale=0.5)
+    assert torch.equal(got.cpu(), torch.from_numpy(ref) + noise * 0.5)
+
+
 def test_patch_gather_fused_noise_is_bit_exact(dev):
     from cmlpl_b200 import ops
     rng = np.random.default_rng(4)
