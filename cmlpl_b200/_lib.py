@@ -67,6 +67,9 @@ SIGNATURES = {
     "cmlpl_graph_contrast_f32": (I, [P, P, P, P, L, I, I, F, I, F, P, P, P, P]),
     "cmlpl_ntxent_f32": (I, [P, L, I, F, P, P, P, P]),
     "cmlpl_adam_multi_f32": (I, [I, P, P, P, P, P, F, F, F, F, I, P]),
+    "cmlpl_train_workspace_bytes": (Z, [I, I, I, I, I]),
+    "cmlpl_train_step": (I, [P, I, P]),
+    "cmlpl_train_step_launches": (I, [I]),
 }
 
 

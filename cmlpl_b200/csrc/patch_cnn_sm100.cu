@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "conv_pair_issue.cuh"
+#include "train_common.cuh"
+#include "train_kernels.cuh"
 
 namespace cmlpl {
 
@@ -84,12 +86,18 @@ constexpr int kEpiWarps = kEpiThreads / 32, kLoadWarp0 = kEpiWarps, kMmaWarp = k
     if (TRACE && blockIdx.x == 0 && (p - p_begin) < 64) trace[(p - p_begin) * 16 + (slot)] = clock64(); \
   } while (0)
 
-template <int W, bool TRACE>
+// TRAIN = the forward trunk of the fused training step (tools/models.py:133-140 in batch mode): every "pixel" is one
+// sample of one of the two BaseNet2 peers whose conv0 output a0 [8 chunks][20x20][8] lies in the workspace.  The CTAs
+// are split between the nets (each keeps ONE net's weights, converted from the fp32 parameters in the prologue) and
+// the epilogues additionally save what the backward pass needs: the ReLU masks of both blocks as bits, the pooled
+// conv1 output p1 (B operand of conv2's weight gradient) and the pooled conv2 output as fp32 in the classifier's
+// flatten order (tools/models.py:141).
+template <int W, bool TRACE, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
                  const unsigned char* __restrict__ packed_w1, const unsigned char* __restrict__ packed_w2,
                  const float* __restrict__ b1g, const float* __restrict__ b2g, __half* __restrict__ p2out,
-                 int p2_tiled, long long* __restrict__ trace) {
+                 int p2_tiled, long long* __restrict__ trace, TrainCnnArgs ta) {
   using Cfg = PatchCfg<W>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -98,15 +106,36 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
   float* sbias = reinterpret_cast<float*>(smem + Cfg::S_BIAS);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::S_TMEM);
 
-  const int64_t npix = int64_t(band_rows) * cols;
-  const int64_t per = (npix + gridDim.x - 1) / gridDim.x;
-  const int64_t p_begin = blockIdx.x * per;
-  const int64_t p_end = (p_begin + per < npix) ? p_begin + per : npix;
-  const int pitch = cols + W - 1;   // padded map width in pixels
-  const int plane_rows = band_rows + W - 1;   // padded map height (rows per chunk plane)
+  // TRAIN: the grid is split evenly between the two nets; p runs over the GLOBAL sample index net*nb + row
+  const int cpn = TRAIN ? int(gridDim.x >> 1) : 1;
+  const int net = TRAIN ? int(blockIdx.x) / cpn : 0;
+  const int64_t npix = TRAIN ? int64_t(ta.nb) : int64_t(band_rows) * cols;
+  const int64_t nctas = TRAIN ? cpn : gridDim.x;
+  const int64_t cta = TRAIN ? int(blockIdx.x) - net * cpn : blockIdx.x;
+  const int64_t per = (npix + nctas - 1) / nctas;
+  const int64_t p_lo = cta * per;
+  const int64_t p_begin = (TRAIN ? int64_t(net) * ta.nb : 0) + (p_lo < npix ? p_lo : npix);
+  const int64_t p_end = (TRAIN ? int64_t(net) * ta.nb : 0) + ((p_lo + per < npix) ? p_lo + per : npix);
+  const int pitch = TRAIN ? W : cols + W - 1;   // padded map width in pixels
+  const int plane_rows = TRAIN ? W : band_rows + W - 1;   // padded map height (rows per chunk plane)
 
   // ---------------------------------------------------------------- one-time setup
-  {  // weights -> smem (already in UMMA layout), zero the activation planes, biases
+  if constexpr (TRAIN) {
+    // fp32 [co][ci][dy][dx] -> fp16 [3 dx][8 kchunks][192 rows = (2-dy)*64 + co][8 ci]  (conv_pair_issue.cuh)
+    __half* s1 = reinterpret_cast<__half*>(smem + Cfg::S_W1);
+    __half* s2 = reinterpret_cast<__half*>(smem + Cfg::S_W2);
+    const float* g1 = ta.w1[net];
+    const float* g2 = ta.w2[net];
+    for (int i = tid; i < 64 * 64 * 9; i += kThreads) {
+      const int co = i / 576, r = i - co * 576, ci = r / 9, t = r - ci * 9, dy = t / 3, dx = t - dy * 3;
+      const int dst = ((dx * 8 + (ci >> 3)) * kWRows + (2 - dy) * 64 + co) * 8 + (ci & 7);
+      s1[dst] = __float2half_rn(__ldg(g1 + i));
+      s2[dst] = __float2half_rn(__ldg(g2 + i));
+    }
+    uint4* z = reinterpret_cast<uint4*>(smem + Cfg::S_A2);
+    const int zn = (Cfg::SMEM - Cfg::S_A2) / 16;
+    for (int i = tid; i < zn; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  } else {  // weights -> smem (already in UMMA layout), zero the activation planes, biases
     const uint4* g1 = reinterpret_cast<const uint4*>(packed_w1);
     const uint4* g2 = reinterpret_cast<const uint4*>(packed_w2);
     uint4* s1 = reinterpret_cast<uint4*>(smem + Cfg::S_W1);
@@ -117,6 +146,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
     for (int i = tid; i < zn; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
+  if constexpr (TRAIN) { b1g = ta.b1[net]; b2g = ta.b2[net]; }
   if (tid < 64) { sbias[tid] = b1g[tid]; sbias[64 + tid] = b2g[tid]; }
   if (tid == 0) {
     mbar_init(bars + 8 * BAR_A1_FULL, kLoadThreads);
@@ -158,8 +188,13 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
     }
     uint32_t ph = 0;
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
-      const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
-      const __half* src = f0pad + (int64_t(rb) * pitch + c) * 8;
+      const __half* src;
+      if constexpr (TRAIN) {
+        src = ta.a0 + p * int64_t(kActBytes / 2);
+      } else {
+        const int rb = int(p / cols), c = int(p - int64_t(rb) * cols);
+        src = f0pad + (int64_t(rb) * pitch + c) * 8;
+      }
       mbar_wait(bars + 8 * BAR_A1_EMPTY, ph ^ 1, 1);         // conv1 MMAs + residual reads of the previous patch done
       // hold the copies back until the previous patch's conv1 epilogue has finished: the LSU queue is
       // shared with the epilogue's shared-memory traffic, and the load still hides under conv2
@@ -223,17 +258,25 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
     const float* bias2 = sbias + 64 + chalf * 32;
     uint32_t ph = 0;
     // bias + residual + ReLU on both rows of the pooling window, sum, add the horizontal neighbour
+    uint32_t mbits_e = 0, mbits_o = 0;   // TRAIN: ReLU masks (even / odd row of the pooling window), 16 bits per call
+    float pooled[16];                    // TRAIN reads the fp32 pooled values of the last call
     auto pool16 = [&](const float* e, const float* o, const uint4* re, const uint4* ro, const float* bias,
                       uint4& out_lo, uint4& out_hi) {
       const __half2* he = reinterpret_cast<const __half2*>(re);
       const __half2* ho = reinterpret_cast<const __half2*>(ro);
-      float pooled[16];
+      mbits_e = 0; mbits_o = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 fe = __half22float2(he[j]), fo = __half22float2(ho[j]);
         const float b0 = bias[2 * j], b1 = bias[2 * j + 1];
-        pooled[2 * j] = fmaxf(e[2 * j] + b0 + fe.x, 0.f) + fmaxf(o[2 * j] + b0 + fo.x, 0.f);
-        pooled[2 * j + 1] = fmaxf(e[2 * j + 1] + b1 + fe.y, 0.f) + fmaxf(o[2 * j + 1] + b1 + fo.y, 0.f);
+        const float e0 = e[2 * j] + b0 + fe.x, o0 = o[2 * j] + b0 + fo.x;
+        const float e1 = e[2 * j + 1] + b1 + fe.y, o1 = o[2 * j + 1] + b1 + fo.y;
+        if constexpr (TRAIN) {
+          mbits_e |= (e0 > 0.f ? 1u : 0u) << (2 * j) | (e1 > 0.f ? 1u : 0u) << (2 * j + 1);
+          mbits_o |= (o0 > 0.f ? 1u : 0u) << (2 * j) | (o1 > 0.f ? 1u : 0u) << (2 * j + 1);
+        }
+        pooled[2 * j] = fmaxf(e0, 0.f) + fmaxf(o0, 0.f);
+        pooled[2 * j + 1] = fmaxf(e1, 0.f) + fmaxf(o1, 0.f);
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) pooled[j] = (pooled[j] + __shfl_xor_sync(0xffffffffu, pooled[j], 1)) * 0.25f;
@@ -297,6 +340,17 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
           *reinterpret_cast<uint4*>(dst) = w0;
           *reinterpret_cast<uint4*>(dst + Cfg::CH2) = w1;
         }
+        uint32_t me = mbits_e, mo = mbits_o;
+        unsigned char* p1g = nullptr;
+        if constexpr (TRAIN) {
+          // pooled conv1 output of this sample: p1 [8 chunks][10x10][8]
+          p1g = reinterpret_cast<unsigned char*>(ta.p1) + p * int64_t(kAct2Bytes) + (chalf * 4) * (kTPos2 * 16) +
+                (i * (W / 2) + (x >> 1)) * 16;
+          if (writer) {
+            *reinterpret_cast<uint4*>(p1g) = w0;
+            *reinterpret_cast<uint4*>(p1g + kTPos2 * 16) = w1;
+          }
+        }
         if (tid == 0 && h == 0) CMLPL_TRACE(15);
         tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 0) * 64 + 16, e);
         tmem_ld16(lane_addr + Cfg::TM_C1 + (h * 2 + 1) * 64 + 16, o);
@@ -307,6 +361,17 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         if (writer) {
           *reinterpret_cast<uint4*>(dst + 2 * Cfg::CH2) = w0;
           *reinterpret_cast<uint4*>(dst + 3 * Cfg::CH2) = w1;
+        }
+        if constexpr (TRAIN) {
+          if (writer) {
+            *reinterpret_cast<uint4*>(p1g + 2 * kTPos2 * 16) = w0;
+            *reinterpret_cast<uint4*>(p1g + 3 * kTPos2 * 16) = w1;
+          }
+          if (valid) {   // m1 [sample][y][x][half]: bit c%32 of word c/32 = (a1[c][y][x] > 0), rows y = 2i, 2i+1
+            uint32_t* mg = ta.m1 + (p * kTPos + (2 * i) * W + x) * 2 + chalf;
+            mg[0] = me | (mbits_e << 16);
+            mg[2 * W] = mo | (mbits_o << 16);
+          }
         }
         if (tid == 0) CMLPL_TRACE(7 + 2 * h);
       }
@@ -349,14 +414,37 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
         tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64, o);
         tmem_ld_wait();
         pool16(e, o, &re[0], &ro[0], bias2, w0, w1);
-        if (writer) { __stcs(d4, w0); __stcs(d4 + dstep, w1); }
+        uint32_t me = mbits_e, mo = mbits_o;
+        float* catg = nullptr;
+        if constexpr (TRAIN) {
+          // flatten order of tools/models.py:141: feature = channel * 25 + pooled position
+          catg = ta.cat + p * int64_t(kCatDim) + (chalf * 32) * Cfg::P + pos;
+          if (writer) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) catg[j * Cfg::P] = pooled[j];
+          }
+        } else {
+          if (writer) { __stcs(d4, w0); __stcs(d4 + dstep, w1); }
+        }
         tmem_ld16(lane_addr + Cfg::TM_C2 + 0 * 64 + 16, e);
         tmem_ld16(lane_addr + Cfg::TM_C2 + 1 * 64 + 16, o);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bars + 8 * BAR_C2_EMPTY);
         pool16(e, o, &re[2], &ro[2], bias2 + 16, w0, w1);
-        if (writer) { __stcs(d4 + 2 * dstep, w0); __stcs(d4 + 3 * dstep, w1); }
+        if constexpr (TRAIN) {
+          if (writer) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) catg[(16 + j) * Cfg::P] = pooled[j];
+          }
+          if (valid) {   // m2 [sample][y][x][half], rows y = 2i, 2i+1 of the 10x10 conv2 output
+            uint32_t* mg = ta.m2 + (p * kTPos2 + (2 * i) * Cfg::H2 + x) * 2 + chalf;
+            mg[0] = me | (mbits_e << 16);
+            mg[2 * Cfg::H2] = mo | (mbits_o << 16);
+          }
+        } else {
+          if (writer) { __stcs(d4 + 2 * dstep, w0); __stcs(d4 + 3 * dstep, w1); }
+        }
       }
       if (tid == 0) CMLPL_TRACE(12);
       // A2 is rewritten by the next patch's conv1 epilogue: all residual reads must be done
@@ -387,7 +475,7 @@ static int launch_patch_cnn(const void* f0pad, int cols, int w, int band_rows, c
   using Cfg = PatchCfg<20>;
   const PackedLayout L = packed_layout(1, 1, w);   // conv offsets do not depend on B, C
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  auto kern = trace ? patch_cnn_kernel<20, true> : patch_cnn_kernel<20, false>;
+  auto kern = trace ? patch_cnn_kernel<20, true, false> : patch_cnn_kernel<20, false, false>;
   CMLPL_MAX_DYN_SMEM(kern, Cfg::SMEM);
   const int64_t npix = int64_t(band_rows) * cols;
   int64_t grid = grid_override > 0 ? grid_override : sm_count();
@@ -395,10 +483,23 @@ static int launch_patch_cnn(const void* f0pad, int cols, int w, int band_rows, c
   kern<<<int(grid), kThreads, Cfg::SMEM, stream>>>(
       static_cast<const __half*>(f0pad), cols, band_rows, pk + L.w1, pk + L.w2,
       reinterpret_cast<const float*>(pk + L.b1), reinterpret_cast<const float*>(pk + L.b2),
-      static_cast<__half*>(p2), p2_tiled, trace);
+      static_cast<__half*>(p2), p2_tiled, trace, TrainCnnArgs{});
   CMLPL_CHECK_LAUNCH("patch_cnn");
   return CMLPL_OK;
 }
+
+namespace cmlpl {
+int launch_train_cnn(const TrainCnnArgs& ta, cudaStream_t st) {
+  using Cfg = PatchCfg<20>;
+  auto kern = patch_cnn_kernel<20, false, true>;
+  CMLPL_MAX_DYN_SMEM(kern, Cfg::SMEM);
+  int grid = sm_count() & ~1;                       // split evenly between the two nets
+  if (grid > 2 * ta.nb) grid = 2 * ta.nb;
+  kern<<<grid, kThreads, Cfg::SMEM, st>>>(nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, ta);
+  CMLPL_CHECK_LAUNCH("train_cnn");
+  return CMLPL_OK;
+}
+}  // namespace cmlpl
 
 extern "C" int cmlpl_patch_cnn_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
                                    cmlpl_stream_t stream) {

@@ -108,7 +108,6 @@ class FusedAdam(torch.optim.Optimizer):
                 ops.adam_multi(ps, gs, ms, vs, group["lr"], *group["betas"], group["eps"], step)
         # the kernel writes through raw pointers: bump the version counters ourselves so that everything keyed on
         # them (BaseNet2.packed_weights' cache, autograd's saved-tensor checks) sees the update
-        for group in self.param_groups:
-            for p in group["params"]:
-                if p.grad is not None:
-                    torch._C._increment_version(p)
+        touched = [p for group in self.param_groups for p in group["params"] if p.grad is not None]
+        if touched:
+            torch._C._increment_version(touched)        # takes an iterable of tensors

@@ -305,6 +305,76 @@ int cmlpl_adam_multi_f32(int n_tensors, float* const* p_host, const float* const
                          float lr, float beta1, float beta2, float eps, int step,
                          cmlpl_stream_t stream);
 
+
+/* ------------------------------------------------------- fused training step --
+ * One mutual-learning step of train.py:150-272 for BOTH BaseNet2 peers as ~17 kernel launches on `stream`
+ * (CUDA-graph capturable: every per-step scalar lives in the device-side cmlpl_train_params block).
+ * Contractions run on tcgen05 (fp16 operands = TF32's 11-bit significand, fp32 accumulate in TMEM): conv0 / conv1 /
+ * conv2 forward (tools/models.py:132-140), their data gradients and weight gradients (train.py:267,271); gradient
+ * operands are scaled by a power of two chosen on device from max|dL/dcat| so they sit in fp16's normal range.
+ * Bar: |d| <= 1e-3 * max|ref| against the fp32 path (cmlpl_conv2d_f32 & co. stay the 1e-5 reference).
+ *
+ * Row order inside a net: [bs labelled ; btu unlabelled] (train.py:174,184); nb = bs + btu.
+ * Tensor index order in cmlpl_train_net arrays: 0 conv0.weight [64,60,1,1], 1 conv0.bias, 2 conv1.weight
+ * [64,64,3,3], 3 conv1.bias, 4 conv2.weight, 5 conv2.bias, 6 feat_spe.weight [1024,B], 7 feat_spe.bias,
+ * 8 classifier.weight [C,2624], 9 classifier.bias (state-dict layouts, tools/models.py:102-127).
+ */
+#define CMLPL_TRAIN_TENSORS 10
+typedef struct cmlpl_train_net {
+  float* p[CMLPL_TRAIN_TENSORS];   /* parameters, updated in place by the Adam phase */
+  float* g[CMLPL_TRAIN_TENSORS];   /* gradients of total_loss (train.py:266/270), overwritten every step */
+  float* m[CMLPL_TRAIN_TENSORS];   /* Adam exp_avg */
+  float* v[CMLPL_TRAIN_TENSORS];   /* Adam exp_avg_sq */
+  float* queue_feats;              /* f32 [queue, 1024]  memory bank this net's targets are smoothed with (train.py:138-145) */
+  float* queue_probs;              /* f32 [queue, C] */
+} cmlpl_train_net;
+
+typedef struct cmlpl_train_params {   /* lives in DEVICE memory; the host refreshes it before every step */
+  float noise_scale;      /* train.py:157 args.noise (ignored for inputs passed with cube == NULL) */
+  float dropout_p;        /* tools/models.py:147; used only when drop_mask == NULL */
+  float temperature;      /* train.py:213,246 */
+  float alpha;            /* train.py:215 */
+  float adap_thr;         /* args.thr * exp(-0.5 (epoch/num_epochs)^2), train.py:147-148,221 */
+  float lr, beta1, beta2, eps, bc1, bc2_sqrt;   /* Adam: bias corrections 1-beta1^t, sqrt(1-beta2^t) */
+  int smooth;             /* epoch > 0 or batch_index > queue_batch, train.py:212 */
+  int queue_ptr[2];       /* write positions of the two banks for THIS step (train.py:232-237, host keeps the quirk) */
+  unsigned long long seed, offset;   /* device Philox stream for noise / dropout when no tensors are injected */
+  float grad_amax;        /* scratch: max |dL/dcat[:, :1600]| of this step (written by the head backward) */
+  int pad_;
+} cmlpl_train_params;
+
+typedef struct cmlpl_train_io {
+  int bs, btu, bands, classes, w, queue;      /* w must be 20, classes <= 16, bands <= 256 */
+  /* ---- inputs */
+  const float* cube; int scene_rows, cols;    /* f32 [R, cols, 60] PCA cube, or NULL: patch_noise then HOLDS the input patches */
+  const int64_t* pix;                         /* i64 [nb] raster pixel per row (both nets read the same pixels) */
+  const float* patch_noise;                   /* f32 [2, nb, 60, w, w] N(0,1) draws (train.py:157-182) or NULL -> Philox */
+  const float* spectra;                       /* f32 [rows, B] z-scored spectra */
+  const int64_t* spec_row;                    /* i64 [nb] row of `spectra` per sample; NULL: row pix[i] (cube mode) or the
+                                                 assembled inputs f32 [2, nb, B] themselves (cube == NULL) */
+  const float* spec_noise;                    /* f32 [2, nb, B] or NULL -> Philox (none when cube == NULL) */
+  const float* drop_mask;                     /* f32 [2, nb, 2624] inverted-dropout mask (0 or 1/(1-p)) or NULL -> Philox */
+  const int64_t* labels;                      /* i64 [bs] 0-based (train.py:159) */
+  cmlpl_train_net net[2];
+  cmlpl_train_params* params;                 /* device */
+  /* ---- outputs (all device) */
+  float* logits;      /* f32 [2, nb, C] */
+  float* feat;        /* f32 [2, nb, 1024] unit rows (models.py:145-146) */
+  float* probs;       /* f32 [2, btu, C]: [0] = probs (target of net 0, from net 1), [1] = probs1 (train.py:203-217) */
+  float* mask;        /* f32 [2, btu]:    [0] = mask, [1] = masks (train.py:222,228) */
+  float* hist;        /* f32 [12]: lc, total, cls, con, acc(net1 on labelled), total1, cls1, con1, lc1, 3 spare */
+  float* grad_flat; size_t grad_flat_bytes;   /* optional: one block holding every g[] tensor of both nets (cleared with ONE
+                                                 memset instead of one per tensor) */
+  void* work; size_t work_bytes;              /* cmlpl_train_workspace_bytes() */
+} cmlpl_train_io;
+
+size_t cmlpl_train_workspace_bytes(int bs, int btu, int bands, int classes, int queue);
+/* phases: bit 0 forward (gather+noise -> logits, feat), bit 1 losses (+ bank update, dlogits, dfeat),
+ * bit 2 backward (all gradients), bit 3 Adam.  15 = the whole step. */
+int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stream_t stream);
+/* number of kernel launches cmlpl_train_step(io, phases) enqueues (for bench.py's gpu_launches) */
+int cmlpl_train_step_launches(int phases);
+
 #ifdef __cplusplus
 }
 #endif
