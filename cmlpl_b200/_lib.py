@@ -68,6 +68,7 @@ SIGNATURES = {
     "cmlpl_ntxent_f32": (I, [P, L, I, F, P, P, P, P]),
     "cmlpl_adam_multi_f32": (I, [I, P, P, P, P, P, F, F, F, F, I, P]),
     "cmlpl_train_workspace_bytes": (Z, [I, I, I, I, I]),
+    "cmlpl_train_workspace_layout": (I, [I, I, I, I, I, P]),
     "cmlpl_train_step": (I, [P, I, P]),
     "cmlpl_train_step_launches": (I, [I]),
 }

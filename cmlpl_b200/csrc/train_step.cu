@@ -23,6 +23,15 @@ extern "C" size_t cmlpl_train_workspace_bytes(int bs, int btu, int bands, int cl
   return train_ws_layout(bs, btu, bands, classes, queue).total;
 }
 
+extern "C" int cmlpl_train_workspace_layout(int bs, int btu, int bands, int classes, int queue, size_t* offsets) {
+  CMLPL_CHECK_ARG(offsets && bs > 0 && btu > 0 && bands > 0 && classes > 0 && queue > 0, "train_workspace_layout: bad args");
+  const TrainWs L = train_ws_layout(bs, btu, bands, classes, queue);
+  const size_t v[20] = {L.x16, L.a0, L.p1, L.m1, L.m2, L.cat, L.dmask, L.ynoisy, L.norm, L.dlogits,
+                        L.dfeat, L.dcat, L.dhp, L.dz1, L.da0, L.S, L.G, L.dG, L.probs_orig, L.total};
+  for (int i = 0; i < 20; ++i) offsets[i] = v[i];
+  return CMLPL_OK;
+}
+
 extern "C" int cmlpl_train_step_launches(int phases) {
   return ((phases & 1) ? 4 : 0) + ((phases & 2) ? 4 : 0) + ((phases & 4) ? 6 : 0) + ((phases & 8) ? 1 : 0);
 }

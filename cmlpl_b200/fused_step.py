@@ -96,11 +96,12 @@ class FusedMutualStep:
                 o += pad(n)
         self.queue_feats = [z(self.queue, 1024), z(self.queue, 1024)]
         self.queue_probs = [z(self.queue, self.C), z(self.queue, self.C)]
-        self.logits = z(2, self.nb, self.C)
-        self.feat = z(2, self.nb, 1024)
-        self.probs = z(2, btu, self.C)
-        self.mask = z(2, btu)
+        # outputs are allocated for the constructor's (largest) batch; a smaller last batch (train.py's DataLoader keeps
+        # the partial batch) uses the head of the same buffers -- self.logits / feat / probs / mask are per-step views
+        self._logits, self._feat = z(2 * self.nb * self.C), z(2 * self.nb * 1024)
+        self._probs, self._mask = z(2 * btu * self.C), z(2 * btu)
         self.hist = z(12)
+        self._views(bs, btu)
         lib = _lib.load()
         self.work = torch.zeros((lib.cmlpl_train_workspace_bytes(bs, btu, self.B, self.C, self.queue),),
                                 dtype=torch.uint8, device=dev)
@@ -111,14 +112,21 @@ class FusedMutualStep:
         self.pix = torch.zeros((self.nb,), dtype=torch.int64, device=dev)
         self.labels = torch.zeros((bs,), dtype=torch.int64, device=dev)
         self.use_graph = use_graph
-        self._graph = None
-        self._graph_key = None
+        self._graphs = {}
         self._keep = None
 
     # ------------------------------------------------------------------ plumbing
+    def _views(self, bs, btu):
+        nb = bs + btu
+        self.cur = (bs, btu)
+        self.logits = self._logits[:2 * nb * self.C].view(2, nb, self.C)
+        self.feat = self._feat[:2 * nb * 1024].view(2, nb, 1024)
+        self.probs = self._probs[:2 * btu * self.C].view(2, btu, self.C)
+        self.mask = self._mask[:2 * btu].view(2, btu)
+
     def _io(self, cube, patches, spectra, spec_row, patch_noise, spec_noise, drop_mask):
         io = TrainIO()
-        io.bs, io.btu, io.bands, io.classes, io.w, io.queue = self.bs, self.btu, self.B, self.C, 20, self.queue
+        io.bs, io.btu, io.bands, io.classes, io.w, io.queue = self.cur[0], self.cur[1], self.B, self.C, 20, self.queue
         if cube is not None:
             io.cube, io.scene_rows, io.cols = cube.data_ptr(), cube.shape[0], cube.shape[1]
             io.pix = self.pix.data_ptr()
@@ -147,6 +155,7 @@ class FusedMutualStep:
 
     def _set_params(self, epoch, batch_index, phases):
         p = self.prm
+        nb = self.cur[0] + self.cur[1]
         p.noise_scale, p.dropout_p, p.temperature, p.alpha = self.noise, self.dropout, self.T, self.alpha
         p.adap_thr = self.thr * math.exp(-0.5 * ((epoch / self.num_epochs) ** 2))          # train.py:147-148,221
         p.smooth = 1 if (epoch > 0 or batch_index > self.queue_batch) else 0                # train.py:212
@@ -156,10 +165,10 @@ class FusedMutualStep:
         p.bc1 = 1.0 - self.betas[0] ** step
         p.bc2_sqrt = math.sqrt(1.0 - self.betas[1] ** step)
         p.seed, p.offset = self.seed, self.offset
-        if self.queue_ptr + self.nb > self.queue or self.queue_ptr1 + self.nb > self.queue:
+        if self.queue_ptr + nb > self.queue or self.queue_ptr1 + nb > self.queue:
             # train.py:232 would raise on the shape mismatch of the slice assignment
             raise RuntimeError("memory-bank write [%d, %d) exceeds the queue of %d rows (train.py:232-237)"
-                               % (max(self.queue_ptr, self.queue_ptr1), max(self.queue_ptr, self.queue_ptr1) + self.nb, self.queue))
+                               % (max(self.queue_ptr, self.queue_ptr1), max(self.queue_ptr, self.queue_ptr1) + nb, self.queue))
         self.prm_dev.copy_(self.prm_host, non_blocking=True)
         if phases & 2:
             self.queue_ptr = (self.queue_ptr + 256) % self.queue                            # train.py:234 (literal 256)
@@ -167,6 +176,20 @@ class FusedMutualStep:
         if phases & 8:
             self.adam_step = step
         self.offset += 1
+
+    WS_FIELDS = ("x16", "a0", "p1", "m1", "m2", "cat", "dmask", "ynoisy", "norm", "dlogits", "dfeat", "dcat", "dhp",
+                 "dz1", "da0", "S", "G", "dG", "probs_orig", "total")
+
+    def workspace_layout(self):
+        """{region: byte offset into self.work} (cmlpl_train_workspace_layout; tests and profiling)."""
+        off = (c_size_t * 20)()
+        _lib.call("cmlpl_train_workspace_layout", self.bs, self.btu, self.B, self.C, self.queue, off)
+        return dict(zip(self.WS_FIELDS, [int(v) for v in off]))
+
+    def grad_scale(self):
+        """The power-of-two scale the last backward pass applied to dz1 / da0 (reads the device params: syncs)."""
+        prm = TrainParams.from_buffer_copy(bytes(self.prm_dev.cpu().numpy()))
+        return 2.0 ** (12 - math.frexp(prm.grad_amax)[1]) if prm.grad_amax > 0 else 1.0
 
     @staticmethod
     def launches(phases=15):
@@ -186,43 +209,48 @@ class FusedMutualStep:
                                       f"{None if t is None else tuple(t.shape)}")
         if (cube is None) == (patches is None):
             raise _lib.CmlplError("pass either cube+pix or assembled patches")
+        bs = int(labels.numel())
+        nb = int(pix.numel()) if cube is not None and pix is not None else (int(patches.shape[1]) if patches is not None else 0)
+        if not (0 < bs <= self.bs and bs < nb and nb - bs <= self.btu):
+            raise _lib.CmlplError(f"batch of {bs} labelled + {nb - bs} unlabelled rows does not fit the step built for "
+                                  f"{self.bs} + {self.btu}")
+        if (bs, nb - bs) != self.cur:
+            self._views(bs, nb - bs)
         if cube is not None:
-            chk(pix, (self.nb,), "pix")
+            chk(pix, (nb,), "pix")
             if cube.dim() != 3 or cube.shape[2] != 60 or cube.dtype != torch.float32 or not cube.is_contiguous():
                 raise _lib.CmlplError("cube must be contiguous f32 [R, C, 60]")
             if spectra is None or spectra.dim() != 2 or spectra.shape[1] != self.B or spectra.dtype != torch.float32:
                 raise _lib.CmlplError("spectra must be f32 [rows, B]")
-            self.pix.copy_(pix, non_blocking=True)
+            self.pix[:nb].copy_(pix, non_blocking=True)
             if patch_noise is not None:
-                chk(patch_noise, (2, self.nb, 60, 20, 20), "patch_noise")
+                chk(patch_noise, (2, nb, 60, 20, 20), "patch_noise")
             if spec_noise is not None:
-                chk(spec_noise, (2, self.nb, self.B), "spec_noise")
+                chk(spec_noise, (2, nb, self.B), "spec_noise")
         else:
-            chk(patches, (2, self.nb, 60, 20, 20), "patches")
-            chk(spectra, (2, self.nb, self.B), "spectra")
-        chk(labels, (self.bs,), "labels")
-        self.labels.copy_(labels, non_blocking=True)
+            chk(patches, (2, nb, 60, 20, 20), "patches")
+            chk(spectra, (2, nb, self.B), "spectra")
+        chk(labels, (bs,), "labels")
+        self.labels[:bs].copy_(labels, non_blocking=True)
         dm = None
         if drop_masks is not None:
             dm = drop_masks if isinstance(drop_masks, torch.Tensor) else torch.stack(list(drop_masks))
-            chk(dm, (2, self.nb, CAT), "drop_masks")
+            chk(dm, (2, nb, CAT), "drop_masks")
         self._set_params(epoch, batch_index, phases)
         stream = torch.cuda.current_stream().cuda_stream
-        key = (phases, _ptr(cube), _ptr(patches), _ptr(spectra), _ptr(spec_row), _ptr(patch_noise), _ptr(spec_noise), _ptr(dm))
+        key = (phases, bs, nb, _ptr(cube), _ptr(patches), _ptr(spectra), _ptr(spec_row), _ptr(patch_noise), _ptr(spec_noise), _ptr(dm))
         if self.use_graph:
-            if self._graph is None or self._graph_key != key:
+            if key not in self._graphs:
                 io = self._io(cube, patches, spectra, spec_row, patch_noise, spec_noise, dm)
-                _lib.call("cmlpl_train_step", ctypes.byref(io), phases, c_void_p(stream))     # warm-up: func attributes
+                _lib.call("cmlpl_train_step", ctypes.byref(io), phases, c_void_p(stream))     # this step, eagerly
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g):                                                     # capture only (nothing runs)
                     _lib.call("cmlpl_train_step", ctypes.byref(io), phases,
                               c_void_p(torch.cuda.current_stream().cuda_stream))
-                # the warm-up call already advanced the state by one real step; the graph is replayed from now on
-                self._graph, self._graph_key = g, key
-                self._keep = (cube, patches, spectra, spec_row, patch_noise, spec_noise, dm)
+                self._graphs[key] = (g, (cube, patches, spectra, spec_row, patch_noise, spec_noise, dm))
             else:
-                self._graph.replay()
+                self._graphs[key][0].replay()
         else:
             io = self._io(cube, patches, spectra, spec_row, patch_noise, spec_noise, dm)
             _lib.call("cmlpl_train_step", ctypes.byref(io), phases, c_void_p(stream))

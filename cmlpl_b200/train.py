@@ -10,6 +10,9 @@ update that reads ``queue_ptr`` (train.py:234,237), zero-initialised bank rows e
 denominator, thr=1 masking everything in epoch 0.
 Differences (documented, opt-in free): batches are gathered on the GPU from the PCA cube instead of
 a DataLoader over XP.npy; noise / dropout use the device generator; no SVG / CSV reporting.
+By default the step runs as ONE ``cmlpl_train_step`` call (cmlpl_b200/fused_step.py: tcgen05 convolutions in fp16
+operands / fp32 accumulation, 15 launches in a CUDA graph); ``--fp32_step`` selects ``mutual_step`` below, the fp32
+path that meets the reference's 1e-5 bar.
 """
 from __future__ import annotations
 
@@ -151,12 +154,36 @@ def main(args):
     lb, ub = args.labeled_batch_size, args.unlabeled_batch_size
     num_batches = min(math.ceil(len(labeled) / lb), math.ceil(len(unlabeled) / ub))                 # :134
     hist_dev = []
+    fused = None
+    if not getattr(args, "fp32_step", False) and labeled.scene_ready and labeled.w == 20:
+        # default: the whole step is cmlpl_train_step (gather + Philox noise inside the first kernel, tcgen05
+        # convolutions, 15 launches replayed from a CUDA graph); --fp32_step keeps the fp32 reference path below
+        from .fused_step import FusedMutualStep
+        fused = FusedMutualStep(st.Base, st.Base1, bs=lb, btu=ub, lr=args.lr, temperature=args.temperature,
+                                alpha=args.alpha, thr=args.thr, num_epochs=args.num_epochs, queue_batch=args.queue_batch,
+                                noise=args.noise, dropout=args.dropout, seed=1088, use_graph=True)
+        st.extras["fused"] = fused
+        cube = whole.cube_device()
+        spectra_all = torch.from_numpy(whole.X.astype(np.float32)).to(device)
+        pix_l = torch.from_numpy(labeled.index).to(device)
+        pix_u = torch.from_numpy(unlabeled.index).to(device)
+        y_all = torch.from_numpy(Yall).to(device)
     for epoch in range(args.num_epochs):
         perm_l = torch.randperm(len(labeled), device=device)
         perm_u = torch.randperm(len(unlabeled), device=device)
         for batch_index in range(num_batches):
             pl = perm_l[batch_index * lb:(batch_index + 1) * lb]
             pu = perm_u[batch_index * ub:(batch_index + 1) * ub]
+            if fused is not None:
+                pl_pix = pix_l[pl]
+                hist = fused.step(y_all[pl_pix], epoch, batch_index, cube=cube, pix=torch.cat([pl_pix, pix_u[pu]]),
+                                  spectra=spectra_all)[:5].clone()
+                hist_dev.append(hist)
+                if (batch_index + 1) % args.print_per_batches == 0:
+                    m = torch.stack(hist_dev[-args.print_per_batches:]).mean(0).tolist()
+                    print('Epoch %d/%d:  %d/%d loss_contrast= %.2f total_loss = %.4f cls_loss = %.4f con_loss = %.4f acc = %.2f\n'
+                          % (epoch + 1, args.num_epochs, batch_index + 1, num_batches, m[0], m[1], m[2], m[3], m[4] * 100))
+                continue
             XP_l1, X_l1, Y_train = noisy_batch(labeled, pl, args.noise)          # :157-159
             XP_l2, X_l2, _ = noisy_batch(labeled, pl, args.noise)                # :163-164
             XP_u1, X_u1, _ = noisy_batch(unlabeled, pu, args.noise)              # :170-171
@@ -208,6 +235,8 @@ def build_parser():
     parser.add_argument('--noise', type=float, default=0.5)
     parser.add_argument('--m', type=int, default=5, help='number of stochastic augmentations')
     parser.add_argument('--root', type=str, default='./dataset/')
+    parser.add_argument('--fp32_step', action='store_true',
+                        help='run the step through the fp32 reference-precision kernels instead of cmlpl_train_step')
     return parser
 
 

@@ -369,6 +369,12 @@ typedef struct cmlpl_train_io {
 } cmlpl_train_io;
 
 size_t cmlpl_train_workspace_bytes(int bs, int btu, int bands, int classes, int queue);
+/* Byte offsets of the workspace regions (tests / profiling): offsets[20] = {x16, a0, p1, m1, m2, cat, dmask, ynoisy,
+ * norm, dlogits, dfeat, dcat, dhp, dz1, da0, S, G, dG, probs_orig, total}.  Per-sample activations x16 / a0 / dz1 / da0
+ * are f16 [2*nb][8 chunks][400][8], p1 f16 [2*nb][8][100][8]; m1 / m2 are ReLU masks u32 [2*nb][positions][2] (bit c%32
+ * of word c/32); cat / dmask / dcat f32 [2*nb][2624]; dz1 / da0 carry the power-of-two gradient scale
+ * 2^(12 - exponent(grad_amax)). */
+int cmlpl_train_workspace_layout(int bs, int btu, int bands, int classes, int queue, size_t* offsets);
 /* phases: bit 0 forward (gather+noise -> logits, feat), bit 1 losses (+ bank update, dlogits, dfeat),
  * bit 2 backward (all gradients), bit 3 Adam.  15 = the whole step. */
 int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stream_t stream);

@@ -215,7 +215,7 @@ def main():
     n = 200
     ev0.record()
     for it in range(n):
-        fs2._graph.replay()
+        list(fs2._graphs.values())[0][0].replay()
     ev1.record(); torch.cuda.synchronize()
     print("graph replay only: %.3f ms" % (ev0.elapsed_time(ev1) / n))
     fs3 = FS.FusedMutualStep(nets[0], nets[1], bs=bs, btu=bs, thr=0.15, num_epochs=20, use_graph=False)
