@@ -29,26 +29,31 @@ namespace cmlpl {
 
 template <int W>
 struct PatchCfg {
-  static_assert(W % 4 == 0, "two 2x2 pools need w % 4 == 0");
-  // ---- conv1 input: W x W, parity planes of (W/2+1) rows x (W+2) padded columns
+  // W = 20: the reference's window (tools/models.py:127 fixes 2624 classifier inputs).  Odd W (W = 11, BASELINE
+  // configs[4]) follows ExtractPatches_for_base (hyper_tools.py:300-317) and the floor semantics of avg_pool2d: the
+  // last row / column of an odd map feeds the convolution taps of its neighbours but no pooling window.
+  // Padded row widths are EVEN so that the two columns of a pooling window are lanes L and L^1 of a tile.
+  // ---- conv1 input: W x W, parity planes of (W/2+1) rows x PW1 padded columns
   static constexpr int H1 = W;
-  static constexpr int PW1 = W + 2;
+  static constexpr int NP1 = W / 2;                 // output row pairs (= pooled rows)
+  static constexpr int PW1 = (W + 3) & ~1;
   static constexpr int PR1 = W / 2 + 1;
   static constexpr int ENT1 = 1 + PR1 * PW1;        // +1 leading zero entry (x = -1 of row 0)
   static constexpr int CH1 = ENT1 * 16;             // bytes between 16-B K-chunks (= LBO)
   static constexpr int PLANE1 = 8 * CH1;
-  static constexpr int M1 = (W / 2) * PW1;          // outputs per parity
+  static constexpr int M1 = NP1 * PW1;              // outputs per parity
   static constexpr int NT1 = (M1 + 127) / 128;      // 128-row tiles per parity
   // ---- conv2 input: W/2 x W/2
   static constexpr int H2 = W / 2;
-  static constexpr int PW2 = H2 + 2;
+  static constexpr int NP2 = H2 / 2;
+  static constexpr int PW2 = (H2 + 3) & ~1;
   static constexpr int PR2 = H2 / 2 + 1;
   static constexpr int ENT2 = 1 + PR2 * PW2;
   static constexpr int CH2 = ENT2 * 16;
   static constexpr int PLANE2 = 8 * CH2;
-  static constexpr int M2 = (H2 / 2) * PW2;
+  static constexpr int M2 = NP2 * PW2;
   static_assert(M2 <= 128, "conv2 parity plane must fit one tile");
-  static constexpr int P = (W / 4) * (W / 4);       // pooled positions written per pixel
+  static constexpr int P = NP2 * NP2;               // pooled positions written per pixel
   // ---- TMEM columns (fp32 accumulators, 64 per tile)
   static constexpr int TM_C1 = 0;                   // (half h, parity q) -> (h*2+q)*64
   static constexpr int TM_C2 = NT1 * 2 * 64;        // parity q -> TM_C2 + q*64
@@ -172,19 +177,19 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
     // F0 is chunk-planar in HBM ([8 chunks][rows][cols][8 halves]).  64 threads = 8 chunks x 8 pixels per
     // step; 5 steps cover two window rows (40 pixels) and the pattern repeats for each of the W/2 row
     // pairs: global += 2 rows, both planes += one plane row.  Per-thread offsets are computed once.
-    static_assert(W % 2 == 0 && (2 * W) % 8 == 0, "row-pair pattern needs 2W divisible by 8");
-    constexpr int STEPS = 2 * W / 8;
+    constexpr bool kPairs = (W % 2 == 0) && ((2 * W) % 8 == 0);     // row-pair pattern (W = 20)
+    constexpr int STEPS = kPairs ? 2 * W / 8 : (W * W + 7) / 8;     // otherwise: the whole window, 8 pixels per step
     const int lt = tid - kEpiThreads;                        // 0..63
     const int lch = lt >> 3, lpx = lt & 7;
     int64_t goff[STEPS];                                     // halves, relative to the window origin of chunk 0
-    uint32_t soff[STEPS];                                    // smem byte address for row pair 0
+    uint32_t soff[STEPS];                                    // smem byte address (row pair 0 in the pair pattern)
 #pragma unroll
     for (int st = 0; st < STEPS; ++st) {
-      const int pix = st * 8 + lpx;                          // 0 .. 2W-1 within the row pair
-      const int y = pix / W, x = pix - y * W;                // y in {0,1}
+      const int pix = st * 8 + lpx;                          // 0 .. 2W-1 within the row pair, or 0 .. W*W-1
+      const int y = pix / W, x = pix - y * W;
       goff[st] = ((int64_t(lch) * plane_rows + y) * pitch + x) * 8;
-      // even plane: row g ; odd plane: row g+1  (g = row pair)
-      soff[st] = sbase + Cfg::S_A1 + y * Cfg::PLANE1 + lch * Cfg::CH1 + (1 + y * Cfg::PW1 + x) * 16;
+      // window row y -> plane y&1, plane row (y + (y&1)) / 2: even plane row g holds y = 2g, odd plane row g+1 holds 2g+1
+      soff[st] = sbase + Cfg::S_A1 + (y & 1) * Cfg::PLANE1 + lch * Cfg::CH1 + (1 + ((y + (y & 1)) >> 1) * Cfg::PW1 + x) * 16;
     }
     uint32_t ph = 0;
     for (int64_t p = p_begin; p < p_end; ++p, ph ^= 1) {
@@ -200,11 +205,17 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
       // shared with the epilogue's shared-memory traffic, and the load still hides under conv2
       if (p > p_begin) mbar_wait(bars + 8 * BAR_A2_FULL, ph ^ 1, 10);
       if (lt == 0) CMLPL_TRACE(0);
+      if constexpr (kPairs) {
 #pragma unroll
-      for (int g = 0; g < W / 2; ++g) {
+        for (int g = 0; g < W / 2; ++g) {
+#pragma unroll
+          for (int st = 0; st < STEPS; ++st)
+            cp_async16(soff[st] + g * Cfg::PW1 * 16, src + goff[st] + int64_t(2 * g) * pitch * 8);
+        }
+      } else {
 #pragma unroll
         for (int st = 0; st < STEPS; ++st)
-          cp_async16(soff[st] + g * Cfg::PW1 * 16, src + goff[st] + int64_t(2 * g) * pitch * 8);
+          if (st * 8 + lpx < W * W) cp_async16(soff[st], src + goff[st]);
       }
       cp_async_wait_all();
       fence_proxy_async();                                   // generic-proxy writes -> visible to the MMA
@@ -293,7 +304,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
       for (int h = 0; h < Cfg::NT1; ++h) {
         const int m = h * 128 + L;
         const int i = m / Cfg::PW1, x = m - i * Cfg::PW1;
-        const bool valid = (m < Cfg::M1) && (x < W);
+        const bool valid = (m < Cfg::M1) && (x < 2 * Cfg::NP1);
         const bool writer = valid && ((x & 1) == 0);
         // residual = conv0 output at the same position (models.py:133,135), rows 2i and 2i+1: read it
         // back from the A1 planes (same fp16 values the MMA consumes) before waiting for the
@@ -382,7 +393,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
       {
         const int m = L;
         const int i = m / Cfg::PW2, x = m - i * Cfg::PW2;
-        const bool valid = (m < Cfg::M2) && (x < Cfg::H2);
+        const bool valid = (m < Cfg::M2) && (x < 2 * Cfg::NP2);
         const bool writer = valid && ((x & 1) == 0);
         // residual = pooled conv1 output (models.py:137,139): rows 2i (even plane row i), 2i+1 (odd plane row i+1)
         uint4 re[4], ro[4];
@@ -399,7 +410,7 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
           }
         }
         // row-major [pixel][pos][64]  or  UMMA A-operand tiles [pixel/128][pos*8 + chunk][pixel%128][8]
-        const int pos = i * (Cfg::H2 / 2) + (x >> 1);
+        const int pos = i * Cfg::NP2 + (x >> 1);
         __half* dst = p2_tiled ? p2out + (((p >> 7) * (Cfg::P * 8) + pos * 8 + chalf * 4) * 128 + (p & 127)) * 8
                                : p2out + (p * Cfg::P + pos) * 64 + chalf * 32;
         const int dstep = p2_tiled ? 128 : 1;                  // uint4 stride between consecutive 8-channel chunks
@@ -468,22 +479,34 @@ using namespace cmlpl;
 static int launch_patch_cnn(const void* f0pad, int cols, int w, int band_rows, const void* packed, void* p2,
                             int p2_tiled, long long* trace, int grid_override, cudaStream_t stream) {
   CMLPL_CHECK_ARG(f0pad && packed && p2, "patch_cnn: null pointer");
-  CMLPL_CHECK_ARG(w == 20, "patch_cnn: w=%d unsupported (BaseNet2's classifier fixes w=20, tools/models.py:127)", w);
+  CMLPL_CHECK_ARG(w == 20 || w == 11, "patch_cnn: w=%d unsupported (20 = the reference's BaseNet2, tools/models.py:127; "
+                  "11 = the odd-window variant of BASELINE configs[4])", w);
   CMLPL_CHECK_ARG(cols > 0 && band_rows > 0, "patch_cnn: bad dims");
   CMLPL_CHECK_ARG(reinterpret_cast<uintptr_t>(f0pad) % 16 == 0 && reinterpret_cast<uintptr_t>(p2) % 16 == 0 &&
                       reinterpret_cast<uintptr_t>(packed) % 16 == 0, "patch_cnn: buffers must be 16-byte aligned");
-  using Cfg = PatchCfg<20>;
   const PackedLayout L = packed_layout(1, 1, w);   // conv offsets do not depend on B, C
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  auto kern = trace ? patch_cnn_kernel<20, true, false> : patch_cnn_kernel<20, false, false>;
-  CMLPL_MAX_DYN_SMEM(kern, Cfg::SMEM);
   const int64_t npix = int64_t(band_rows) * cols;
   int64_t grid = grid_override > 0 ? grid_override : sm_count();
   if (grid > npix) grid = npix;
-  kern<<<int(grid), kThreads, Cfg::SMEM, stream>>>(
-      static_cast<const __half*>(f0pad), cols, band_rows, pk + L.w1, pk + L.w2,
-      reinterpret_cast<const float*>(pk + L.b1), reinterpret_cast<const float*>(pk + L.b2),
-      static_cast<__half*>(p2), p2_tiled, trace, TrainCnnArgs{});
+  if (w == 11) {
+    CMLPL_CHECK_ARG(!trace, "patch_cnn: the trace build exists for w=20 only");
+    using Cfg = PatchCfg<11>;
+    auto kern = patch_cnn_kernel<11, false, false>;
+    CMLPL_MAX_DYN_SMEM(kern, Cfg::SMEM);
+    kern<<<int(grid), kThreads, Cfg::SMEM, stream>>>(
+        static_cast<const __half*>(f0pad), cols, band_rows, pk + L.w1, pk + L.w2,
+        reinterpret_cast<const float*>(pk + L.b1), reinterpret_cast<const float*>(pk + L.b2),
+        static_cast<__half*>(p2), p2_tiled, trace, TrainCnnArgs{});
+  } else {
+    using Cfg = PatchCfg<20>;
+    auto kern = trace ? patch_cnn_kernel<20, true, false> : patch_cnn_kernel<20, false, false>;
+    CMLPL_MAX_DYN_SMEM(kern, Cfg::SMEM);
+    kern<<<int(grid), kThreads, Cfg::SMEM, stream>>>(
+        static_cast<const __half*>(f0pad), cols, band_rows, pk + L.w1, pk + L.w2,
+        reinterpret_cast<const float*>(pk + L.b1), reinterpret_cast<const float*>(pk + L.b2),
+        static_cast<__half*>(p2), p2_tiled, trace, TrainCnnArgs{});
+  }
   CMLPL_CHECK_LAUNCH("patch_cnn");
   return CMLPL_OK;
 }

@@ -129,7 +129,8 @@ static int launch_conv0(const T* in, int K, int scene_rows, int cols, int slab_r
 // one warp per pixel; lanes stride over the K = P*64 pooled features in 8-half chunks.
 template <int CMAX>
 __global__ void __launch_bounds__(256)
-classify_kernel(const __half* __restrict__ p2, const float* __restrict__ spe, int64_t n, int K, int C,
+classify_kernel(const __half* __restrict__ p2, const float* __restrict__ spe, const float* __restrict__ part,
+                int64_t part_stride, int64_t n, int K, int C,
                 const float* __restrict__ wc, const float* __restrict__ bc,
                 uint8_t* __restrict__ labels, float* __restrict__ logits) {
   const int lane = threadIdx.x & 31;
@@ -166,6 +167,9 @@ classify_kernel(const __half* __restrict__ p2, const float* __restrict__ spe, in
       if (c < C) {
         float v = warp_sum(acc[c]);
         v += (spe ? spe[p * C + c] : 0.f) + bc[c];
+        if (part)      // spectral_logits_kernel: four hidden-quarter partials f32 [4][part_stride][16]
+          v += (part[p * 16 + c] + part[(part_stride + p) * 16 + c]) +
+               (part[(2 * part_stride + p) * 16 + c] + part[(3 * part_stride + p) * 16 + c]);
         if (logits && lane == 0) logits[p * C + c] = v;
         if (v > best) { best = v; arg = c; }   // strict '>' : first index wins ties
       }
@@ -190,7 +194,7 @@ static bool use_tc_head(int B, int C) { return C <= 16 && ((B + 15) / 16) * 2 <=
 struct SceneWs {
   size_t f0pad, p2, spe, hidden, x16, h16, g, pm, yq, lmap, total;
   int64_t chunk;
-  bool tc;
+  bool tc, dense;
 };
 // tensor-core path (<= 16 classes, <= 224 bands): conv0 map, spectral tiles, conv1 variants (fp32 scratch), pooled
 // parity planes, the 25 conv2 variants, the 25 class-partial maps.  CUDA-core path: conv0 map, per-pixel pooled
@@ -201,6 +205,7 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   const int64_t mtiles = (n + 127) / 128;
   const int P = ((w / 2) / 2) * ((w / 2) / 2);
   s.tc = use_tc_head(B, C);
+  s.dense = s.tc && w == 20;                               // the exact-compute-sharing kernels are specialised to w = 20
   size_t o = 0;
   s.f0pad = o; o = align256(o + size_t(band_rows + w - 1) * (cols + w - 1) * 64 * 2);
   s.p2 = s.spe = s.hidden = s.x16 = s.h16 = s.g = s.pm = s.yq = s.lmap = 0;
@@ -208,15 +213,19 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   if (s.tc) {
     s.x16 = o; o = align256(o + size_t(mtiles) * (((B + 15) / 16) * 2) * 2048);
     s.h16 = o; o = align256(o + size_t(4) * mtiles * 128 * 64);   // partial spectral logits f32 [4 quarters][mtiles*128][16]
+  }
+  if (s.dense) {
     const size_t qpos = size_t(4) * ((band_rows + w) / 2) * ((cols + w) / 2);     // positions of the 4 parity planes
     s.g = o;                                               // (fp32 conv1 variants: not materialised any more)
     s.pm = o; o = align256(o + qpos * 9 * 64 * 2);         // pooled variants, f16 parity planes [9][4][8][PR2][PC2][8]
     s.yq = o; o = align256(o + qpos * 25 * 64 * 2);        // conv2 variants, f16 [25][4][8][PR2][PC2][8]
     s.lmap = o; o = align256(o + qpos * 25 * 16 * 4);      // class partials, f32 [4][25][4][PR2][PC2][4]
   } else {
-    s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);
-    s.spe = o; o = align256(o + size_t(n) * C * 4);
-    s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);
+    s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);     // per-pixel pooled conv features (patch_cnn_sm100.cu)
+    if (!s.tc) {
+      s.spe = o; o = align256(o + size_t(n) * C * 4);
+      s.hidden = o; o = align256(o + size_t(s.chunk) * 1024 * 4);
+    }
   }
   s.total = o;
   return s;
@@ -236,7 +245,7 @@ extern "C" int cmlpl_scene_workspace_layout(int band_rows, int cols, int num_fea
   CMLPL_CHECK_ARG(offsets && band_rows > 0 && cols > 0 && num_classes > 0 && num_features > 0 && w >= 4,
                   "scene_workspace_layout: bad args");
   const SceneWs s = scene_ws(band_rows, cols, num_features, num_classes, w);
-  const size_t v[12] = {s.f0pad, s.x16, s.h16, s.g, s.pm, s.yq, s.lmap, s.p2, s.spe, s.hidden, s.total, size_t(s.tc)};
+  const size_t v[12] = {s.f0pad, s.x16, s.h16, s.g, s.pm, s.yq, s.lmap, s.p2, s.spe, s.hidden, s.total, size_t(s.dense)};
   for (int i = 0; i < 12; ++i) offsets[i] = v[i];
   return CMLPL_OK;
 }
@@ -308,9 +317,9 @@ extern "C" int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_
   return CMLPL_OK;
 }
 
-extern "C" int cmlpl_classify_f16(const void* p2, const float* spe_logits, int64_t n, int num_features,
-                                  int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
-                                  cmlpl_stream_t stream) {
+static int classify_launch(const void* p2, const float* spe_logits, const float* part, int64_t part_stride, int64_t n,
+                           int num_features, int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
+                           cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(p2 && packed && labels, "classify: null pointer");
   CMLPL_CHECK_ARG(n >= 0 && num_classes > 0 && num_classes <= 32 && w >= 4, "classify: bad dims (C=%d w=%d)",
                   num_classes, w);
@@ -325,11 +334,19 @@ extern "C" int cmlpl_classify_f16(const void* p2, const float* spe_logits, int64
   if (grid > cap) grid = cap;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (num_classes <= 16)
-    classify_kernel<16><<<int(grid), 256, 0, s>>>(static_cast<const __half*>(p2), spe_logits, n, K, num_classes, wc, bc, labels, logits);
+    classify_kernel<16><<<int(grid), 256, 0, s>>>(static_cast<const __half*>(p2), spe_logits, part, part_stride, n, K,
+                                                  num_classes, wc, bc, labels, logits);
   else
-    classify_kernel<32><<<int(grid), 256, 0, s>>>(static_cast<const __half*>(p2), spe_logits, n, K, num_classes, wc, bc, labels, logits);
+    classify_kernel<32><<<int(grid), 256, 0, s>>>(static_cast<const __half*>(p2), spe_logits, part, part_stride, n, K,
+                                                  num_classes, wc, bc, labels, logits);
   CMLPL_CHECK_LAUNCH("classify");
   return CMLPL_OK;
+}
+
+extern "C" int cmlpl_classify_f16(const void* p2, const float* spe_logits, int64_t n, int num_features,
+                                  int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
+                                  cmlpl_stream_t stream) {
+  return classify_launch(p2, spe_logits, nullptr, 0, n, num_features, num_classes, w, packed, labels, logits, stream);
 }
 
 extern "C" int cmlpl_argmax_u8(const float* logits, int64_t n, int num_classes, uint8_t* labels, cmlpl_stream_t stream) {
@@ -348,8 +365,10 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
                                  int band_rows, const void* packed, void* workspace, size_t workspace_bytes,
                                  uint8_t* labels, float* logits, cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(cube && spectra && packed && workspace && labels, "scene_infer: null pointer");
-  CMLPL_CHECK_ARG(w == 20, "scene_infer: w=%d unsupported (the reference classifier is hard-wired to 2624 inputs, "
-                  "tools/models.py:127, i.e. w=20)", w);
+  // w = 20: the reference's BaseNet2 (classifier hard-wired to 2624 inputs, tools/models.py:127).  w = 11: the odd-window
+  // variant BASELINE configs[4] names (ExtractPatches_for_base windows, hyper_tools.py:300-317; pooled 5 -> 2, classifier
+  // over 64*2*2 + 1024 = 1280 inputs) -- a documented extension, evaluated per pixel by patch_cnn_kernel<11>.
+  CMLPL_CHECK_ARG(w == 20 || w == 11, "scene_infer: w=%d unsupported (20, or 11 for the odd-window variant)", w);
   CMLPL_CHECK_ARG(band_rows > 0 && cols > 0 && num_classes > 0 && num_classes <= 32, "scene_infer: bad dims");
   const SceneWs ws = scene_ws(band_rows, cols, num_features, num_classes, w);
   CMLPL_CHECK_ARG(workspace_bytes >= ws.total, "scene_infer: workspace %zu < required %zu", workspace_bytes, ws.total);
@@ -363,7 +382,11 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
     rc = cmlpl_spectral_logits_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16,
                                   reinterpret_cast<float*>(wsb + ws.h16), stream);
     if (rc != CMLPL_OK) return rc;
-    return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
+    if (ws.dense) return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
+    rc = cmlpl_patch_cnn_f16(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.p2, stream);
+    if (rc != CMLPL_OK) return rc;
+    return classify_launch(wsb + ws.p2, nullptr, reinterpret_cast<const float*>(wsb + ws.h16), ((n + 127) / 128) * 128, n,
+                           num_features, num_classes, w, packed, labels, logits, stream);
   }
   rc = cmlpl_spectral_head_f32(spectra, n, num_features, num_classes, w, packed,
                                reinterpret_cast<float*>(wsb + ws.hidden), ws.chunk,

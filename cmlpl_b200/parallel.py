@@ -35,17 +35,35 @@ def slab_of(r0: int, r1: int, scene_rows: int, w: int):
     return lo_v, hi_v + 1
 
 
+class LabelGather:
+    """Preallocated buffers of ``gather_label_map`` for a fixed (scene_rows, cols, world): nothing is allocated
+    inside a timed step (the per-call ``zeros`` + ``empty`` showed up in the N = 8 step)."""
+
+    def __init__(self, scene_rows: int, cols: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.n = scene_rows * cols
+        self.per = -(-scene_rows // self.world) * cols
+        self.pad = torch.zeros(self.per, dtype=torch.uint8, device=device)
+        self.out = torch.empty(self.world * self.per, dtype=torch.uint8, device=device)
+
+    def __call__(self, local_labels: torch.Tensor) -> torch.Tensor:
+        src = local_labels
+        if local_labels.numel() != self.per:                    # short / empty last band: pad to the common height
+            self.pad[: local_labels.numel()] = local_labels
+            src = self.pad
+        if self.out.is_cuda:
+            dist.all_gather_into_tensor(self.out, src, group=self.group)
+        else:
+            dist.all_gather(list(self.out.view(self.world, -1).unbind(0)), src, group=self.group)
+        return self.out[: self.n]
+
+
 def gather_label_map(local_labels: torch.Tensor, scene_rows: int, cols: int, group=None) -> torch.Tensor:
     """all-gather the per-band uint8 labels into the raster-ordered label map [scene_rows*cols].
-    Bands are padded to the common band height so one fixed-size all_gather suffices."""
-    world = dist.get_world_size(group)
-    per = -(-scene_rows // world)
-    buf = torch.zeros(per * cols, dtype=torch.uint8, device=local_labels.device)
-    buf[: local_labels.numel()] = local_labels
-    out = torch.empty(world * per * cols, dtype=torch.uint8, device=local_labels.device)
-    dist.all_gather_into_tensor(out, buf, group=group) if out.is_cuda else \
-        dist.all_gather(list(out.view(world, -1).unbind(0)), buf, group=group)
-    return out[: scene_rows * cols]
+    Bands are padded to the common band height so one fixed-size all_gather suffices.  (Allocates its buffers;
+    hot loops keep a ``LabelGather``.)"""
+    return LabelGather(scene_rows, cols, local_labels.device, group)(local_labels)
 
 
 def reduce_confusion(cm: torch.Tensor, group=None) -> torch.Tensor:

@@ -121,8 +121,13 @@ class _L2NormFn(torch.autograd.Function):
 
 
 class BaseNet2(nn.Module):
-    def __init__(self, num_features=103, dropout=0, num_classes=0):
+    def __init__(self, num_features=103, dropout=0, num_classes=0, w=20):
+        """Reference signature (models.py:98) plus ``w``: the reference hard-wires the classifier to 2624 inputs, i.e.
+        w = 20 (models.py:127).  ``w=11`` builds the odd-window variant BASELINE configs[4] names -- windows as in
+        ExtractPatches_for_base (hyper_tools.py:300-317), pooled 11 -> 5 -> 2, classifier over 64*2*2 + 1024 = 1280
+        inputs -- a documented extension; every other layer is unchanged."""
         super().__init__()
+        self.w = w
         # creation order == reference (models.py:102-127) so a given torch seed yields the same weights
         self.conv0 = nn.Conv2d(CONV_IN, CONV_CH, kernel_size=1, stride=1, bias=True)
         self.conv1 = nn.Conv2d(CONV_CH, CONV_CH, kernel_size=3, stride=1, padding=1, bias=True)
@@ -136,7 +141,7 @@ class BaseNet2(nn.Module):
         self.feat_ss = nn.Linear(N_FC1, 256)
         self.feat_ss2 = nn.Linear(N_FC1, 64)
         self.feat_ss3 = nn.Linear(256, 64)
-        self.classifier = nn.Linear(2624, num_classes)
+        self.classifier = nn.Linear(CONV_CH * ((w // 2) // 2) ** 2 + N_FC1, num_classes)
         self.l2norm = Normalize(2)
         self._packed = None   # (version key, packed weights) cache for scene inference
 

@@ -158,6 +158,40 @@ def synth_cube(R: int, C: int, B: int, K: int, seed: int = 1088, block: int = 8)
     return np.clip(cube, 0, 8000).astype(np.uint16), gt.astype(np.uint8)
 
 
+def synth_cube_hard(R: int, C: int, B: int, K: int, seed: int = 1088, spread: float = 50.0, sigma: float = 200.0,
+                    block: int = 8):
+    """A scene whose classes are NOT trivially separable (parity stress): every class prototype
+    is one common spectrum plus a small class offset (``spread`` DN per band) under the same sensor noise, so a
+    net trained on 5 labels per class lands well below 100 % and many pixels sit near a decision boundary."""
+    rng = np.random.default_rng(seed)
+    gb = rng.integers(0, K + 1, size=(-(-R // block), -(-C // block)))
+    gt = np.kron(gb, np.ones((block, block), dtype=np.int64))[:R, :C]
+    base = rng.uniform(1000, 3000, size=(1, B))
+    P = base + spread * rng.standard_normal((K + 1, B))
+    cube = P[gt] + rng.normal(0, sigma, size=(R, C, B))
+    return np.clip(cube, 0, 8000).astype(np.uint16), gt.astype(np.uint8)
+
+
+def preprocess_params(cube_u16: np.ndarray, n_PC: int = 60):
+    """The affine maps behind hyper_tools.py:285-292 as explicit float64 parameters:
+    spectra = (X - mu) / sigma;  cubePCA = ((X - mu) @ U - pca_mu) / pca_sigma."""
+    R, C, B = cube_u16.shape
+    X = cube_u16.reshape(R * C, B).astype(np.float64)
+    mu = X.mean(0)
+    Xc = X - mu
+    sigma = Xc.std(0)
+    U = np.linalg.svd(np.cov(Xc.T))[0][:, :n_PC]
+    proj = Xc @ U
+    return {"mu": mu, "sigma": sigma, "U": U, "pca_mu": proj.mean(0), "pca_sigma": (proj - proj.mean(0)).std(0)}
+
+
+def apply_preprocess(cube_u16: np.ndarray, pp: dict):
+    R, C, B = cube_u16.shape
+    Xc = cube_u16.reshape(R * C, B).astype(np.float64) - pp["mu"]
+    cube = ((Xc @ pp["U"]) - pp["pca_mu"]) / pp["pca_sigma"]
+    return cube.reshape(R, C, -1), Xc / pp["sigma"]
+
+
 def preprocess(cube_u16: np.ndarray, n_PC: int = 60):
     """hyper_tools.py:285-292: returns (cubePCA f64 [R,C,n_PC], spectra f64 [N,B])."""
     R, C, B = cube_u16.shape

@@ -250,6 +250,113 @@ def gold_train(num_epochs=2, num_unlabel=512):
         os.chdir(cwd)
 
 
+def gold_hard(R=150, C=140, spread=50.0, sigma=200.0, num_epochs=3, num_unlabel=2048, write=True):
+    """A >= 20 k-pixel scene that the reference does NOT classify perfectly: run the unmodified
+    sample_generation.main + train.main on it and keep the trained weights, the reference's label map and the
+    preprocessing parameters.  The scene itself is regenerated from its seed by the tests."""
+    B, K = 103, 9
+    cube, gt = O.synth_cube_hard(R, C, B, K, seed=1088, spread=spread, sigma=sigma)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="cmlpl_gold_hard_")
+    os.makedirs(os.path.join(tmp, "dataset"))
+    sio.savemat(os.path.join(tmp, "dataset", "PaviaU.mat"), {"paviaU": cube})
+    sio.savemat(os.path.join(tmp, "dataset", "PaviaU_gt.mat"), {"paviaU_gt": gt})
+    os.chdir(tmp)
+    try:
+        import sample_generation as RS
+        RS.main(argparse.Namespace(dataID=1, num_label=5, w=20, n_PC=60))
+        d = os.path.join(tmp, "dataset", "PaviaU")
+        X = np.load(os.path.join(d, "X.npy"))
+        Y = np.load(os.path.join(d, "Y.npy"))
+        te = np.load(os.path.join(d, "test_array.npy"))
+        pp = O.preprocess_params(cube, 60)
+        Xp, Xs = O.apply_preprocess(cube, pp)
+        close(Xs, X, 1e-12, "explicit z-score vs the reference's X.npy")
+        XPr = np.load(os.path.join(d, "XP.npy"), mmap_mode="r")
+        idx = np.array([0, 77, C * 40 + 3, R * C - 1])
+        close(O.extract_patches_at(Xp, 20, idx), np.asarray(XPr[idx]), 1e-5, "explicit PCA cube vs the reference's XP.npy")
+        import train as RT
+        RT.DrawResult = lambda *a, **k: np.zeros((2, 2, 3))
+        ns = argparse.Namespace(
+            dataID=1, num_label=5, save_path_prefix="./", labeled_batch_size=128, unlabeled_batch_size=128,
+            val_batch_size=512, num_workers=0, lr=5e-4, num_epochs=num_epochs, print_per_batches=4,
+            num_unlabel=num_unlabel, thr=1, alpha=0.95, queue_batch=17, temperature=0.3, teacher_alpha=0.95,
+            dropout=0.8, noise=0.5, m=5)
+        RT.seed_torch()
+        _, loc = ref_shims.capture_locals(RT.main, ns, names=("Base", "predict_label", "OA", "Kappa", "producerA"))
+        ref_sd = {k: v.detach().numpy() for k, v in loc["Base"].state_dict().items() if k in O.LIVE_KEYS}
+        OA, kappa, pa = O.cal_accuracy(loc["predict_label"][te], (Y.astype(np.int64) - 1)[te])
+        print("hard scene: reference OA = %.4f kappa = %.4f" % (OA, kappa))
+        fsd = {k: torch.from_numpy(v) for k, v in ref_sd.items()}
+        band = np.arange(60 * C, 64 * C)                       # a row band for the fixture's logits
+        lab, logit = O.test_whole(fsd, Xp, Xs, 20, return_logits=True)
+        agree = float(np.mean(lab == loc["predict_label"]))
+        print("oracle test_whole vs reference on the hard scene:", agree)
+        assert agree >= 0.999
+        if write:
+            np.savez_compressed(
+                os.path.join(GOLD, "hard_scene.npz"),
+                shape=np.array([R, C, B, K]), spread=spread, sigma=sigma, seed=1088,
+                mu=pp["mu"], sigma_x=pp["sigma"], U=pp["U"], pca_mu=pp["pca_mu"], pca_sigma=pp["pca_sigma"],
+                predict_label=loc["predict_label"].astype(np.uint8), OA=OA, Kappa=kappa, producerA=pa,
+                test_array=te, Y=Y, band=band, logits_band=logit[band].astype(np.float32),
+                cube_checksum=np.array([int(cube.astype(np.int64).sum()), int((cube.astype(np.int64) ** 2).sum() % (1 << 61))]),
+                **{f"sd.{k}": v for k, v in ref_sd.items()})
+            print("hard_scene.npz ok")
+        return OA
+    finally:
+        os.chdir(cwd)
+
+
+def gold_loader():
+    """hsi_loader.HSIDataSet of the reference on the files its own sample_generation.main wrote for the 40x36 scene:
+    lengths, the tiled label / spectrum order of every split and full items."""
+    R, C, B, K = 40, 36, 103, 9
+    cube, gt = O.synth_cube(R, C, B, K, seed=1088)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="cmlpl_gold_loader_")
+    os.makedirs(os.path.join(tmp, "dataset"))
+    sio.savemat(os.path.join(tmp, "dataset", "PaviaU.mat"), {"paviaU": cube})
+    sio.savemat(os.path.join(tmp, "dataset", "PaviaU_gt.mat"), {"paviaU_gt": gt})
+    os.chdir(tmp)
+    out = {}
+    try:
+        import sample_generation as RS
+        RS.main(argparse.Namespace(dataID=1, num_label=5, w=20, n_PC=60))
+        d = os.path.join(tmp, "dataset", "PaviaU")
+        for f in ("train_array", "test_array", "unlabel_array", "Y"):
+            out[f] = np.load(os.path.join(d, f + ".npy"))
+        out["X"] = np.load(os.path.join(d, "X.npy"))                       # f64 [N, B], the file contract
+        cases = {"label_tiled": dict(setindex="label", max_iters=137), "label_plain": dict(setindex="label"),
+                 "unlabel_head": dict(setindex="unlabel", max_iters=300, num_unlabel=200),      # tiled to 300 rows
+                 "unlabel_short": dict(setindex="unlabel", max_iters=96, num_unlabel=200),      # head of the split only
+                 "unlabel_plain": dict(setindex="unlabel", num_unlabel=50),
+                 "test": dict(setindex="test"), "wholeset": dict(setindex="wholeset")}
+        for name, kw in cases.items():
+            ds = RL.HSIDataSet(1, **kw)
+            n = len(ds)
+            out[f"{name}.len"] = np.array(n)
+            picks = sorted({0, 1, n // 2, n - 1})
+            out[f"{name}.picks"] = np.array(picks)
+            # order of the whole split through cheap per-item signatures
+            sig = np.array([ds[i][1][:4] for i in range(n)])
+            out[f"{name}.spec_sig"] = sig
+            if kw["setindex"] != "wholeset":
+                out[f"{name}.labels"] = np.array([int(ds[i][2]) for i in range(n)])
+            for j, i in enumerate(picks[:2]):
+                item = ds[i]
+                out[f"{name}.item{j}.xp"] = item[0]
+                out[f"{name}.item{j}.x"] = item[1]
+                assert item[0].dtype == np.float32 and item[1].dtype == np.float32
+                if len(item) == 3:
+                    assert item[2].dtype == np.int64 or item[2].dtype == int
+            out[f"{name}.arity"] = np.array(len(ds[0]))
+        np.savez_compressed(os.path.join(GOLD, "loader.npz"), **out)
+        print("loader.npz ok:", {k: int(v) for k, v in out.items() if k.endswith(".len")})
+    finally:
+        os.chdir(cwd)
+
+
 def gold_step():
     """One full-size (128+128) mutual-learning step through the oracle, with every input
     regenerable from the fixture (cube + indices + seeds).  The oracle's ref_step was
@@ -351,7 +458,7 @@ def gold_loss_helper():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
-    which = sys.argv[1:] or ["patches", "basenet2", "metrics", "train", "step", "loss_helper"]
+    which = sys.argv[1:] or ["patches", "basenet2", "metrics", "train", "step", "loss_helper", "loader", "hard"]
     if "patches" in which:
         gold_patches()
     if "basenet2" in which:
@@ -364,3 +471,7 @@ if __name__ == "__main__":
         gold_step()
     if "loss_helper" in which:
         gold_loss_helper()
+    if "loader" in which:
+        gold_loader()
+    if "hard" in which:
+        gold_hard()
