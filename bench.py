@@ -258,13 +258,20 @@ def make_timed(world, dev, dist):
 
     def timed(fn, steps, warmup):
         # clocks ramp from idle and the power state settles over the first second of load: hold the load before timing
-        t_end = time.perf_counter() + (1.0 if state["first"] else 0.2)
+        # (a COUNT agreed between the ranks, never a per-rank clock: the steps contain collectives)
+        target = 1.0 if state["first"] else 0.2
         state["first"] = False
-        while time.perf_counter() < t_end:
-            for _ in range(5):
-                fn()
-            torch.cuda.synchronize()
-        for _ in range(warmup):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        est = max((time.perf_counter() - t0) / 5, 1e-5)
+        n_pre = torch.tensor([min(int(math.ceil(target / est)), 20000)], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(n_pre, op=dist.ReduceOp.MAX)
+        for _ in range(int(n_pre.item()) + warmup):
             fn()
         if world > 1:
             dist.barrier()
@@ -435,7 +442,8 @@ def main():
     torch.cuda.set_device(local)
     _lib.require_device()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local)
     cube_pca, spectra, gt = scene
     timed = make_timed(world, dev, dist)

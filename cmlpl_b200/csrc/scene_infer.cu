@@ -412,7 +412,7 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
                                      float* logits, cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(raw && wf && bf && mu && inv_sigma && packed && workspace && labels, "scene_infer_raw: null pointer");
   CMLPL_CHECK_ARG(dtype == 0 || dtype == 1, "scene_infer_raw: dtype must be 0 (uint16) or 1 (float32)");
-  CMLPL_CHECK_ARG(w == 20, "scene_infer_raw: w=%d unsupported (tools/models.py:127 fixes w=20)", w);
+  CMLPL_CHECK_ARG(w == 20 || w == 11, "scene_infer_raw: w=%d unsupported (20, or 11 for the odd-window variant)", w);
   CMLPL_CHECK_ARG(band_rows > 0 && cols > 0 && num_classes > 0 && num_features > 0, "scene_infer_raw: bad dims");
   CMLPL_CHECK_ARG(use_tc_head(num_features, num_classes), "scene_infer_raw: needs <= 16 classes and <= 224 bands");
   CMLPL_CHECK_ARG(w / 2 <= scene_rows && w / 2 <= cols, "scene_infer_raw: window larger than the scene");
@@ -444,5 +444,9 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
   int rc = cmlpl_spectral_logits_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
                                         wsb + ws.x16, reinterpret_cast<float*>(wsb + ws.h16), stream);
   if (rc != CMLPL_OK) return rc;
-  return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
+  if (ws.dense) return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
+  rc = cmlpl_patch_cnn_f16(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.p2, stream);
+  if (rc != CMLPL_OK) return rc;
+  return classify_launch(wsb + ws.p2, nullptr, reinterpret_cast<const float*>(wsb + ws.h16), ((n + 127) / 128) * 128, n,
+                         num_features, num_classes, w, packed, labels, logits, stream);
 }
