@@ -63,6 +63,9 @@ SIGNATURES = {
     "cmlpl_confusion_i64": (I, [P, P, L, I, P, P]),
     "cmlpl_ce_fwd_bwd_f32": (I, [P, P, P, P, L, I, F, P, P, P]),
     "cmlpl_softmax_entropy_f32": (I, [P, L, I, F, P, P]),
+    "cmlpl_softmax_js_f32": (I, [P, P, L, I, F, P, P, P]),
+    "cmlpl_sim_nt_tc_f32": (I, [P, P, I, I, I, P, P]),
+    "cmlpl_set_loss_gemm_mode": (I, [I]),
     "cmlpl_bank_smooth_f32": (I, [P, P, P, P, L, I, I, L, F, F, I, F, P, P, P, P, P]),
     "cmlpl_graph_contrast_f32": (I, [P, P, P, P, L, I, I, F, I, F, P, P, P, P]),
     "cmlpl_ntxent_f32": (I, [P, L, I, F, P, P, P, P]),

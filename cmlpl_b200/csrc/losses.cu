@@ -64,6 +64,51 @@ __global__ void softmax_entropy_kernel(const float* __restrict__ z, int64_t rows
   ent[r] = e;
 }
 
+// ---------------------------------------------------------------- softmax JS divergence (trian_CCT.py:76-84)
+// loss = 0.5 * (kl_div(log_softmax(z), M, 'mean') + kl_div(log(t + 1e-5), M, 'mean')),  M = (softmax(z) + t) / 2,
+// 'mean' = over all rows*C elements.  One thread per row; gradient w.r.t. z in the same pass (t is a constant):
+//   f_k = 2 M log M - M log p - M log(t + eps);  g_k = df/dp_k = log M + 1 - log(p)/2 - M/p - log(t + eps)/2
+//   dz_j = p_j (g_j - sum_k g_k p_k) * scale * 0.5 / (rows*C)
+__global__ void js_kernel(const float* __restrict__ z, const float* __restrict__ t, int64_t rows, int C, float scale,
+                          float* __restrict__ loss, float* __restrict__ dz) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  float li = 0.f;
+  if (r < rows) {
+    const float* zr = z + r * C; const float* tr = t + r * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, zr[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(zr[c] - mx);
+    const float lse = mx + logf(se);
+    float gp = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float lp = zr[c] - lse, p = expf(lp), tt = tr[c];
+      const float M = 0.5f * (p + tt), lt = logf(tt + 1e-5f);
+      const float lM = M > 0.f ? logf(M) : 0.f;                // xlogy: 0 * log 0 = 0 (F.kl_div)
+      li += M * (lM - lp) + M * (lM - lt);
+      gp += (lM + 1.f - 0.5f * lp - M / p - 0.5f * lt) * p;
+    }
+    if (dz) {
+      const float cf = scale * 0.5f / (float(rows) * float(C));
+      for (int c = 0; c < C; ++c) {
+        const float lp = zr[c] - lse, p = expf(lp), tt = tr[c];
+        const float M = 0.5f * (p + tt), lt = logf(tt + 1e-5f);
+        const float lM = M > 0.f ? logf(M) : 0.f;
+        dz[r * C + c] = cf * p * ((lM + 1.f - 0.5f * lp - M / p - 0.5f * lt) - gp);
+      }
+    }
+  }
+  li = warp_sum(li);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = li;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v * scale * 0.5f / (float(rows) * float(C)));
+  }
+}
+
 // ---------------------------------------------------------------- memory-bank smoothing (train.py:203-222)
 // one warp per row: probs_orig = softmax(z); A = exp(S/T) over the bank (S = f.Qf^T precomputed by the
 // GEMM core, streamed once), probs = alpha*p + (1-alpha) * (A/sum A).Qp ; mask = max(probs) >= thr
@@ -211,6 +256,21 @@ __global__ void adam_kernel(AdamTable t, float lr, float b1, float b2, float eps
 
 using namespace cmlpl;
 
+// Similarity matrices S = A . B^T (both operands [rows, K] with K contiguous) of the loss entry points: fp32 FFMA tiles by
+// default (the 1e-5 parity path); mode 1 rounds the operands to fp16 and runs them on tcgen05 (cmlpl_sim_nt_tc_f32,
+// |d| ~ 1e-4 on unit-norm features) -- at the config-3 stress size the CUDA-core GEMM dominates these calls.
+static thread_local int g_loss_gemm_mode = 0;
+extern "C" int cmlpl_set_loss_gemm_mode(int mode) {
+  CMLPL_CHECK_ARG(mode == 0 || mode == 1, "set_loss_gemm_mode: 0 (fp32 CUDA cores) or 1 (tcgen05 fp16 operands)");
+  g_loss_gemm_mode = mode;
+  return CMLPL_OK;
+}
+static int sim_nt(const float* A, const float* B, int M, int N, int K, float* C, cudaStream_t s, const char* name) {
+  if (g_loss_gemm_mode == 1 && K % 64 == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0)
+    return cmlpl_sim_nt_tc_f32(A, B, M, N, K, C, s);
+  return launch_gemm(M, N, K, 1, StridedA{A, K, 1}, StridedB{B, 1, K}, StridedC{C, N, 1, nullptr, 1.f, 0.f, 0}, s, name);
+}
+
 extern "C" int cmlpl_ce_fwd_bwd_f32(const float* logits, const int64_t* labels, const float* probs, const float* mask,
                                     int64_t rows, int C, float scale, float* loss, float* dlogits, cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(logits && loss, "ce: null pointer");
@@ -220,6 +280,16 @@ extern "C" int cmlpl_ce_fwd_bwd_f32(const float* logits, const int64_t* labels, 
   ce_kernel<<<int((rows + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, probs, mask, rows, C,
                                                                                     scale, loss, dlogits);
   CMLPL_CHECK_LAUNCH("ce");
+  return CMLPL_OK;
+}
+
+extern "C" int cmlpl_softmax_js_f32(const float* logits, const float* targets, int64_t rows, int C, float scale,
+                                    float* loss, float* dlogits, cmlpl_stream_t stream) {
+  CMLPL_CHECK_ARG(logits && targets && loss, "softmax_js: null pointer");
+  CMLPL_CHECK_ARG(rows >= 0 && C > 0 && C <= 4096, "softmax_js: bad dims");
+  if (rows == 0) return CMLPL_OK;
+  js_kernel<<<int((rows + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, targets, rows, C, scale, loss, dlogits);
+  CMLPL_CHECK_LAUNCH("softmax_js");
   return CMLPL_OK;
 }
 
@@ -243,8 +313,7 @@ extern "C" int cmlpl_bank_smooth_f32(const float* logits, const float* feats, co
   if (rows == 0) return CMLPL_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (smooth) {   // S = feats . queue_feats^T   (train.py:213)
-    int rc = launch_gemm(int(rows), int(queue), dim, 1, StridedA{feats, dim, 1}, StridedB{queue_feats, 1, dim},
-                         StridedC{work, queue, 1, nullptr, 1.f, 0.f, 0}, s, "bank_sim");
+    int rc = sim_nt(feats, queue_feats, int(rows), int(queue), dim, work, s, "bank_sim");
     if (rc != CMLPL_OK) return rc;
   }
   const int grid = int((rows + 3) / 4);
@@ -265,8 +334,7 @@ extern "C" int cmlpl_graph_contrast_f32(const float* f_row, const float* f_col, 
   CMLPL_CHECK_ARG(n > 0 && dim > 0 && C > 0 && T > 0 && (grad_side == 0 || grad_side == 1), "graph_contrast: bad args");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* G = work; float* Q0 = work + n * n; float* dG = work + 2 * n * n;
-  int rc = launch_gemm(int(n), int(n), dim, 1, StridedA{f_row, dim, 1}, StridedB{f_col, 1, dim},
-                       StridedC{G, n, 1, nullptr, 1.f, 0.f, 0}, s, "graph_sim");          // train.py:246 / :257
+  int rc = sim_nt(f_row, f_col, int(n), int(n), dim, G, s, "graph_sim");                  // train.py:246 / :257
   if (rc != CMLPL_OK) return rc;
   rc = launch_gemm(int(n), int(n), C, 1, StridedA{p1, C, 1}, StridedB{p, 1, C},
                    StridedC{Q0, n, 1, nullptr, 1.f, 0.f, 0}, s, "graph_q0");              // train.py:249
@@ -291,8 +359,7 @@ extern "C" int cmlpl_ntxent_f32(const float* z, int64_t bs, int dim, float T, fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t n = 2 * bs;
   float* S = work; float* dS = work + n * n;
-  int rc = launch_gemm(int(n), int(n), dim, 1, StridedA{z, dim, 1}, StridedB{z, 1, dim},
-                       StridedC{S, n, 1, nullptr, 1.f, 0.f, 0}, s, "ntxent_sim");         // models.py:27 on unit rows
+  int rc = sim_nt(z, z, int(n), int(n), dim, S, s, "ntxent_sim");                        // models.py:27 on unit rows
   if (rc != CMLPL_OK) return rc;
   ntxent_kernel<<<int((n + 3) / 4), 128, 0, s>>>(S, bs, 1.f / T, loss, dz ? dS : nullptr);
   CMLPL_CHECK_LAUNCH("ntxent");

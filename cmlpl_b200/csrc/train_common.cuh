@@ -41,7 +41,7 @@ __host__ __device__ inline TrainWs train_ws_layout(int bs, int btu, int B, int C
   L.dhp = take(ns * kHid * 4);
   L.dz1 = take(ns * kActBytes);
   L.da0 = take(ns * kActBytes);
-  L.S = take(size_t(2) * btu * queue * 4);
+  L.S = take(size_t(2) * (2 * ((queue + 127) / 128)) * btu * 33 * 4);   // streaming bank-smoothing partials
   L.G = take(size_t(btu) * btu * 4);
   L.dG = take(size_t(btu) * btu * 4);
   L.probs_orig = take(size_t(2) * btu * C * 4);

@@ -112,12 +112,29 @@ int launch_multi_gemm(const MultiGemm& mg, cudaStream_t st, const char* name) {
 // ============================================================================ classifier forward
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// block-wide sum of NV per-thread values (128 threads = 4 warps); the result is valid in every thread
+template <int NV>
+__device__ __forceinline__ void block_sum4(float (&v)[NV], float* red /* [4][NV] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();                                   // red may still be read from a previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[warp * NV + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = (red[i] + red[NV + i]) + (red[2 * NV + i] + red[3 * NV + i]);
+}
+
+// one CTA (4 warps) per row: 656 float4 groups of the 2624 features over 128 threads
 template <int CMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 head_fwd_kernel(HeadArgs a) {
-  const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (s >= 2 * a.nb) return;
-  const int lane = threadIdx.x & 31;
+  __shared__ float red[4 * (CMAX + 1)];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x;
   const int e = s / a.nb;
   const float* cat = a.cat + int64_t(s) * kCatDim;
   float* dm = a.dmask + int64_t(s) * kCatDim;
@@ -125,11 +142,10 @@ head_fwd_kernel(HeadArgs a) {
   const float p = a.prm->dropout_p;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const unsigned long long seed = a.prm->seed, offset = a.prm->offset;
-  float acc[CMAX];
+  float acc[CMAX + 1];                                 // [CMAX] = sum of squares of the spectral features
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-  float nsq = 0.f;
-  for (int g = lane; g < kCatDim / 4; g += 32) {
+  for (int c = 0; c <= CMAX; ++c) acc[c] = 0.f;
+  for (int g = tid; g < kCatDim / 4; g += 128) {
     const float4 x = ld4(cat + 4 * g);
     float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
     if (a.drop_mask) {
@@ -142,7 +158,7 @@ head_fwd_kernel(HeadArgs a) {
     }
     *reinterpret_cast<float4*>(dm + 4 * g) = m;
     const float4 xd = make_float4(x.x * m.x, x.y * m.y, x.z * m.z, x.w * m.w);
-    if (4 * g >= kConvFeat) nsq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    if (4 * g >= kConvFeat) acc[CMAX] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
       if (c < a.C) {
@@ -151,24 +167,23 @@ head_fwd_kernel(HeadArgs a) {
       }
     }
   }
-  nsq = warp_sum(nsq);
+  block_sum4<CMAX + 1>(acc, red);
+  const float nr = sqrtf(acc[CMAX]);                           // models.py:88: no epsilon
+  if (tid == 0) a.norm[s] = nr;
+  if (tid < a.C) {
+    float v = 0.f;
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c) acc[c] = warp_sum(acc[c]);
-  const float nr = sqrtf(nsq);                                 // models.py:88: no epsilon
-  if (lane == 0) {
-    a.norm[s] = nr;
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < a.C) a.logits[int64_t(s) * a.C + c] = acc[c] + a.bc[e][c];
+    for (int c = 0; c < CMAX; ++c) v = tid == c ? acc[c] : v;
+    a.logits[int64_t(s) * a.C + tid] = v + a.bc[e][tid];
   }
   float* f = a.feat + int64_t(s) * kHid;
-  for (int j = lane; j < kHid; j += 32) f[j] = cat[kConvFeat + j] / nr;
+  for (int j = tid; j < kHid; j += 128) f[j] = cat[kConvFeat + j] / nr;
 }
 
 int launch_head_fwd(const HeadArgs& a, cudaStream_t st) {
-  const int grid = (2 * a.nb + 7) / 8;
-  if (a.C <= 16) head_fwd_kernel<16><<<grid, 256, 0, st>>>(a);
-  else head_fwd_kernel<32><<<grid, 256, 0, st>>>(a);
+  const int grid = 2 * a.nb;
+  if (a.C <= 16) head_fwd_kernel<16><<<grid, 128, 0, st>>>(a);
+  else head_fwd_kernel<32><<<grid, 128, 0, st>>>(a);
   CMLPL_CHECK_LAUNCH("train_head_fwd");
   return CMLPL_OK;
 }
@@ -198,23 +213,21 @@ loss_rows_kernel(LossArgs a) {
     if (lane == 0)
       for (int c = 0; c < C; ++c) po[c] = p[c];
     if (a.prm->smooth) {
-      const float invT = 1.f / a.prm->temperature, alpha = a.prm->alpha;
-      const float* S = a.S + (int64_t(t) * a.btu + r) * a.queue;
-      const float* qp = a.queue_probs[t];
-      float asum = 0.f, acc[CMAX];
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-      for (int j = lane; j < a.queue; j += 32) {
-        const float w = expf(S[j] * invT);                   // unit-norm features: |S| <= 1, plain exp is safe
-        asum += w;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c)
-          if (c < C) acc[c] = fmaf(w, qp[int64_t(j) * C + c], acc[c]);
+      // A = exp(f.Qf^T / T) row-normalised, probs = alpha*probs + (1-alpha) * A.Qp (train.py:213-215): the exp sums
+      // were streamed out of the similarity tiles by sim_tc_kernel (one partial per bank tile and column half)
+      const float alpha = a.prm->alpha;
+      const int nparts = 2 * ((a.queue + 127) / 128);
+      const float* part = a.S + (int64_t(t) * nparts * a.btu + r) * 33;
+      float asum = 0.f, acc = 0.f;                           // lane c < C accumulates class c
+      for (int q = 0; q < nparts; ++q) {
+        const float* pq = part + int64_t(q) * a.btu * 33;
+        asum += pq[32];
+        if (lane < C) acc += pq[lane];
       }
-      asum = warp_sum(asum);
+      const float sm = acc / asum;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
-        if (c < C) p[c] = alpha * p[c] + (1.f - alpha) * (warp_sum(acc[c]) / asum);
+        if (c < C) p[c] = alpha * p[c] + (1.f - alpha) * __shfl_sync(0xffffffffu, sm, c);
     }
     if (lane == 0) {
       float best = -INFINITY;
@@ -369,11 +382,11 @@ int launch_loss_graph(const LossArgs& a, cudaStream_t st) {
 
 // ============================================================================ head backward
 template <int CMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 head_bwd_kernel(HeadArgs a) {
-  const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (s >= 2 * a.nb) return;
-  const int lane = threadIdx.x & 31;
+  __shared__ float red[4];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x;
   const int e = s / a.nb, r = s - e * a.nb;
   const float* wc = a.wc[e];
   const float* cat = a.cat + int64_t(s) * kCatDim;
@@ -386,13 +399,13 @@ head_bwd_kernel(HeadArgs a) {
   const bool unl = r >= a.bs;
   const float* df = unl ? a.dfeat + (int64_t(e) * a.btu + (r - a.bs)) * kHid : nullptr;
   const float* ft = a.feat + int64_t(s) * kHid;
-  float dot = 0.f;
+  float dot[1] = {0.f};
   if (unl)
-    for (int j = lane; j < kHid; j += 32) dot = fmaf(df[j], ft[j], dot);
-  dot = warp_sum(dot);
+    for (int j = tid; j < kHid; j += 128) dot[0] = fmaf(df[j], ft[j], dot[0]);
+  block_sum4<1>(dot, red);
   const float inv_norm = 1.f / a.norm[s];
   float amax = 0.f;
-  for (int g = lane; g < kCatDim / 4; g += 32) {
+  for (int g = tid; g < kCatDim / 4; g += 128) {
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
@@ -411,8 +424,8 @@ head_bwd_kernel(HeadArgs a) {
       const float4 h = ld4(cat + 4 * g);
       if (unl) {
         const float4 f = ld4(ft + j), q = ld4(df + j);
-        d.x += (q.x - f.x * dot) * inv_norm; d.y += (q.y - f.y * dot) * inv_norm;
-        d.z += (q.z - f.z * dot) * inv_norm; d.w += (q.w - f.w * dot) * inv_norm;
+        d.x += (q.x - f.x * dot[0]) * inv_norm; d.y += (q.y - f.y * dot[0]) * inv_norm;
+        d.z += (q.z - f.z * dot[0]) * inv_norm; d.w += (q.w - f.w * dot[0]) * inv_norm;
       }
       float4 o;
       o.x = h.x > 0.f ? d.x : 0.f; o.y = h.y > 0.f ? d.y : 0.f; o.z = h.z > 0.f ? d.z : 0.f; o.w = h.w > 0.f ? d.w : 0.f;
@@ -420,13 +433,13 @@ head_bwd_kernel(HeadArgs a) {
     }
   }
   amax = warp_max(amax);
-  if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&a.prm_rw->grad_amax), __float_as_uint(amax));
+  if ((tid & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&a.prm_rw->grad_amax), __float_as_uint(amax));
 }
 
 int launch_head_bwd(const HeadArgs& a, cudaStream_t st) {
-  const int grid = (2 * a.nb + 7) / 8;
-  if (a.C <= 16) head_bwd_kernel<16><<<grid, 256, 0, st>>>(a);
-  else head_bwd_kernel<32><<<grid, 256, 0, st>>>(a);
+  const int grid = 2 * a.nb;
+  if (a.C <= 16) head_bwd_kernel<16><<<grid, 128, 0, st>>>(a);
+  else head_bwd_kernel<32><<<grid, 128, 0, st>>>(a);
   CMLPL_CHECK_LAUNCH("train_head_bwd");
   return CMLPL_OK;
 }

@@ -16,6 +16,17 @@ struct GemmProb {
 struct MultiGemm { GemmProb p[4]; int count; };
 int launch_multi_gemm(const MultiGemm& mg, cudaStream_t st, const char* name);
 
+// S = A . B^T on tcgen05 (train_sim_sm100.cu).  mode 0: store the tile; mode 1: streaming bank-smoothing partials.
+struct SimProb {
+  const float* A; const float* B; int64_t lda, ldb;   // A [M, K], B [N, K], K contiguous
+  int M, N, K, mode;
+  float* Cout; int64_t ldc;                            // mode 0
+  const float* qp; float* part; int C;                 // mode 1: queue_probs [N, C], part [2*ceil(N/128)][M][33]
+  const int* enable;
+};
+struct SimBatch { SimProb p[4]; int count; const cmlpl_train_params* prm; };
+int launch_sim_tc(const SimBatch& sb, cudaStream_t st, const char* name);
+
 struct HeadArgs {
   const cmlpl_train_params* prm; cmlpl_train_params* prm_rw;
   int nb, bs, btu, C, training;
@@ -34,7 +45,8 @@ struct LossArgs {
   const cmlpl_train_params* prm;
   int bs, btu, C, queue;
   const float* logits; const float* feat; const int64_t* labels;
-  const float* S; const float* G; float* dG;
+  const float* S;                  // bank-smoothing partials [2 banks][2*ceil(queue/128)][btu][33]
+  const float* G; float* dG;
   float* queue_feats[2]; float* queue_probs[2];
   float* probs_orig; float* probs; float* mask;
   float* dlogits; float* hist;

@@ -111,22 +111,24 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
     la.dlogits = f32(L.dlogits); la.hist = io->hist;
     const float* xs = io->feat + int64_t(bs) * kHid;              // unlabelled features of net 0 (xs_feature)
     const float* xw = io->feat + (int64_t(nb) + bs) * kHid;       // unlabelled features of net 1 (xw_feature)
-    MultiGemm sims{};
+    SimBatch sims{};
     sims.count = 3;
+    sims.prm = prm;
+    const int nparts = 2 * ((Q + 127) / 128);
     for (int t = 0; t < 2; ++t) {
       la.queue_feats[t] = io->net[t].queue_feats; la.queue_probs[t] = io->net[t].queue_probs;
-      // S[t] = feats_u(net 1-t) . queue_feats[t]^T  (train.py:213,217)
-      sims.p[t] = GemmProb{t == 0 ? xw : xs, kHid, 1, io->net[t].queue_feats, 1, kHid, f32(L.S) + int64_t(t) * btu * Q, Q, 1,
-                           nullptr, &prm->smooth, btu, Q, kHid, 1.f, 0};
+      // bank t: feats_u(net 1-t) . queue_feats[t]^T, streamed into exp sums (train.py:213-217), never materialised
+      sims.p[t] = SimProb{t == 0 ? xw : xs, io->net[t].queue_feats, kHid, kHid, btu, Q, kHid, 1, nullptr, 0,
+                          io->net[t].queue_probs, f32(L.S) + int64_t(t) * nparts * btu * 33, C, &prm->smooth};
     }
-    sims.p[2] = GemmProb{xs, kHid, 1, xw, 1, kHid, f32(L.G), btu, 1, nullptr, nullptr, btu, btu, kHid, 1.f, 0};   // train.py:246
+    sims.p[2] = SimProb{xs, xw, kHid, kHid, btu, btu, kHid, 0, f32(L.G), btu, nullptr, nullptr, 0, nullptr};   // train.py:246
     MultiGemm dfe{};
     dfe.count = 2;
     // d xs = dG . xw (loss_contrast -> net 0), d xw = dG^T . xs (loss_contrast1 -> net 1); dG carries 0.5/T/n
     dfe.p[0] = GemmProb{f32(L.dG), btu, 1, xw, kHid, 1, f32(L.dfeat), kHid, 1, nullptr, nullptr, btu, kHid, btu, 1.f, 0};
     dfe.p[1] = GemmProb{f32(L.dG), 1, btu, xs, kHid, 1, f32(L.dfeat) + int64_t(btu) * kHid, kHid, 1, nullptr, nullptr,
                         btu, kHid, btu, 1.f, 0};
-    if ((rc = launch_multi_gemm(sims, st, "train_sims")) != CMLPL_OK) return rc;
+    if ((rc = launch_sim_tc(sims, st, "train_sims")) != CMLPL_OK) return rc;
     if ((rc = launch_loss_rows(la, st)) != CMLPL_OK) return rc;
     if ((rc = launch_loss_graph(la, st)) != CMLPL_OK) return rc;
     if ((rc = launch_multi_gemm(dfe, st, "train_dfeat")) != CMLPL_OK) return rc;

@@ -279,6 +279,19 @@ def ce_fwd_bwd(logits, labels=None, probs=None, mask=None, scale=1.0, want_grad=
     return loss, dz
 
 
+def softmax_js(logits, targets, scale=1.0, want_grad=True):
+    """trian_CCT.py:76-84 -> (scale*L, scale*dL/dlogits)."""
+    _chk(logits, name="logits"); _chk(targets, name="targets")
+    if logits.shape != targets.shape or logits.dim() != 2:
+        raise _lib.CmlplError("softmax_js: logits and targets must be [rows, C] of the same shape")
+    rows, C = logits.shape
+    loss = torch.zeros((), dtype=_f32, device=logits.device)
+    dz = torch.empty_like(logits) if want_grad else None
+    _lib.call("cmlpl_softmax_js_f32", logits.data_ptr(), targets.data_ptr(), rows, C, float(scale), loss.data_ptr(),
+              _p(dz), _stream())
+    return loss, dz
+
+
 def bank_smooth(logits, feats, queue_feats, queue_probs, alpha, T, smooth, thr):
     """train.py:203-222 -> (probs_orig, probs, mask)."""
     _chk(logits, name="logits")

@@ -269,6 +269,19 @@ int cmlpl_ce_fwd_bwd_f32(const float* logits, const int64_t* labels, const float
                          const float* mask, int64_t rows, int C, float scale,
                          float* loss, float* dlogits, cmlpl_stream_t stream);
 
+/* S = A . B^T with A f32 [M, K], B f32 [N, K] (K contiguous, K % 64 == 0) on tcgen05: operands rounded to fp16, fp32
+ * accumulation; C f32 [M, N].  The similarity matrices of train.py:213,246 and tools/models.py:27.
+ * cmlpl_set_loss_gemm_mode(1) makes cmlpl_bank_smooth_f32 / cmlpl_graph_contrast_f32 / cmlpl_ntxent_f32 use it for
+ * their similarity GEMM (default 0: fp32 CUDA-core tiles, the 1e-5 parity path).  The setting is per host thread. */
+int cmlpl_sim_nt_tc_f32(const float* A, const float* B, int M, int N, int K, float* C, cmlpl_stream_t stream);
+int cmlpl_set_loss_gemm_mode(int mode);
+
+/* trian_CCT.py:76-84 softmax_js_loss: *loss += scale * 0.5 * (kl_div(log_softmax(z), M, 'mean') +
+ * kl_div(log(t + 1e-5), M, 'mean')) with M = (softmax(z) + t)/2 and 'mean' over all rows*C elements;
+ * dlogits (may be NULL) = scale * dL/dz, targets are constants.  logits, targets f32 [rows, C]. */
+int cmlpl_softmax_js_f32(const float* logits, const float* targets, int64_t rows, int C, float scale,
+                         float* loss, float* dlogits, cmlpl_stream_t stream);
+
 /* loss_helper.py:247-248: entropy_i = -sum_c p_ic log(p_ic + eps), p = softmax(logits_i).  f32 [rows]. */
 int cmlpl_softmax_entropy_f32(const float* logits, int64_t rows, int C, float eps, float* entropy,
                               cmlpl_stream_t stream);

@@ -357,6 +357,50 @@ def gold_loader():
         os.chdir(cwd)
 
 
+def _reference_function(path, name):
+    """Compile ONE function of a reference script that cannot be imported as a module (trian_CCT.py imports names the
+    repository does not ship): its unmodified source text, executed in a namespace holding torch and F."""
+    import ast
+    import torch.nn.functional as F_
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch, "F": F_}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def gold_ablation():
+    """f4: softmax_js_loss of trian_CCT.py:76-84 (the reference's own function object) and the CPS cross-supervision
+    losses of trian_CPS.py:232-247 (restated inline: the script has no function boundary there)."""
+    js = _reference_function(os.path.join(ref_shims.REFERENCE_ROOT, "trian_CCT.py"), "softmax_js_loss")
+    g = torch.Generator().manual_seed(31)
+    out = {}
+    for tag, (n, C) in {"a": (37, 9), "b": (128, 16)}.items():
+        z = (torch.randn(n, C, generator=g) * 2).requires_grad_(True)
+        t = torch.softmax(torch.randn(n, C, generator=g) * 3, 1)
+        if tag == "a":
+            t[0] = 0.0; t[0, 3] = 1.0                      # exact zeros in the target (xlogy branch of F.kl_div)
+        loss = js(z, t)
+        loss.backward()
+        out.update({f"js_{tag}_z": z.detach().numpy(), f"js_{tag}_t": t.numpy(), f"js_{tag}_loss": loss.detach().numpy(),
+                    f"js_{tag}_grad": z.grad.numpy()})
+    # CPS
+    bs, n, C = 24, 56, 9
+    ob = (torch.randn(n, C, generator=g)).requires_grad_(True); oe = (torch.randn(n, C, generator=g)).requires_grad_(True)
+    Y = torch.randint(0, C, (bs,), generator=g)
+    ce = torch.nn.CrossEntropyLoss()
+    cls, cls1 = ce(ob[:bs], Y), ce(oe[:bs], Y)
+    p1, p2 = torch.max(ob[bs:], 1)[1], torch.max(oe[bs:], 1)[1]
+    con, con1 = ce(ob[bs:], p2.detach()).mean(), ce(oe[bs:], p1.detach()).mean()
+    tot, tot1 = cls + 0.1 * con, cls1 + 0.1 * con1
+    tot.backward(); tot1.backward()
+    out.update(cps_ob=ob.detach().numpy(), cps_oe=oe.detach().numpy(), cps_Y=Y.numpy(), cps_total=tot.detach().numpy(),
+               cps_total1=tot1.detach().numpy(), cps_con=con.detach().numpy(), cps_con1=con1.detach().numpy(),
+               cps_gb=ob.grad.numpy(), cps_ge=oe.grad.numpy())
+    np.savez_compressed(os.path.join(GOLD, "ablation.npz"), **out)
+    print("ablation.npz ok")
+
+
 def gold_step():
     """One full-size (128+128) mutual-learning step through the oracle, with every input
     regenerable from the fixture (cube + indices + seeds).  The oracle's ref_step was
@@ -458,7 +502,7 @@ def gold_loss_helper():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
-    which = sys.argv[1:] or ["patches", "basenet2", "metrics", "train", "step", "loss_helper", "loader", "hard"]
+    which = sys.argv[1:] or ["patches", "basenet2", "metrics", "train", "step", "loss_helper", "ablation", "loader", "hard"]
     if "patches" in which:
         gold_patches()
     if "basenet2" in which:
@@ -471,6 +515,8 @@ if __name__ == "__main__":
         gold_step()
     if "loss_helper" in which:
         gold_loss_helper()
+    if "ablation" in which:
+        gold_ablation()
     if "loader" in which:
         gold_loader()
     if "hard" in which:

@@ -36,12 +36,22 @@ def run(dev, C=16):
             return e0.elapsed_time(e1) / reps
 
         r = {}
+        from cmlpl_b200 import _lib
+        zz = torch.cat([fs, fw]).contiguous()
+        _lib.call("cmlpl_set_loss_gemm_mode", 1)            # similarity GEMMs on tcgen05 (fp16 operands)
+        ref_l, _ = ops.graph_contrast(fs, fw, p1, p, 0.3, 0, 1.0, True)
+        r["graph_contrast_tc_ms"] = t(lambda: ops.graph_contrast(fs, fw, p1, p, 0.3, 0, 1.0, True))
+        r["bank_smooth_tc_ms"] = t(lambda: ops.bank_smooth(z, fw, qf, qp, 0.95, 0.3, True, 0.5))
+        r["ntxent_tc_ms"] = t(lambda: ops.ntxent(zz, n, 0.5, True))
+        _lib.call("cmlpl_set_loss_gemm_mode", 0)
+        l32, _ = ops.graph_contrast(fs, fw, p1, p, 0.3, 0, 1.0, True)
+        r["graph_contrast_tc_vs_fp32_rel"] = float((ref_l - l32).abs() / l32.abs())
         r["graph_contrast_ms"] = t(lambda: ops.graph_contrast(fs, fw, p1, p, 0.3, 0, 1.0, True))
         r["graph_contrast_matrix_bytes"] = 3 * n * n * 4
         r["graph_contrast_operand_bytes"] = 3 * n * 1024 * 4
         r["bank_smooth_ms"] = t(lambda: ops.bank_smooth(z, fw, qf, qp, 0.95, 0.3, True, 0.5))
         r["bank_smooth_matrix_bytes"] = n * queue * 4
-        r["ntxent_ms"] = t(lambda: ops.ntxent(torch.cat([fs, fw]), n, 0.5, True))
+        r["ntxent_ms"] = t(lambda: ops.ntxent(zz, n, 0.5, True))
         r["ntxent_matrix_bytes"] = 2 * (2 * n) ** 2 * 4
         r["note"] = ("matrices are produced by the GEMM and consumed by the row kernel that follows; at n = 1024 they are "
                      "4-16 MB, far below the 126 MB L2")

@@ -84,24 +84,7 @@ def main():
     lib = _lib.load()
     bsz = lambda n: n
     ws = fs.work
-    # recompute the layout like train_common.cuh
-    def layout():
-        o = 0
-        out = {}
-        ns = 2 * nb
-        def take(name, nbytes):
-            nonlocal o
-            out[name] = o
-            o = (o + nbytes + 255) // 256 * 256
-        take("x16", ns * 51200); take("a0", ns * 51200); take("p1", ns * 12800); take("m1", ns * 3200); take("m2", ns * 800)
-        take("cat", ns * 2624 * 4); take("dmask", ns * 2624 * 4); take("ynoisy", ns * B * 4); take("norm", ns * 4)
-        take("dlogits", ns * C * 4); take("dfeat", 2 * bs * 1024 * 4); take("dcat", ns * 2624 * 4); take("dhp", ns * 1024 * 4)
-        take("dz1", ns * 51200); take("da0", ns * 51200); take("S", 2 * bs * fs.queue * 4); take("G", bs * bs * 4)
-        take("dG", bs * bs * 4); take("probs_orig", 2 * bs * C * 4)
-        out["total"] = o
-        return out
-    lay = layout()
-    assert lay["total"] == ws.numel(), (lay["total"], ws.numel())
+    lay = fs.workspace_layout()
     ns = 2 * nb
     x16 = planes_to_nchw(ws[lay["x16"]:], ns, 400, 20)
     print("x16 vs patches (60 ch):", rel(x16[:, :60], patches.view(ns, 60, 20, 20)), " pad ch max:", float(x16[:, 60:].abs().max()))

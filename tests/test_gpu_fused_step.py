@@ -328,3 +328,26 @@ def test_packed_weights_follow_the_optimizers(dev):
     from cmlpl_b200 import ops
     fresh = ops.pack_basenet2(dict(nets[0].state_dict()), 103, 9, 20)
     assert torch.equal(after[:2 * 73728], fresh[:2 * 73728])          # conv1 / conv2 regions (the rest has padding gaps)
+
+
+@pytest.mark.parametrize("M,N", [(128, 1280), (100, 300), (16, 160)])
+def test_tcgen05_similarity_gemm(dev, M, N):
+    """cmlpl_sim_nt_tc_f32 (fp16 operands on tcgen05, fp32 accumulate) on unit-norm 1024-d features, tails included,
+    and the loss entry points in their tensor-core mode against the fp32 mode."""
+    from cmlpl_b200 import _lib, ops
+    g = torch.Generator().manual_seed(M + N)
+    A = F.normalize(torch.randn(M, 1024, generator=g), dim=1).to(dev)
+    B = F.normalize(torch.randn(N, 1024, generator=g), dim=1).to(dev)
+    C = torch.full((M, N), float("nan"), device=dev)
+    _lib.call("cmlpl_sim_nt_tc_f32", A.data_ptr(), B.data_ptr(), M, N, 1024, C.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    ref = A.double() @ B.double().t()
+    assert float((C.double() - ref).abs().max()) < 1e-3 * float(ref.abs().max())
+    z = torch.randn(M, 9, generator=g).to(dev)
+    qp = torch.softmax(torch.randn(N, 9, generator=g), 1).to(dev)
+    fp32 = ops.bank_smooth(z, A, B, qp, 0.95, 0.3, True, 0.5)
+    _lib.call("cmlpl_set_loss_gemm_mode", 1)
+    try:
+        tc = ops.bank_smooth(z, A, B, qp, 0.95, 0.3, True, 0.5)
+    finally:
+        _lib.call("cmlpl_set_loss_gemm_mode", 0)
+    assert rel(tc[1], fp32[1]) < 1e-3 and torch.equal(tc[0], fp32[0])

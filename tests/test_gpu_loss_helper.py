@@ -92,3 +92,40 @@ def test_contra_memobank_loss_matches_reference(dev, golden_dir):
                                                         i_iter=5)
     assert abs(float(loss) - float(z["mb_loss_mom"])) < 2e-5 * abs(float(z["mb_loss_mom"]))
     assert np.abs(proto.sum((1, 2, 3)).cpu().numpy() - z["mb_proto_sum"]).max() < 1e-2
+
+
+# ------------------------------------------------------------------ f4: ablation entry points (trian_CCT / trian_CPS)
+def test_softmax_js_loss_matches_reference_function(dev, golden_dir):
+    """cmlpl_softmax_js_f32 behind trian_CCT.softmax_js_loss against the reference's own function (trian_CCT.py:76-84,
+    compiled from its unmodified source by oracle/make_golden.py), value and gradient, incl. exact-zero targets."""
+    from cmlpl_b200.trian_CCT import cct_consistency, softmax_js_loss
+    z = np.load(os.path.join(golden_dir, "ablation.npz"))
+    for tag in ("a", "b"):
+        x = torch.from_numpy(z[f"js_{tag}_z"]).to(dev).requires_grad_(True)
+        t = torch.from_numpy(z[f"js_{tag}_t"]).to(dev)
+        loss = softmax_js_loss(x, t)
+        loss.backward()
+        assert abs(float(loss) - float(z[f"js_{tag}_loss"])) <= 1e-5 * abs(float(z[f"js_{tag}_loss"]))
+        g = z[f"js_{tag}_grad"]
+        assert np.abs(x.grad.cpu().numpy() - g).max() <= 1e-4 * np.abs(g).max()
+    with pytest.raises(AssertionError):
+        softmax_js_loss(x.detach(), t)                       # the reference asserts inputs.requires_grad
+    a = torch.randn(8, 9, device=dev, requires_grad=True); b = torch.randn(8, 9, device=dev, requires_grad=True)
+    c = torch.randn(8, 9, device=dev, requires_grad=True)
+    cct_consistency(a, b, c).backward()
+    assert all(torch.isfinite(v.grad).all() for v in (a, b, c))
+
+
+def test_cps_losses_match_reference(dev, golden_dir):
+    from cmlpl_b200.trian_CPS import Distribution_Loss, cps_losses
+    z = np.load(os.path.join(golden_dir, "ablation.npz"))
+    ob = torch.from_numpy(z["cps_ob"]).to(dev).requires_grad_(True)
+    oe = torch.from_numpy(z["cps_oe"]).to(dev).requires_grad_(True)
+    tot, tot1, (cls, cls1, con, con1) = cps_losses(ob, oe, torch.from_numpy(z["cps_Y"]).to(dev))
+    tot.backward(); tot1.backward()
+    for got, want in ((tot, "cps_total"), (tot1, "cps_total1"), (con, "cps_con"), (con1, "cps_con1")):
+        assert abs(float(got) - float(z[want])) <= 1e-5 * abs(float(z[want])), want
+    assert np.abs(ob.grad.cpu().numpy() - z["cps_gb"]).max() <= 1e-5 * np.abs(z["cps_gb"]).max()
+    assert np.abs(oe.grad.cpu().numpy() - z["cps_ge"]).max() <= 1e-5 * np.abs(z["cps_ge"]).max()
+    with pytest.raises(NotImplementedError):
+        Distribution_Loss(loss='mmd')(ob, oe)
