@@ -126,21 +126,11 @@ patch_cnn_kernel(const __half* __restrict__ f0pad, int cols, int band_rows,
 
   // ---------------------------------------------------------------- one-time setup
   if constexpr (TRAIN) {
-    // fp32 [co][ci][dy][dx] -> fp16 [3 dx][8 kchunks][192 rows = (2-dy)*64 + co][8 ci]  (conv_pair_issue.cuh)
-    __half* s1 = reinterpret_cast<__half*>(smem + Cfg::S_W1);
-    __half* s2 = reinterpret_cast<__half*>(smem + Cfg::S_W2);
-    const float* g1 = ta.w1[net];
-    const float* g2 = ta.w2[net];
-    for (int i = tid; i < 64 * 64 * 9; i += kThreads) {
-      const int co = i / 576, r = i - co * 576, ci = r / 9, t = r - ci * 9, dy = t / 3, dx = t - dy * 3;
-      const int dst = ((dx * 8 + (ci >> 3)) * kWRows + (2 - dy) * 64 + co) * 8 + (ci & 7);
-      s1[dst] = __float2half_rn(__ldg(g1 + i));
-      s2[dst] = __float2half_rn(__ldg(g2 + i));
-    }
-    uint4* z = reinterpret_cast<uint4*>(smem + Cfg::S_A2);
-    const int zn = (Cfg::SMEM - Cfg::S_A2) / 16;
-    for (int i = tid; i < zn; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-  } else {  // weights -> smem (already in UMMA layout), zero the activation planes, biases
+    // this net's fp16 forward packs [3 dx][8 kchunks][192 rows][8 ci] (written by train_conv0_kernel this step)
+    packed_w1 = ta.wpack + size_t(net * 2 + 0) * 2 * kWPackBytes;
+    packed_w2 = ta.wpack + size_t(net * 2 + 1) * 2 * kWPackBytes;
+  }
+  {    // weights -> smem (already in UMMA layout), zero the activation planes, biases
     const uint4* g1 = reinterpret_cast<const uint4*>(packed_w1);
     const uint4* g2 = reinterpret_cast<const uint4*>(packed_w2);
     uint4* s1 = reinterpret_cast<uint4*>(smem + Cfg::S_W1);

@@ -76,13 +76,10 @@ train_conv_bwd_kernel(ConvBwdArgs a) {
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < 16 * C::CH / 16; i += kBwdThreads) z[i] = make_uint4(0, 0, 0, 0);
-    // fp32 [co][ci][dy][dx] -> fp16 [tap][ci chunk][co][8 ci]
-    const float* wg = a.wgt[net];
-    __half* sw = reinterpret_cast<__half*>(smem + C::S_W);
-    for (int i = tid; i < 64 * 64 * 9; i += kBwdThreads) {
-      const int co = i / 576, r = i - co * 576, ci = r / 9, t = r - ci * 9;
-      sw[((t * 8 + (ci >> 3)) * 64 + co) * 8 + (ci & 7)] = __float2half_rn(__ldg(wg + i));
-    }
+    // fp16 [tap][ci chunk][co][8 ci], packed by train_conv0_kernel this step
+    const uint4* wg = reinterpret_cast<const uint4*>(a.wpack[net]);
+    uint4* sw = reinterpret_cast<uint4*>(smem + C::S_W);
+    for (int i = tid; i < C::WBYTES / 16; i += kBwdThreads) sw[i] = __ldg(wg + i);
     if (tid < 128) reinterpret_cast<__half*>(smem + C::S_ONES)[tid] = __float2half_rn(1.f);
   }
   if (tid == 0) {
@@ -260,8 +257,9 @@ train_conv_bwd_kernel(ConvBwdArgs a) {
     if (nsamp > 0) {
       mbar_wait(bars + 8 * BB_W_DONE, (nsamp - 1) & 1, 54);
       tc_fence_after();
+      // staged as [tap][co][ci]: a thread's 32 accumulator columns are 32 consecutive ci -> eight 16-byte vector reds
       const int set = lane >> 4, co = q4 * 16 + (lane & 15);
-      float* gw = a.g_w[net] + co * 576;
+      float* gs = a.g_stage[net] + co * 64 + chalf * 32;
 #pragma unroll 1
       for (int j = 0; j < 5; ++j) {
         float v[32];
@@ -271,7 +269,9 @@ train_conv_bwd_kernel(ConvBwdArgs a) {
         const int tap = set * 5 + j;
         if (tap < 9) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) atomicAdd(gw + (chalf * 32 + c) * 9 + tap, v[c] * invS);
+          for (int c = 0; c < 32; c += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gs + tap * 4096 + c), "f"(v[c] * invS),
+                         "f"(v[c + 1] * invS), "f"(v[c + 2] * invS), "f"(v[c + 3] * invS) : "memory");
         } else if (tap == 9 && chalf == 0) {
           atomicAdd(a.g_b[net] + co, v[0] * invS);
         }
@@ -328,6 +328,12 @@ train_conv0_bwd_kernel(Conv0BwdArgs a) {
   const int nsamp = k_end - k_begin;
   const int64_t s0 = int64_t(net) * a.nb + k_begin;
   reinterpret_cast<__half*>(smem + S_ONES)[tid] = __float2half_rn(1.f);
+  // the 3x3 weight gradients train_conv_bwd_kernel staged as [net][conv][tap][co][ci] -> torch's [co][ci][3][3]
+  for (int i = blockIdx.x * 128 + tid; i < 4 * 36864; i += int(gridDim.x) * 128) {
+    const int t4 = i / 36864, j = i - t4 * 36864;                   // j = (tap * 64 + co) * 64 + ci, coalesced read
+    const int tap = j >> 12, co = (j >> 6) & 63, ci = j & 63;
+    a.g_w3[t4 >> 1][t4 & 1][(co * 64 + ci) * 9 + tap] = __ldg(a.gstage + i);
+  }
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(bars + 8 * i, 1);
     fence_barrier_init();

@@ -17,9 +17,10 @@ constexpr int kAct2Bytes = 8 * kTPos2 * 16;   // p1 of one sample: 12 800 B
 constexpr int kCatDim = 64 * 25 + 1024;       // 2624 (tools/models.py:127)
 constexpr int kConvFeat = 64 * 25;
 constexpr int kHid = 1024;
+constexpr int kWPackBytes = 9 * 64 * 64 * 2;  // one 3x3 conv's weights in fp16: 73 728 B
 
 struct TrainWs {
-  size_t x16, a0, p1, m1, m2, cat, dmask, ynoisy, norm, dlogits, dfeat, dcat, dhp, dz1, da0, S, G, dG, probs_orig, total;
+  size_t x16, a0, p1, m1, m2, cat, dmask, ynoisy, norm, dlogits, dfeat, dcat, dhp, dz1, da0, S, G, dG, probs_orig, wpack, gstage, total;
 };
 __host__ __device__ inline TrainWs train_ws_layout(int bs, int btu, int B, int C, int queue) {
   TrainWs L;
@@ -45,6 +46,8 @@ __host__ __device__ inline TrainWs train_ws_layout(int bs, int btu, int B, int C
   L.G = take(size_t(btu) * btu * 4);
   L.dG = take(size_t(btu) * btu * 4);
   L.probs_orig = take(size_t(2) * btu * C * 4);
+  L.wpack = take(size_t(8) * kWPackBytes);     // fp16 3x3 weights [net][conv1|conv2][forward | backward layout]
+  L.gstage = take(size_t(4) * 36864 * 4);      // fp32 3x3 weight gradients [net][conv1|conv2][tap][co][ci] (vector reds)
   L.total = o;
   return L;
 }

@@ -54,6 +54,16 @@ train_conv0_kernel(Conv0Args a) {
     if (tid < 12) a.hist[tid] = 0.f;
     if (tid == 12) a.prm_rw->grad_amax = 0.f;
   }
+  // ---- this CTA's slice of the 3x3 weights -> fp16 packs: forward layout [3 dx][8 kchunks][192 rows = (2-dy)*64 + co][8 ci]
+  //      (conv_pair_issue.cuh) and backward layout [tap][ci chunk][co][8 ci] (train_bwd_sm100.cu)
+  for (int i = s * THREADS + tid; i < 4 * 36864; i += int(gridDim.x) * THREADS) {
+    const int t4 = i / 36864, j = i - t4 * 36864;                 // t4 = net * 2 + conv
+    const int co = j / 576, r = j - co * 576, ci = r / 9, t = r - ci * 9, dy = t / 3, dx = t - dy * 3;
+    const __half h = __float2half_rn(__ldg(a.w3[t4 >> 1][t4 & 1] + j));
+    __half* base = reinterpret_cast<__half*>(a.wpack + size_t(t4) * 2 * kWPackBytes);
+    base[((dx * 8 + (ci >> 3)) * 192 + (2 - dy) * 64 + co) * 8 + (ci & 7)] = h;
+    base[kWPackBytes / 2 + ((t * 8 + (ci >> 3)) * 64 + co) * 8 + (ci & 7)] = h;
+  }
   // ---- spectral input: gather + noise (fp32, consumed by the feat_spe GEMM)
   {
     const float sigma = a.prm->noise_scale;
@@ -82,34 +92,53 @@ train_conv0_kernel(Conv0Args a) {
     const float* nz = a.noise ? a.noise + int64_t(s) * 60 * kTPos : nullptr;
     unsigned char* xg = reinterpret_cast<unsigned char*>(a.x16) + int64_t(s) * kActBytes;
     const bool draw = a.cube && !nz && sigma != 0.f;
-    for (int i = tid; i < 16 * kTPos; i += THREADS) {
-      const int q = i / kTPos, p = i - q * kTPos;          // q: group of 4 channels, p: window position
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q < 15) {
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nz) {
-          z.x = __ldg(nz + (4 * q + 0) * kTPos + p); z.y = __ldg(nz + (4 * q + 1) * kTPos + p);
-          z.z = __ldg(nz + (4 * q + 2) * kTPos + p); z.w = __ldg(nz + (4 * q + 3) * kTPos + p);
-        } else if (draw) {
-          z = philox_normal4(seed, offset, PHILOX_PATCH, uint32_t(s) * 6000u + uint32_t(i));
-        }
-        if (a.cube) {
-          const int y = p / kTW, x = p - y * kTW;
-          const int sr = mirror_index(r - kTW / 2 + y, a.scene_rows), sc = mirror_index(c - kTW / 2 + x, a.cols);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(a.cube + (int64_t(sr) * a.cols + sc) * 60) + q);
-          // x + randn * noise: mul then add, two roundings like torch (train.py:157)
-          v.x = __fadd_rn(b.x, __fmul_rn(z.x, sigma)); v.y = __fadd_rn(b.y, __fmul_rn(z.y, sigma));
-          v.z = __fadd_rn(b.z, __fmul_rn(z.z, sigma)); v.w = __fadd_rn(b.w, __fmul_rn(z.w, sigma));
-        } else {
-          v = z;                                            // the caller passed the assembled patches
+    // 6400 items (16 channel quads x 400 positions) / 256 threads = 25 per thread, in batches of 5 with all global
+    // loads of a batch issued before any is consumed
+    constexpr int U = 5;
+#pragma unroll 1
+    for (int i0 = tid; i0 < 16 * kTPos; i0 += THREADS * U) {
+      float4 b[U], z[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * THREADS;
+        const int q = i / kTPos, p = i - q * kTPos;        // q: group of 4 channels, p: window position
+        b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        z[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < 15 * kTPos) {
+          if (nz) {
+            z[u].x = __ldg(nz + (4 * q + 0) * kTPos + p); z[u].y = __ldg(nz + (4 * q + 1) * kTPos + p);
+            z[u].z = __ldg(nz + (4 * q + 2) * kTPos + p); z[u].w = __ldg(nz + (4 * q + 3) * kTPos + p);
+          }
+          if (a.cube) {
+            const int y = p / kTW, x = p - y * kTW;
+            const int sr = mirror_index(r - kTW / 2 + y, a.scene_rows), sc = mirror_index(c - kTW / 2 + x, a.cols);
+            b[u] = __ldg(reinterpret_cast<const float4*>(a.cube + (int64_t(sr) * a.cols + sc) * 60) + q);
+          }
         }
       }
-      const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-      const int off = (q >> 1) * CH + p * 16 + (q & 1) * 8;
-      *reinterpret_cast<uint2*>(smem + S_X + off) = pk;
-      *reinterpret_cast<uint2*>(xg + off) = pk;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * THREADS;
+        if (i >= 16 * kTPos) continue;
+        const int q = i / kTPos, p = i - q * kTPos;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < 15) {
+          if (draw) z[u] = philox_normal4(seed, offset, PHILOX_PATCH, uint32_t(s) * 6000u + uint32_t(i));
+          if (a.cube) {
+            // x + randn * noise: mul then add, two roundings like torch (train.py:157)
+            v.x = __fadd_rn(b[u].x, __fmul_rn(z[u].x, sigma)); v.y = __fadd_rn(b[u].y, __fmul_rn(z[u].y, sigma));
+            v.z = __fadd_rn(b[u].z, __fmul_rn(z[u].z, sigma)); v.w = __fadd_rn(b[u].w, __fmul_rn(z[u].w, sigma));
+          } else {
+            v = z[u];                                       // the caller passed the assembled patches
+          }
+        }
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        const int off = (q >> 1) * CH + p * 16 + (q & 1) * 8;
+        *reinterpret_cast<uint2*>(smem + S_X + off) = pk;
+        *reinterpret_cast<uint2*>(xg + off) = pk;
+      }
     }
   }
   fence_proxy_async();

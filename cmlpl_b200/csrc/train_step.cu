@@ -27,7 +27,7 @@ extern "C" int cmlpl_train_workspace_layout(int bs, int btu, int bands, int clas
   CMLPL_CHECK_ARG(offsets && bs > 0 && btu > 0 && bands > 0 && classes > 0 && queue > 0, "train_workspace_layout: bad args");
   const TrainWs L = train_ws_layout(bs, btu, bands, classes, queue);
   const size_t v[20] = {L.x16, L.a0, L.p1, L.m1, L.m2, L.cat, L.dmask, L.ynoisy, L.norm, L.dlogits,
-                        L.dfeat, L.dcat, L.dhp, L.dz1, L.da0, L.S, L.G, L.dG, L.probs_orig, L.total};
+                        L.dfeat, L.dcat, L.dhp, L.dz1, L.da0, L.S, L.G, L.dG, L.probs_orig, L.total};   // (+ wpack, gstage: internal)
   for (int i = 0; i < 20; ++i) offsets[i] = v[i];
   return CMLPL_OK;
 }
@@ -83,14 +83,16 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
     a.prm = prm; a.x16 = f16(L.x16); a.a0 = f16(L.a0); a.nb = nb;
     a.spectra = io->spectra; a.spec_row = io->spec_row; a.spec_noise = io->spec_noise; a.ynoisy = f32(L.ynoisy); a.bands = B;
     a.hist = io->hist; a.prm_rw = io->params;
+    a.wpack = ws + L.wpack;
     TrainCnnArgs t{};
-    t.a0 = f16(L.a0); t.p1 = f16(L.p1); t.m1 = reinterpret_cast<uint32_t*>(ws + L.m1);
+    t.a0 = f16(L.a0); t.wpack = ws + L.wpack; t.p1 = f16(L.p1); t.m1 = reinterpret_cast<uint32_t*>(ws + L.m1);
     t.m2 = reinterpret_cast<uint32_t*>(ws + L.m2); t.cat = f32(L.cat); t.nb = nb;
     MultiGemm mg{};
     mg.count = 2;
     for (int e = 0; e < 2; ++e) {
       a.w0[e] = io->net[e].p[0]; a.b0[e] = io->net[e].p[1];
-      t.w1[e] = io->net[e].p[2]; t.b1[e] = io->net[e].p[3]; t.w2[e] = io->net[e].p[4]; t.b2[e] = io->net[e].p[5];
+      a.w3[e][0] = io->net[e].p[2]; a.w3[e][1] = io->net[e].p[4];
+      t.b1[e] = io->net[e].p[3]; t.b2[e] = io->net[e].p[5];
       // h = relu(feat_spe(y)) into the tail of cat (models.py:142-144)
       mg.p[e] = GemmProb{f32(L.ynoisy) + int64_t(e) * nb * B, B, 1, io->net[e].p[6], 1, B,
                          f32(L.cat) + int64_t(e) * nb * kCatDim + kConvFeat, kCatDim, 1, io->net[e].p[7], nullptr,
@@ -142,6 +144,7 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
         for (int i = 0; i < CMLPL_TRAIN_TENSORS; ++i)
           CMLPL_CUDA(cudaMemsetAsync(io->net[e].g[i], 0, size_t(numel(i, B, C)) * 4, st));
     }
+    CMLPL_CUDA(cudaMemsetAsync(ws + L.gstage, 0, size_t(4) * 36864 * 4, st));
     if ((rc = launch_head_bwd(ha, st)) != CMLPL_OK) return rc;
     if ((rc = launch_head_wgrad(ha, st)) != CMLPL_OK) return rc;
     MultiGemm dws{};
@@ -153,14 +156,17 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
     b2.dcat = f32(L.dcat); b2.m2 = reinterpret_cast<const uint32_t*>(ws + L.m2);
     b2.m1 = reinterpret_cast<const uint32_t*>(ws + L.m1); b2.act = f16(L.p1); b2.dz_out = f16(L.dz1);
     b1.act = f16(L.a0); b1.dz_in = f16(L.dz1); b1.dz_out = f16(L.da0);
-    b0.da0 = f16(L.da0); b0.x16 = f16(L.x16);
+    b0.da0 = f16(L.da0); b0.x16 = f16(L.x16); b0.gstage = f32(L.gstage);
     for (int e = 0; e < 2; ++e) {
       // dWs[j][b] = sum_s dhp[s][j] * y[s][b]  (feat_spe weight gradient)
       dws.p[e] = GemmProb{f32(L.dhp) + int64_t(e) * nb * kHid, 1, kHid, f32(L.ynoisy) + int64_t(e) * nb * B, B, 1,
                           io->net[e].g[6], B, 1, nullptr, nullptr, kHid, B, nb, 1.f, 0};
-      b2.wgt[e] = io->net[e].p[4]; b2.g_w[e] = io->net[e].g[4]; b2.g_b[e] = io->net[e].g[5];
-      b1.wgt[e] = io->net[e].p[2]; b1.g_w[e] = io->net[e].g[2]; b1.g_b[e] = io->net[e].g[3];
+      b2.wpack[e] = ws + L.wpack + size_t(e * 2 + 1) * 2 * kWPackBytes + kWPackBytes;
+      b1.wpack[e] = ws + L.wpack + size_t(e * 2 + 0) * 2 * kWPackBytes + kWPackBytes;
+      b2.g_stage[e] = f32(L.gstage) + size_t(e * 2 + 1) * 36864; b2.g_b[e] = io->net[e].g[5];
+      b1.g_stage[e] = f32(L.gstage) + size_t(e * 2 + 0) * 36864; b1.g_b[e] = io->net[e].g[3];
       b0.g_w[e] = io->net[e].g[0]; b0.g_b[e] = io->net[e].g[1];
+      b0.g_w3[e][0] = io->net[e].g[2]; b0.g_w3[e][1] = io->net[e].g[4];
     }
     if ((rc = launch_multi_gemm(dws, st, "train_spectral_wgrad")) != CMLPL_OK) return rc;
     if ((rc = launch_train_conv_bwd(10, b2, st)) != CMLPL_OK) return rc;
