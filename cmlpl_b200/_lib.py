@@ -70,6 +70,11 @@ SIGNATURES = {
     "cmlpl_graph_contrast_f32": (I, [P, P, P, P, L, I, I, F, I, F, P, P, P, P]),
     "cmlpl_ntxent_f32": (I, [P, L, I, F, P, P, P, P]),
     "cmlpl_adam_multi_f32": (I, [I, P, P, P, P, P, F, F, F, F, I, P]),
+    "cmlpl_comm_unique_id": (I, [P]),
+    "cmlpl_comm_init": (I, [I, I, P, P]),
+    "cmlpl_comm_allgather_labels": (I, [P, P, L, P, P]),
+    "cmlpl_comm_allreduce_confusion": (I, [P, P, I, P]),
+    "cmlpl_comm_destroy": (I, [P]),
     "cmlpl_train_workspace_bytes": (Z, [I, I, I, I, I]),
     "cmlpl_train_workspace_layout": (I, [I, I, I, I, I, P]),
     "cmlpl_train_step": (I, [P, I, P]),

@@ -4,8 +4,8 @@ conventions and side effects (in-place mutation of ``target`` and of the memory 
 
 On the per-pixel ``[N, C]`` shapes of this path ``compute_unsupervised_loss`` runs on the
 libcmlpl_sm100.so kernels (row entropy, masked cross entropy forward+backward); the percentile is
-taken from a device sort and interpolated like ``np.percentile`` (the reference does a full D2H +
-numpy sort there).  The segmentation-style 4-D criteria (Criterion*, Ohem*) and the ReCo memory-bank
+taken from a device sort and interpolated like ``np.percentile`` entirely on the device -- no host
+synchronisation (the reference does a full D2H + numpy sort there).  The segmentation-style 4-D criteria (Criterion*, Ohem*) and the ReCo memory-bank
 loss are bookkeeping-heavy and shape-incompatible with the hot path; they are kept as thin device
 tensor code that routes every cross entropy through the same kernel.
 """
@@ -38,19 +38,19 @@ def _flatten_nchw(pred):
     return pred.permute(0, 2, 3, 1).reshape(b * h * w, c)
 
 
-def _percentile_linear(sorted_vals: torch.Tensor, q: float) -> float:
-    """np.percentile(..., q) (linear interpolation) from an ascending device tensor."""
-    n = sorted_vals.numel()
-    pos = (n - 1) * (q / 100.0)
-    lo = int(np.floor(pos))
-    hi = min(lo + 1, n - 1)
-    a, b = (float(v) for v in sorted_vals[[lo, hi]].tolist())
-    # numpy's _lerp: a + (b - a) * t, switched to b - (b - a) * (1 - t) for t >= 0.5
-    t = pos - lo
-    out = a + (b - a) * t
-    if t >= 0.5:
-        out = b - (b - a) * (1 - t)
-    return float(np.float32(out)) if sorted_vals.dtype == torch.float32 else out
+def _percentile_linear(values: torch.Tensor, valid: torch.Tensor, q: float) -> torch.Tensor:
+    """np.percentile(values[valid], q) (linear interpolation) as a 0-dim DEVICE tensor, with no host synchronisation:
+    invalid entries sort to the end as +inf, the interpolation position comes from the device-side count.  The lerp
+    is numpy's (``a + (b-a)*t``, switched to ``b - (b-a)*(1-t)`` for t >= 0.5) in float64, rounded to the input dtype."""
+    srt = torch.sort(torch.where(valid, values, torch.full_like(values, float("inf"))))[0]
+    n = valid.sum()
+    pos = (n - 1).double() * (q / 100.0)
+    lo = torch.floor(pos).long().clamp(min=0)
+    hi = torch.minimum(lo + 1, (n - 1).clamp(min=0))
+    a, b = srt[lo].double(), srt[hi].double()
+    t = pos - lo.double()
+    out = torch.where(t >= 0.5, b - (b - a) * (1 - t), a + (b - a) * t)
+    return out.to(values.dtype)
 
 
 # ------------------------------------------------------------------ loss_helper.py:19-36
@@ -76,8 +76,8 @@ def compute_unsupervised_loss(predict, target, percent, pred_teacher):
     with torch.no_grad():
         entropy = ops.softmax_entropy(pred_teacher.detach().contiguous().float(), 1e-10)
         valid = target != IGNORE
-        thresh = _percentile_linear(torch.sort(entropy[valid])[0], percent)
-        target[entropy.ge(thresh) & valid] = IGNORE
+        thresh = _percentile_linear(entropy, valid, percent)            # device scalar: the reference syncs here
+        target.masked_fill_(entropy.ge(thresh) & valid, IGNORE)
         weight = batch_size / torch.sum(target != IGNORE)
     return weight * _masked_ce(predict, target)
 

@@ -83,3 +83,47 @@ def sharded_scene_labels(infer_band, scene_rows: int, cols: int, labels_true: to
     if labels_true is not None and confusion_fn is not None:
         cm = reduce_confusion(confusion_fn(local, labels_true[r0 * cols:r1 * cols], num_classes), group)
     return gather_label_map(local, scene_rows, cols, group), cm
+
+
+class CComm:
+    """The C-ABI communicator (cmlpl_comm_*: NCCL resolved inside libcmlpl_sm100.so) for hosts without
+    torch.distributed.  ``CComm.unique_id()`` on rank 0 -> 128 bytes to hand to every rank -> ``CComm(rank, world, id)``."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes):
+        import ctypes
+        from . import _lib
+        self._lib, self._ct = _lib, ctypes
+        self.rank, self.world = rank, world
+        self._h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        _lib.call("cmlpl_comm_init", rank, world, buf, ctypes.byref(self._h))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes
+        from . import _lib
+        buf = ctypes.create_string_buffer(128)
+        _lib.call("cmlpl_comm_unique_id", buf)
+        return buf.raw
+
+    def gather_label_map(self, local_labels: torch.Tensor, scene_rows: int, cols: int) -> torch.Tensor:
+        per = -(-scene_rows // self.world) * cols
+        src = local_labels
+        if local_labels.numel() != per:
+            src = torch.zeros(per, dtype=torch.uint8, device=local_labels.device)
+            src[: local_labels.numel()] = local_labels
+        out = torch.empty(self.world * per, dtype=torch.uint8, device=local_labels.device)
+        self._lib.call("cmlpl_comm_allgather_labels", self._h, src.data_ptr(), per, out.data_ptr(),
+                       self._ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return out[: scene_rows * cols]
+
+    def reduce_confusion(self, cm: torch.Tensor) -> torch.Tensor:
+        assert cm.dtype == torch.int64 and cm.is_cuda and cm.is_contiguous()
+        self._lib.call("cmlpl_comm_allreduce_confusion", self._h, cm.data_ptr(), cm.numel(),
+                       self._ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return cm
+
+    def close(self):
+        if self._h:
+            self._lib.call("cmlpl_comm_destroy", self._h)
+            self._h = self._ct.c_void_p()

@@ -319,6 +319,23 @@ int cmlpl_adam_multi_f32(int n_tensors, float* const* p_host, const float* const
                          cmlpl_stream_t stream);
 
 
+/* ------------------------------------------------------------- collectives --
+ * The two exchanges at the end of a row-band sharded scene inference, for hosts that do not bring their
+ * own process group (the Python layer of this repo uses torch.distributed): NCCL over NVLink, one communicator per
+ * process / device, resolved at run time from libnccl.so.2.
+ *   cmlpl_comm_unique_id        rank 0 fills id128 (128 bytes), the host hands it to the other ranks
+ *   cmlpl_comm_init             collective over all ranks; *out is owned by the caller until cmlpl_comm_destroy
+ *   cmlpl_comm_allgather_labels out u8 [world * per_rank] <- every rank's local u8 [per_rank] (bands padded to the
+ *                               common height, hyper_tools.py:426-431 label map in raster order)
+ *   cmlpl_comm_allreduce_confusion  cm i64 [count] summed in place (hyper_tools.py:208-223 counts) */
+typedef struct cmlpl_comm cmlpl_comm;
+int cmlpl_comm_unique_id(void* id128);
+int cmlpl_comm_init(int rank, int world, const void* id128, cmlpl_comm** out);
+int cmlpl_comm_allgather_labels(cmlpl_comm* comm, const uint8_t* local, int64_t per_rank, uint8_t* out,
+                                cmlpl_stream_t stream);
+int cmlpl_comm_allreduce_confusion(cmlpl_comm* comm, int64_t* cm, int count, cmlpl_stream_t stream);
+int cmlpl_comm_destroy(cmlpl_comm* comm);
+
 /* ------------------------------------------------------- fused training step --
  * One mutual-learning step of train.py:150-272 for BOTH BaseNet2 peers as ~17 kernel launches on `stream`
  * (CUDA-graph capturable: every per-step scalar lives in the device-side cmlpl_train_params block).
