@@ -9,6 +9,23 @@
 using namespace cmlpl;
 
 namespace {
+// Fork / join inside the step: kernels without a mutual dependency (the spectral GEMM next to the conv trunk; the head
+// weight gradients next to the conv backward chain) run on a side stream between two events.  Works the same in eager
+// mode and under stream capture (the events become graph edges).  One side stream + four events per device, created
+// on first use and kept for the life of the process -- the only persistent resources the library owns.
+struct StepStreams { cudaStream_t side = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; };
+StepStreams* step_streams() {
+  static StepStreams per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  StepStreams& s = per_dev[dev];
+  if (!s.side) {
+    if (cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : s.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
 constexpr int64_t kNumel[CMLPL_TRAIN_TENSORS] = {64 * 60, 64, 64 * 64 * 9, 64, 64 * 64 * 9, 64, 0 /*1024*B*/, 1024, 0 /*C*2624*/, 0 /*C*/};
 int64_t numel(int i, int B, int C) {
   if (i == 6) return int64_t(1024) * B;
@@ -61,6 +78,8 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
                       (!io->drop_mask || reinterpret_cast<uintptr_t>(io->drop_mask) % 16 == 0),
                   "train_step: feat / cube / drop_mask must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StepStreams* ss = step_streams();
+  CMLPL_CHECK_ARG(ss, "train_step: could not create the side stream");
   unsigned char* ws = static_cast<unsigned char*>(io->work);
   auto f32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto f16 = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
@@ -99,8 +118,13 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
                          nb, kHid, B, 1.f, 1};
     }
     if ((rc = launch_train_conv0(a, st)) != CMLPL_OK) return rc;
+    // fork: the spectral GEMM (needs only the noisy spectra of kernel 1) next to the conv trunk
+    CMLPL_CUDA(cudaEventRecord(ss->ev[0], st));
+    CMLPL_CUDA(cudaStreamWaitEvent(ss->side, ss->ev[0], 0));
+    if ((rc = launch_multi_gemm(mg, ss->side, "train_spectral_fwd")) != CMLPL_OK) return rc;
+    CMLPL_CUDA(cudaEventRecord(ss->ev[1], ss->side));
     if ((rc = launch_train_cnn(t, st)) != CMLPL_OK) return rc;
-    if ((rc = launch_multi_gemm(mg, st, "train_spectral_fwd")) != CMLPL_OK) return rc;
+    CMLPL_CUDA(cudaStreamWaitEvent(st, ss->ev[1], 0));
     if ((rc = launch_head_fwd(ha, st)) != CMLPL_OK) return rc;
   }
 
@@ -146,7 +170,6 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
     }
     CMLPL_CUDA(cudaMemsetAsync(ws + L.gstage, 0, size_t(4) * 36864 * 4, st));
     if ((rc = launch_head_bwd(ha, st)) != CMLPL_OK) return rc;
-    if ((rc = launch_head_wgrad(ha, st)) != CMLPL_OK) return rc;
     MultiGemm dws{};
     dws.count = 2;
     ConvBwdArgs b2{}, b1{};
@@ -168,10 +191,16 @@ extern "C" int cmlpl_train_step(const cmlpl_train_io* io, int phases, cmlpl_stre
       b0.g_w[e] = io->net[e].g[0]; b0.g_b[e] = io->net[e].g[1];
       b0.g_w3[e][0] = io->net[e].g[2]; b0.g_w3[e][1] = io->net[e].g[4];
     }
-    if ((rc = launch_multi_gemm(dws, st, "train_spectral_wgrad")) != CMLPL_OK) return rc;
+    // fork: the head weight gradients (classifier, feat_spe) next to the conv backward chain
+    CMLPL_CUDA(cudaEventRecord(ss->ev[2], st));
+    CMLPL_CUDA(cudaStreamWaitEvent(ss->side, ss->ev[2], 0));
+    if ((rc = launch_head_wgrad(ha, ss->side)) != CMLPL_OK) return rc;
+    if ((rc = launch_multi_gemm(dws, ss->side, "train_spectral_wgrad")) != CMLPL_OK) return rc;
+    CMLPL_CUDA(cudaEventRecord(ss->ev[3], ss->side));
     if ((rc = launch_train_conv_bwd(10, b2, st)) != CMLPL_OK) return rc;
     if ((rc = launch_train_conv_bwd(20, b1, st)) != CMLPL_OK) return rc;
     if ((rc = launch_train_conv0_bwd(b0, st)) != CMLPL_OK) return rc;
+    CMLPL_CUDA(cudaStreamWaitEvent(st, ss->ev[3], 0));
   }
 
   if (phases & 8) {
