@@ -1,0 +1,224 @@
+// conv0 of the scene path on tcgen05: F0 = W . x + b once per PADDED scene position (tools/models.py:102,132 applied to
+// the mirror-padded cube, hyper_tools.py:35-55) -> chunk-planar fp16 map [8 chunks][prow_n][pcol_n][8].
+// x is either the 60-channel PCA cube (float) or the RAW cube (uint16 / float, K = B bands) with the PCA projection and
+// both z-scores folded into W: F0 = Wf . (x - mu) + bf.
+//
+// Persistent CTAs over tiles of 128 consecutive padded positions.  The 256 worker threads read a tile's source pixels
+// (mirrored index map, K contiguous values per pixel: fully coalesced), round to fp16 and write the UMMA K-major tile
+// [K/8 chunks][128 positions][8] straight into shared memory (two stages); one thread issues K/16 tcgen05.mma
+// (M=128, N=64) per tile into one of two TMEM slots; the same workers drain the previous tile (+bias -> fp16 -> F0,
+// 16-byte stores coalesced along positions) while their loads for the next tile are in flight.
+// Replaces the CUDA-core conv0_tiled_kernel of round 1 (L1-wavefront bound on the strided pixel rows).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cmlpl {
+
+namespace c0s {
+constexpr int kWorkers = 256, kThreads = kWorkers + 32;
+enum { X_FULL0 = 0, X_EMPTY0 = 2, D_FULL0 = 4, D_EMPTY0 = 6 };
+}  // namespace c0s
+
+template <typename T, bool kVec4>
+__global__ void __launch_bounds__(c0s::kThreads, 1)
+conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int cols, int slab_row0, int w, int band_row0,
+                int prow_n, int pcol_n, const float* __restrict__ wt /* [K][64] */, const float* __restrict__ bias,
+                const float* __restrict__ mu, const float* __restrict__ inv_sigma, __half* __restrict__ f0pad) {
+  using namespace c0s;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const int KC = KP / 8;
+  // X chunk planes are 2048 + 16 bytes apart (LBO = 2064): consecutive chunks start 16 B further along the banks, so
+  // the loaders' stores (one pixel's K values spread over the chunk planes) do not pile onto the same banks
+  constexpr int XCH = 2064;
+  const int wbytes = KC * 64 * 16, xbytes = (KC * XCH + 127) / 128 * 128;
+  const int S_W = 0, S_X = wbytes, S_BIAS = S_X + 2 * xbytes, S_MU = S_BIAS + 256, S_BAR = S_MU + ((KP * 4 + 127) / 128) * 128;
+  const int S_TMEM = S_BAR + 64;
+  const uint32_t bars = sbase + S_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
+  float* smu = reinterpret_cast<float*>(smem + S_MU);      // per input channel: mean (raw cube) or 0
+  const int64_t plane = int64_t(prow_n) * pcol_n;
+  const int64_t ntiles = (plane + 127) / 128;
+  const int lo = window_lo(w);
+
+  // weights [K][64] f32 -> fp16 K-major B operand [KC][64 n][8 k], zero for k >= K
+  {
+    __half* sw = reinterpret_cast<__half*>(smem + S_W);
+    for (int i = tid; i < KP * 64; i += kThreads) {
+      const int k = i >> 6, n = i & 63;
+      // raw cube: the operand is z-scored per band ((x - mu) * inv_sigma ~ O(1)) and the band's sigma moves into the
+      // weight, so neither side of the product falls into fp16's subnormal range (folded weights alone are ~1e-5)
+      const float sc = (inv_sigma && k < K) ? 1.f / __ldg(inv_sigma + k) : 1.f;
+      sw[((k >> 3) * 64 + n) * 8 + (k & 7)] = __float2half_rn(k < K ? __ldg(wt + k * 64 + n) * sc : 0.f);
+    }
+    if (tid < 64) reinterpret_cast<float*>(smem + S_BIAS)[tid] = __ldg(bias + tid);
+    for (int i = tid; i < KP; i += kThreads) smu[i] = (mu && i < K) ? __ldg(mu + i) : 0.f;
+    // K padding of both X stages (k in [K, KP)) is written once: the loaders only touch k < K
+    if (KP > K) {
+      for (int i = tid; i < 2 * 128 * (KP - K); i += kThreads) {
+        const int st = i / (128 * (KP - K)), r = i - st * 128 * (KP - K);
+        const int pos = r / (KP - K), k = K + (r - pos * (KP - K));
+        *reinterpret_cast<__half*>(smem + S_X + st * xbytes + (k >> 3) * XCH + pos * 16 + (k & 7) * 2) = __float2half_rn(0.f);
+      }
+    }
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bars + 8 * (X_FULL0 + s), kWorkers);
+      mbar_init(bars + 8 * (X_EMPTY0 + s), 1);
+      mbar_init(bars + 8 * (D_FULL0 + s), 1);
+      mbar_init(bars + 8 * (D_EMPTY0 + s), kWorkers);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(sbase + S_TMEM, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t t_first = blockIdx.x, t_step = gridDim.x;
+
+  if (warp == 8) {
+    const uint32_t kI = make_idesc_f16(128, 64);
+    int it = 0;
+    for (int64_t t = t_first; t < ntiles; t += t_step, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(bars + 8 * (X_FULL0 + s), ph, 80);
+      mbar_wait(bars + 8 * (D_EMPTY0 + s), ph ^ 1, 81);
+      tc_fence_after();
+      if (lane == 0) {
+        for (int ks = 0; ks < KP / 16; ++ks)
+          umma_f16(tmem + s * 64, make_desc(sbase + S_X + s * xbytes + ks * 2 * XCH, XCH, 128),
+                   make_desc(sbase + S_W + ks * 2 * 1024, 1024, 128), kI, ks != 0 ? 1u : 0u);
+        umma_commit(bars + 8 * (X_EMPTY0 + s));
+        umma_commit(bars + 8 * (D_FULL0 + s));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q4 = warp & 3, chalf = warp >> 2;
+    const float* sb = reinterpret_cast<const float*>(smem + S_BIAS) + chalf * 32;
+    auto load_tile = [&](int64_t t, int it) {
+      const int s = it & 1;
+      mbar_wait(bars + 8 * (X_EMPTY0 + s), ((it >> 1) & 1) ^ 1, 82);
+      unsigned char* xs = smem + S_X + s * xbytes;
+      const int64_t p0 = t * 128;
+      auto src_of = [&](int pos) -> const T* {
+        int pp = int(p0) + pos; if (pp >= int(plane)) pp = int(plane) - 1;      // plane < 2^31 (checked by the launcher)
+        const int pr = pp / pcol_n, pc = pp - pr * pcol_n;
+        const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0, sc = mirror_index(pc + lo, cols);
+        return in + (int64_t(sr) * cols + sc) * K;
+      };
+      if constexpr (kVec4) {
+        // K = 60 floats, 16-byte aligned pixels: a half-warp reads one pixel (15 float4 on 15 lanes), 8 pixels per lane
+        // in flight; K % 4 == 0 and K <= 64
+        const int hw = lane >> 4, q = lane & 15, Q = K / 4;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pos = 2 * (warp + 8 * j) + hw;
+          v[j] = q < Q ? __ldg(reinterpret_cast<const float4*>(src_of(pos)) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (q < Q) {
+          const float m0 = smu[4 * q], m1 = smu[4 * q + 1], m2 = smu[4 * q + 2], m3 = smu[4 * q + 3];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pos = 2 * (warp + 8 * j) + hw;
+            const __half2 h0 = __floats2half2_rn(v[j].x - m0, v[j].y - m1), h1 = __floats2half2_rn(v[j].z - m2, v[j].w - m3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(xs + (q >> 1) * XCH + pos * 16 + (q & 1) * 8) = pk;
+          }
+        }
+      } else {
+        // scalar elements (uint16 / unaligned float rows): a warp reads one pixel (K values on consecutive lanes),
+        // z-scored on the way (per-lane mean / 1/sigma of its k's stay in registers); K <= 256
+        float mr[8], ir[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int k = lane + 32 * m;
+          mr[m] = k < K ? smu[k] : 0.f;
+          ir[m] = (inv_sigma && k < K) ? __ldg(inv_sigma + k) : 1.f;
+        }
+#pragma unroll 2
+        for (int j = 0; j < 16; ++j) {
+          const int pos = warp + 8 * j;
+          const T* src = src_of(pos);
+          float v[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int k = lane + 32 * m;
+            v[m] = k < K ? float(src[k]) : 0.f;
+          }
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int k = lane + 32 * m;
+            if (k < K)
+              *reinterpret_cast<__half*>(xs + (k >> 3) * XCH + pos * 16 + (k & 7) * 2) = __float2half_rn((v[m] - mr[m]) * ir[m]);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + 8 * (X_FULL0 + s));
+    };
+    int it = 0;
+    if (t_first < ntiles) load_tile(t_first, 0);
+    for (int64_t t = t_first; t < ntiles; t += t_step, ++it) {
+      if (t + t_step < ntiles) load_tile(t + t_step, it + 1);
+      const int s = it & 1;
+      mbar_wait(bars + 8 * (D_FULL0 + s), (it >> 1) & 1, 83);
+      tc_fence_after();
+      float v[32];
+      const uint32_t taddr = tmem + (uint32_t(q4 * 32) << 16) + s * 64 + chalf * 32;
+      tmem_ld16(taddr, v);
+      tmem_ld16(taddr + 16, v + 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bars + 8 * (D_EMPTY0 + s));
+      const int64_t p = t * 128 + q4 * 32 + lane;
+      if (p < plane) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          __half2 h[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            h[j] = __floats2half2_rn(v[c * 8 + 2 * j] + sb[c * 8 + 2 * j], v[c * 8 + 2 * j + 1] + sb[c * 8 + 2 * j + 1]);
+          *reinterpret_cast<uint4*>(f0pad + (int64_t(chalf * 4 + c) * plane + p) * 8) = *reinterpret_cast<uint4*>(h);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+template <typename T, bool kVec4>
+int launch_conv0_tc(const T* in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0, int prow_n, int pcol_n,
+                    const float* wt, const float* bias, const float* mu, const float* inv_sigma, __half* f0pad, cudaStream_t s) {
+  const int KP = (K + 15) / 16 * 16;
+  CMLPL_CHECK_ARG(KP <= 256 && (!kVec4 || (K % 4 == 0 && K <= 64)), "conv0: K=%d unsupported by the tensor-core kernel", K);
+  CMLPL_CHECK_ARG(int64_t(prow_n) * pcol_n < (int64_t(1) << 31) - 256, "conv0: band of %d x %d padded positions is too large",
+                  prow_n, pcol_n);
+  const int KC = KP / 8;
+  const size_t smem = size_t(KC) * 64 * 16 + 2 * ((size_t(KC) * 2064 + 127) / 128 * 128) + 256 + ((KP * 4 + 127) / 128) * 128 + 64 + 16 + 128;
+  auto kern = conv0_tc_kernel<T, kVec4>;
+  CMLPL_MAX_DYN_SMEM(kern, int(smem));
+  const int64_t ntiles = (int64_t(prow_n) * pcol_n + 127) / 128;
+  int grid = sm_count();
+  if (grid > ntiles) grid = int(ntiles);
+  kern<<<grid, c0s::kThreads, smem, s>>>(in, K, KP, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n, wt, bias, mu, inv_sigma, f0pad);
+  CMLPL_CHECK_LAUNCH("conv0_tc");
+  return CMLPL_OK;
+}
+
+template int launch_conv0_tc<float, true>(const float*, int, int, int, int, int, int, int, int, const float*, const float*,
+                                          const float*, const float*, __half*, cudaStream_t);
+template int launch_conv0_tc<float, false>(const float*, int, int, int, int, int, int, int, int, const float*, const float*,
+                                           const float*, const float*, __half*, cudaStream_t);
+template int launch_conv0_tc<uint16_t, false>(const uint16_t*, int, int, int, int, int, int, int, int, const float*,
+                                              const float*, const float*, const float*, __half*, cudaStream_t);
+
+}  // namespace cmlpl

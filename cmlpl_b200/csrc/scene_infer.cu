@@ -17,6 +17,15 @@
 namespace cmlpl {
 
 // ------------------------------------------------------------------ conv0 map
+// Two kernels: the 60-channel PCA cube (z-scored, well conditioned) goes through the tcgen05 kernel of conv0_sm100.cu;
+// the RAW cube keeps the fp32 CUDA-core kernel below, because folding the PCA projection into conv0 makes the
+// contraction ill-conditioned in fp16 -- the noise components of the PCA are differences of band values ~10x larger
+// than the result, so rounding the operands to 11 bits costs ~3e-3 of a z-scored feature (measured: the B = 200 raw
+// parity test misses the 1e-3 logit bar with fp16 operands and passes in fp32).
+template <typename T, bool kVec4>
+int launch_conv0_tc(const T* in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0, int prow_n, int pcol_n,
+                    const float* wt, const float* bias, const float* mu, const float* inv_sigma, __half* f0pad, cudaStream_t s);
+
 // conv0 (1x1) once per PADDED scene position, fp32 FFMA, register-tiled: a thread owns 4 consecutive padded
 // positions x 16 output channels (64 accumulators; per input channel 4 loaded inputs + 4 broadcast LDS.128 of
 // weights feed 64 FMAs), the 4 warps of a half-block share the same 128 positions (inputs hit L1), weights
@@ -284,9 +293,9 @@ extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, 
   const PackedLayout L = packed_layout(1, 1, w);  // w0/b0 offsets do not depend on B, C
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
   const int prow_n = band_rows + w - 1, pcol_n = cols + w - 1;
-  return launch_conv0<float, true>(cube, 60, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n,
-                                   reinterpret_cast<const float*>(pk + L.w0), reinterpret_cast<const float*>(pk + L.b0), nullptr,
-                                   static_cast<__half*>(f0pad), static_cast<cudaStream_t>(stream));
+  return launch_conv0_tc<float, true>(cube, 60, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n,
+                                      reinterpret_cast<const float*>(pk + L.w0), reinterpret_cast<const float*>(pk + L.b0), nullptr,
+                                      nullptr, static_cast<__half*>(f0pad), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cmlpl_spectral_head_f32(const float* spectra, int64_t n, int num_features, int num_classes, int w,
