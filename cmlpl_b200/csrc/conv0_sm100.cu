@@ -19,9 +19,12 @@ constexpr int kWorkers = 256, kThreads = kWorkers + 32;
 enum { X_FULL0 = 0, X_EMPTY0 = 2, D_FULL0 = 4, D_EMPTY0 = 6 };
 }  // namespace c0s
 
-template <typename T, bool kVec4>
+// kSplit (raw cube): both operands are split into fp16 hi + lo parts and every K-step issues hi.hi + hi.lo + lo.hi
+// (~2^-21 relative error).  The folded PCA projection is ill-conditioned -- its noise components are differences of
+// band values ~10x larger than the result -- so single fp16 operands miss the 1e-3 logit bar (measured at B = 200).
+template <typename T, bool kVec4, bool kSplit>
 __global__ void __launch_bounds__(c0s::kThreads, 1)
-conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int cols, int slab_row0, int w, int band_row0,
+conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int nstage, int scene_rows, int cols, int slab_row0, int w, int band_row0,
                 int prow_n, int pcol_n, const float* __restrict__ wt /* [K][64] */, const float* __restrict__ bias,
                 const float* __restrict__ mu, const float* __restrict__ inv_sigma, __half* __restrict__ f0pad) {
   using namespace c0s;
@@ -32,8 +35,9 @@ conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int col
   // X chunk planes are 2048 + 16 bytes apart (LBO = 2064): consecutive chunks start 16 B further along the banks, so
   // the loaders' stores (one pixel's K values spread over the chunk planes) do not pile onto the same banks
   constexpr int XCH = 2064;
-  const int wbytes = KC * 64 * 16, xbytes = (KC * XCH + 127) / 128 * 128;
-  const int S_W = 0, S_X = wbytes, S_BIAS = S_X + 2 * xbytes, S_MU = S_BIAS + 256, S_BAR = S_MU + ((KP * 4 + 127) / 128) * 128;
+  const int whalf = KC * 64 * 16, xhalf = (KC * XCH + 127) / 128 * 128;
+  const int wbytes = whalf * (kSplit ? 2 : 1), xbytes = xhalf * (kSplit ? 2 : 1);      // [hi | lo]
+  const int S_W = 0, S_X = wbytes, S_BIAS = S_X + nstage * xbytes, S_MU = S_BIAS + 256, S_BAR = S_MU + ((KP * 4 + 127) / 128) * 128;
   const int S_TMEM = S_BAR + 64;
   const uint32_t bars = sbase + S_BAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
@@ -50,21 +54,25 @@ conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int col
       // raw cube: the operand is z-scored per band ((x - mu) * inv_sigma ~ O(1)) and the band's sigma moves into the
       // weight, so neither side of the product falls into fp16's subnormal range (folded weights alone are ~1e-5)
       const float sc = (inv_sigma && k < K) ? 1.f / __ldg(inv_sigma + k) : 1.f;
-      sw[((k >> 3) * 64 + n) * 8 + (k & 7)] = __float2half_rn(k < K ? __ldg(wt + k * 64 + n) * sc : 0.f);
+      const float wv = k < K ? __ldg(wt + k * 64 + n) * sc : 0.f;
+      const __half hi = __float2half_rn(wv);
+      sw[((k >> 3) * 64 + n) * 8 + (k & 7)] = hi;
+      if (kSplit) sw[whalf / 2 + ((k >> 3) * 64 + n) * 8 + (k & 7)] = __float2half_rn(wv - __half2float(hi));
     }
     if (tid < 64) reinterpret_cast<float*>(smem + S_BIAS)[tid] = __ldg(bias + tid);
     for (int i = tid; i < KP; i += kThreads) smu[i] = (mu && i < K) ? __ldg(mu + i) : 0.f;
     // K padding of both X stages (k in [K, KP)) is written once: the loaders only touch k < K
     if (KP > K) {
-      for (int i = tid; i < 2 * 128 * (KP - K); i += kThreads) {
+      const int nh = nstage * (kSplit ? 2 : 1);                 // hi / lo halves of every stage are xhalf apart
+      for (int i = tid; i < nh * 128 * (KP - K); i += kThreads) {
         const int st = i / (128 * (KP - K)), r = i - st * 128 * (KP - K);
         const int pos = r / (KP - K), k = K + (r - pos * (KP - K));
-        *reinterpret_cast<__half*>(smem + S_X + st * xbytes + (k >> 3) * XCH + pos * 16 + (k & 7) * 2) = __float2half_rn(0.f);
+        *reinterpret_cast<__half*>(smem + S_X + st * xhalf + (k >> 3) * XCH + pos * 16 + (k & 7) * 2) = __float2half_rn(0.f);
       }
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 2; ++s) {                              // (stage 1 is unused when nstage == 1)
       mbar_init(bars + 8 * (X_FULL0 + s), kWorkers);
       mbar_init(bars + 8 * (X_EMPTY0 + s), 1);
       mbar_init(bars + 8 * (D_FULL0 + s), 1);
@@ -84,15 +92,22 @@ conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int col
     const uint32_t kI = make_idesc_f16(128, 64);
     int it = 0;
     for (int64_t t = t_first; t < ntiles; t += t_step, ++it) {
-      const int s = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(bars + 8 * (X_FULL0 + s), ph, 80);
+      const int s = it & 1, ph = (it >> 1) & 1;                 // TMEM slot
+      const int xs_ = nstage == 2 ? s : 0, xph = nstage == 2 ? ph : (it & 1);   // X stage and its phase
+      mbar_wait(bars + 8 * (X_FULL0 + xs_), xph, 80);
       mbar_wait(bars + 8 * (D_EMPTY0 + s), ph ^ 1, 81);
       tc_fence_after();
       if (lane == 0) {
-        for (int ks = 0; ks < KP / 16; ++ks)
-          umma_f16(tmem + s * 64, make_desc(sbase + S_X + s * xbytes + ks * 2 * XCH, XCH, 128),
-                   make_desc(sbase + S_W + ks * 2 * 1024, 1024, 128), kI, ks != 0 ? 1u : 0u);
-        umma_commit(bars + 8 * (X_EMPTY0 + s));
+        const uint32_t xa = sbase + S_X + xs_ * xbytes, wa = sbase + S_W;
+        for (int ks = 0; ks < KP / 16; ++ks) {
+          umma_f16(tmem + s * 64, make_desc(xa + ks * 2 * XCH, XCH, 128), make_desc(wa + ks * 2 * 1024, 1024, 128), kI,
+                   ks != 0 ? 1u : 0u);
+          if (kSplit) {
+            umma_f16(tmem + s * 64, make_desc(xa + ks * 2 * XCH, XCH, 128), make_desc(wa + whalf + ks * 2 * 1024, 1024, 128), kI, 1u);
+            umma_f16(tmem + s * 64, make_desc(xa + xhalf + ks * 2 * XCH, XCH, 128), make_desc(wa + ks * 2 * 1024, 1024, 128), kI, 1u);
+          }
+        }
+        umma_commit(bars + 8 * (X_EMPTY0 + xs_));
         umma_commit(bars + 8 * (D_FULL0 + s));
       }
       __syncwarp();
@@ -101,8 +116,8 @@ conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int col
     const int q4 = warp & 3, chalf = warp >> 2;
     const float* sb = reinterpret_cast<const float*>(smem + S_BIAS) + chalf * 32;
     auto load_tile = [&](int64_t t, int it) {
-      const int s = it & 1;
-      mbar_wait(bars + 8 * (X_EMPTY0 + s), ((it >> 1) & 1) ^ 1, 82);
+      const int s = nstage == 2 ? (it & 1) : 0;
+      mbar_wait(bars + 8 * (X_EMPTY0 + s), (nstage == 2 ? ((it >> 1) & 1) : (it & 1)) ^ 1, 82);
       unsigned char* xs = smem + S_X + s * xbytes;
       const int64_t p0 = t * 128;
       auto src_of = [&](int pos) -> const T* {
@@ -142,21 +157,32 @@ conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int col
           mr[m] = k < K ? smu[k] : 0.f;
           ir[m] = (inv_sigma && k < K) ? __ldg(inv_sigma + k) : 1.f;
         }
-#pragma unroll 2
-        for (int j = 0; j < 16; ++j) {
-          const int pos = warp + 8 * j;
-          const T* src = src_of(pos);
-          float v[8];
+#pragma unroll 1
+        for (int j0 = 0; j0 < 16; j0 += 4) {                   // 4 pixels (up to 32 loads) in flight per lane
+          float v[4][8];
 #pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const int k = lane + 32 * m;
-            v[m] = k < K ? float(src[k]) : 0.f;
+          for (int jj = 0; jj < 4; ++jj) {
+            const T* src = src_of(warp + 8 * (j0 + jj));
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const int k = lane + 32 * m;
+              v[jj][m] = k < K ? float(src[k]) : 0.f;
+            }
           }
 #pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const int k = lane + 32 * m;
-            if (k < K)
-              *reinterpret_cast<__half*>(xs + (k >> 3) * XCH + pos * 16 + (k & 7) * 2) = __float2half_rn((v[m] - mr[m]) * ir[m]);
+          for (int jj = 0; jj < 4; ++jj) {
+            const int pos = warp + 8 * (j0 + jj);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const int k = lane + 32 * m;
+              if (k < K) {
+                const float z = (v[jj][m] - mr[m]) * ir[m];
+                const __half hi = __float2half_rn(z);
+                unsigned char* d = xs + (k >> 3) * XCH + pos * 16 + (k & 7) * 2;
+                *reinterpret_cast<__half*>(d) = hi;
+                if (kSplit) *reinterpret_cast<__half*>(d + xhalf) = __float2half_rn(z - __half2float(hi));
+              }
+            }
           }
         }
       }
@@ -166,7 +192,7 @@ conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int col
     int it = 0;
     if (t_first < ntiles) load_tile(t_first, 0);
     for (int64_t t = t_first; t < ntiles; t += t_step, ++it) {
-      if (t + t_step < ntiles) load_tile(t + t_step, it + 1);
+      if (t + t_step < ntiles) load_tile(t + t_step, it + 1);   // (waits for the stage: immediate with two stages)
       const int s = it & 1;
       mbar_wait(bars + 8 * (D_FULL0 + s), (it >> 1) & 1, 83);
       tc_fence_after();
@@ -195,7 +221,7 @@ conv0_tc_kernel(const T* __restrict__ in, int K, int KP, int scene_rows, int col
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
-template <typename T, bool kVec4>
+template <typename T, bool kVec4, bool kSplit>
 int launch_conv0_tc(const T* in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0, int prow_n, int pcol_n,
                     const float* wt, const float* bias, const float* mu, const float* inv_sigma, __half* f0pad, cudaStream_t s) {
   const int KP = (K + 15) / 16 * 16;
@@ -203,22 +229,27 @@ int launch_conv0_tc(const T* in, int K, int scene_rows, int cols, int slab_row0,
   CMLPL_CHECK_ARG(int64_t(prow_n) * pcol_n < (int64_t(1) << 31) - 256, "conv0: band of %d x %d padded positions is too large",
                   prow_n, pcol_n);
   const int KC = KP / 8;
-  const size_t smem = size_t(KC) * 64 * 16 + 2 * ((size_t(KC) * 2064 + 127) / 128 * 128) + 256 + ((KP * 4 + 127) / 128) * 128 + 64 + 16 + 128;
-  auto kern = conv0_tc_kernel<T, kVec4>;
+  const size_t xhalf = (size_t(KC) * 2064 + 127) / 128 * 128, mult = kSplit ? 2 : 1;
+  const size_t fixed = size_t(KC) * 64 * 16 * mult + 256 + ((KP * 4 + 127) / 128) * 128 + 64 + 16 + 128;
+  const int nstage = fixed + 2 * xhalf * mult <= 227 * 1024 ? 2 : 1;
+  const size_t smem = fixed + nstage * xhalf * mult;
+  CMLPL_CHECK_ARG(smem <= 227 * 1024, "conv0: K=%d does not fit shared memory", K);
+  auto kern = conv0_tc_kernel<T, kVec4, kSplit>;
   CMLPL_MAX_DYN_SMEM(kern, int(smem));
   const int64_t ntiles = (int64_t(prow_n) * pcol_n + 127) / 128;
   int grid = sm_count();
   if (grid > ntiles) grid = int(ntiles);
-  kern<<<grid, c0s::kThreads, smem, s>>>(in, K, KP, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n, wt, bias, mu, inv_sigma, f0pad);
+  kern<<<grid, c0s::kThreads, smem, s>>>(in, K, KP, nstage, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n, wt, bias, mu,
+                                         inv_sigma, f0pad);
   CMLPL_CHECK_LAUNCH("conv0_tc");
   return CMLPL_OK;
 }
 
-template int launch_conv0_tc<float, true>(const float*, int, int, int, int, int, int, int, int, const float*, const float*,
-                                          const float*, const float*, __half*, cudaStream_t);
-template int launch_conv0_tc<float, false>(const float*, int, int, int, int, int, int, int, int, const float*, const float*,
-                                           const float*, const float*, __half*, cudaStream_t);
-template int launch_conv0_tc<uint16_t, false>(const uint16_t*, int, int, int, int, int, int, int, int, const float*,
-                                              const float*, const float*, const float*, __half*, cudaStream_t);
+template int launch_conv0_tc<float, true, false>(const float*, int, int, int, int, int, int, int, int, const float*, const float*,
+                                                 const float*, const float*, __half*, cudaStream_t);
+template int launch_conv0_tc<float, false, true>(const float*, int, int, int, int, int, int, int, int, const float*, const float*,
+                                                 const float*, const float*, __half*, cudaStream_t);
+template int launch_conv0_tc<uint16_t, false, true>(const uint16_t*, int, int, int, int, int, int, int, int, const float*,
+                                                    const float*, const float*, const float*, __half*, cudaStream_t);
 
 }  // namespace cmlpl

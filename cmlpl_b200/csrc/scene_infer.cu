@@ -17,12 +17,12 @@
 namespace cmlpl {
 
 // ------------------------------------------------------------------ conv0 map
-// Two kernels: the 60-channel PCA cube (z-scored, well conditioned) goes through the tcgen05 kernel of conv0_sm100.cu;
-// the RAW cube keeps the fp32 CUDA-core kernel below, because folding the PCA projection into conv0 makes the
-// contraction ill-conditioned in fp16 -- the noise components of the PCA are differences of band values ~10x larger
-// than the result, so rounding the operands to 11 bits costs ~3e-3 of a z-scored feature (measured: the B = 200 raw
-// parity test misses the 1e-3 logit bar with fp16 operands and passes in fp32).
-template <typename T, bool kVec4>
+// tcgen05 kernel of conv0_sm100.cu: plain fp16 operands for the 60-channel PCA cube (z-scored, well conditioned); for
+// the RAW cube both operands are split into fp16 hi + lo parts (3 MMAs per K-step), because folding the PCA projection
+// into conv0 makes the contraction ill-conditioned in fp16 -- the noise components of the PCA are differences of band
+// values ~10x larger than the result (measured: with single fp16 operands the B = 200 raw parity test misses the 1e-3
+// logit bar).  The fp32 CUDA-core kernel below is kept for inputs the tensor-core kernel does not take.
+template <typename T, bool kVec4, bool kSplit>
 int launch_conv0_tc(const T* in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0, int prow_n, int pcol_n,
                     const float* wt, const float* bias, const float* mu, const float* inv_sigma, __half* f0pad, cudaStream_t s);
 
@@ -293,7 +293,7 @@ extern "C" int cmlpl_conv0_map_f16(const float* cube, int scene_rows, int cols, 
   const PackedLayout L = packed_layout(1, 1, w);  // w0/b0 offsets do not depend on B, C
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
   const int prow_n = band_rows + w - 1, pcol_n = cols + w - 1;
-  return launch_conv0_tc<float, true>(cube, 60, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n,
+  return launch_conv0_tc<float, true, false>(cube, 60, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n,
                                       reinterpret_cast<const float*>(pk + L.w0), reinterpret_cast<const float*>(pk + L.b0), nullptr,
                                       nullptr, static_cast<__half*>(f0pad), static_cast<cudaStream_t>(stream));
 }
@@ -442,10 +442,10 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
   {
     __half* f0 = reinterpret_cast<__half*>(wsb + ws.f0pad);
     const int rc0 = dtype == 0
-        ? launch_conv0<uint16_t, false>(static_cast<const uint16_t*>(raw), num_features, scene_rows, cols, slab_row0, w, band_row0,
-                                        prow_n, pcol_n, wf, bf, mu, f0, s)
-        : launch_conv0<float, false>(static_cast<const float*>(raw), num_features, scene_rows, cols, slab_row0, w, band_row0,
-                                     prow_n, pcol_n, wf, bf, mu, f0, s);
+        ? launch_conv0_tc<uint16_t, false, true>(static_cast<const uint16_t*>(raw), num_features, scene_rows, cols, slab_row0, w,
+                                                 band_row0, prow_n, pcol_n, wf, bf, mu, inv_sigma, f0, s)
+        : launch_conv0_tc<float, false, true>(static_cast<const float*>(raw), num_features, scene_rows, cols, slab_row0, w,
+                                              band_row0, prow_n, pcol_n, wf, bf, mu, inv_sigma, f0, s);
     if (rc0 != CMLPL_OK) return rc0;
   }
   const size_t esz = dtype == 0 ? 2 : 4;
