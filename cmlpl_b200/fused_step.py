@@ -218,10 +218,12 @@ class FusedMutualStep:
             self._views(bs, nb - bs)
         if cube is not None:
             chk(pix, (nb,), "pix")
-            if cube.dim() != 3 or cube.shape[2] != 60 or cube.dtype != torch.float32 or not cube.is_contiguous():
-                raise _lib.CmlplError("cube must be contiguous f32 [R, C, 60]")
-            if spectra is None or spectra.dim() != 2 or spectra.shape[1] != self.B or spectra.dtype != torch.float32:
-                raise _lib.CmlplError("spectra must be f32 [rows, B]")
+            if (not cube.is_cuda or cube.dim() != 3 or cube.shape[2] != 60 or cube.dtype != torch.float32 or
+                    not cube.is_contiguous()):
+                raise _lib.CmlplError("cube must be a contiguous CUDA f32 [R, C, 60] tensor (there is no CPU path)")
+            if (spectra is None or not spectra.is_cuda or spectra.dim() != 2 or spectra.shape[1] != self.B or
+                    spectra.dtype != torch.float32 or not spectra.is_contiguous()):
+                raise _lib.CmlplError("spectra must be a contiguous CUDA f32 [rows, B] tensor")
             self.pix[:nb].copy_(pix, non_blocking=True)
             if patch_noise is not None:
                 chk(patch_noise, (2, nb, 60, 20, 20), "patch_noise")

@@ -351,3 +351,57 @@ def test_tcgen05_similarity_gemm(dev, M, N):
     finally:
         _lib.call("cmlpl_set_loss_gemm_mode", 0)
     assert rel(tc[1], fp32[1]) < 1e-3 and torch.equal(tc[0], fp32[0])
+
+
+def test_fused_step_partial_batch_and_argument_checks(dev, golden_dir):
+    """train.py's DataLoaders keep the last partial batch (10 000 samples / 128 -> a 16-row tail): a FusedMutualStep built
+    for 128 + 128 runs a 16 + 16 step on the head of its buffers and matches the oracle; bad arguments fail loudly."""
+    from cmlpl_b200 import _lib
+    ti = np.load(os.path.join(golden_dir, "train_infer.npz"))
+    Xp, Xs = ti["cube_pca"], ti["spectra"]
+    B, K, bs = 103, 9, 16
+    g = torch.Generator().manual_seed(77)
+    R, C = Xp.shape[:2]
+    li = torch.randint(0, R * C, (bs,), generator=g).numpy(); ui = torch.randint(0, R * C, (bs,), generator=g).numpy()
+    XP_l = torch.from_numpy(O.extract_patches_at(Xp, 20, li)); XP_u = torch.from_numpy(O.extract_patches_at(Xp, 20, ui))
+    X_l = torch.from_numpy(Xs[li]); X_u = torch.from_numpy(Xs[ui])
+    Y_l = torch.randint(0, K, (bs,), generator=g)
+    torch.manual_seed(5)
+    sd, sd1 = O.basenet2_init(B, K), O.basenet2_init(B, K)
+    sa = O.StepArgs(num_epochs=20)
+    sa.thr = 0.12
+    ost = O.make_state(sd, sd1, K, sa)                                         # 1280-row banks like train.py:138
+    queues = [O.normalize(torch.randn(1280, 1024, generator=g).abs()), torch.softmax(torch.randn(1280, K, generator=g) * 2, 1),
+              O.normalize(torch.randn(1280, 1024, generator=g).abs()), torch.softmax(torch.randn(1280, K, generator=g) * 2, 1)]
+    for dst, src in zip((ost.queue_feats, ost.queue_probs, ost.queue_feats1, ost.queue_probs1), queues):
+        dst.copy_(src)
+    ost.queue_ptr, ost.queue_ptr1 = 1024, 0
+    zero = {k: torch.zeros(s) for k, s in (("xp_l1", XP_l.shape), ("x_l1", X_l.shape), ("xp_l2", XP_l.shape), ("x_l2", X_l.shape),
+                                           ("xp_u1", XP_u.shape), ("x_u1", X_u.shape), ("xp_u2", XP_u.shape), ("x_u2", X_u.shape))}
+    r = O.ref_step(ost, XP_l, X_l, Y_l, XP_u, X_u, zero, epoch=2, batch_index=78, args=sa)
+    fs = make_fused(dev, sd, sd1, B, K, queues, thr=sa.thr, num_epochs=sa.num_epochs, lr=sa.lr, temperature=sa.temperature,
+                    alpha=sa.alpha, queue_batch=sa.queue_batch, dropout=0.0, noise=0.0)          # built for 128 + 128
+    fs.queue_ptr, fs.queue_ptr1 = 1024, 0
+    cube = torch.from_numpy(Xp).to(dev).contiguous()
+    spectra = torch.from_numpy(Xs).to(dev).contiguous()
+    pix = torch.from_numpy(np.concatenate([li, ui])).to(dev)
+    hist = fs.step(Y_l.to(dev), 2, 78, cube=cube, pix=pix, spectra=spectra)
+    h = hist.cpu().numpy()
+    assert fs.logits.shape == (2, 32, K) and fs.mask.shape == (2, 16)
+    assert np.abs(h[:5] - r["hist"]).max() <= 1e-3 * np.abs(r["hist"]).max(), (h[:5], r["hist"])
+    assert rel(fs.logits[0], r["logits"]) < 1e-3 and rel(fs.probs[1], r["probs1"]) < 1e-3
+    for i, k in enumerate(HEAD):
+        assert rel(fs.grads[0][6 + i], r["grads"][k]) < 1e-3, k
+    assert (fs.queue_ptr, fs.queue_ptr1) == (ost.queue_ptr, ost.queue_ptr1) == (0, 256)        # literal 256 stride
+    assert rel(fs.queue_feats[0][1024:1056], ost.queue_feats[1024:1056]) < 1e-5
+    # ---- loud failures
+    with pytest.raises(_lib.CmlplError):
+        fs.step(torch.zeros(200, dtype=torch.int64, device=dev), 0, 0, cube=cube, pix=torch.zeros(400, dtype=torch.int64, device=dev),
+                spectra=spectra)                                                             # larger than the step was built for
+    with pytest.raises(_lib.CmlplError):
+        fs.step(Y_l.to(dev), 0, 0, cube=cube.cpu(), pix=pix, spectra=spectra)                  # host tensors: no CPU path
+    with pytest.raises(_lib.CmlplError):
+        fs.step(Y_l.to(dev), 0, 0, cube=cube, pix=pix, spectra=spectra, patches=torch.zeros(2, 32, 60, 20, 20, device=dev))
+    fs.queue_ptr = 1260
+    with pytest.raises(RuntimeError):
+        fs.step(Y_l.to(dev), 0, 0, cube=cube, pix=pix, spectra=spectra)                        # bank write past the queue
