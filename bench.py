@@ -470,9 +470,9 @@ def main():
             self.raw_host = torch.from_numpy(np.ascontiguousarray(raw_u16[rows].reshape(-1, B))).pin_memory()
             self.raw_dev = torch.empty_like(self.raw_host, device=dev)
             self.ws = ops.scene_workspace(self.r1 - self.r0, C, B, K, W, dev)
-            self.labels = torch.empty(self.n, dtype=torch.uint8, device=dev)
-            self.cm = torch.zeros(K, K, dtype=torch.int64, device=dev)
             self.gather = parallel.LabelGather(scene_rows, C, dev) if world > 1 else None
+            self.exchange = parallel.SceneExchange(scene_rows, C, K, dev) if world > 1 else None
+            self.labels = self.exchange.local_labels[: self.n] if world > 1 else torch.empty(self.n, dtype=torch.uint8, device=dev)
             self.map_host = torch.empty(scene_rows * C, dtype=torch.uint8).pin_memory() if world > 1 else None
             self.streamed = StreamedRawScene(pp, scene_rows, C, B, K, W, nsplit=1, row0=self.r0, rows=self.r1 - self.r0,
                                              device=dev)
@@ -481,9 +481,11 @@ def main():
             ops.scene_infer(self.slab, self.spec, packed, K, W, band_row0=self.r0, band_rows=self.r1 - self.r0,
                             scene_rows=self.scene_rows, slab_row0=self.s0, workspace=self.ws, labels=self.labels)
             if world > 1:
-                self.gather(self.labels)
-                self.cm.zero_()
-                parallel.reduce_confusion(ops.confusion(self.labels, self.truth, K, self.cm))
+                # label-map all-gather + confusion all-reduce as ONE collective (parallel.SceneExchange); the labels and
+                # the counts are produced directly in its send buffer
+                self.exchange.local_cm.zero_()
+                ops.confusion(self.labels, self.truth, K, self.exchange.local_cm)
+                self.exchange()
 
         def step_e2e(self):
             # the RAW uint16 band (+halo) in pinned host memory in, uint8 labels out (label map of the whole scene on

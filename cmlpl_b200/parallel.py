@@ -59,6 +59,45 @@ class LabelGather:
         return self.out[: self.n]
 
 
+class SceneExchange:
+    """Both end-of-scene exchanges in ONE collective: every rank contributes [its padded uint8 label band | its int64
+    confusion counts as bytes] to a single all-gather, then sums the `world` confusion blocks locally (integers: the
+    result equals all_reduce(sum) bit for bit).  Halves the latency-bound NCCL time of a sub-millisecond sharded scene.
+    Buffers are allocated once."""
+
+    def __init__(self, scene_rows: int, cols: int, num_classes: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.n = scene_rows * cols
+        self.per = -(-scene_rows // self.world) * cols
+        self.cmb = num_classes * num_classes * 8
+        self.slot = (self.per + 7) // 8 * 8 + self.cmb               # labels padded so the counts stay 8-byte aligned
+        self.send = torch.zeros(self.slot, dtype=torch.uint8, device=device)
+        self.recv = torch.empty(self.world * self.slot, dtype=torch.uint8, device=device)
+        self.labels = torch.empty(self.world * self.per, dtype=torch.uint8, device=device)
+        self.K = num_classes
+        # producers may write straight into the send buffer: the inference kernels into `local_labels`, the confusion
+        # kernel into `local_cm` (zero it first) -- then __call__() needs no copies
+        self.local_labels = self.send[: self.per]
+        self.local_cm = self.send[self.slot - self.cmb:].view(torch.int64).view(num_classes, num_classes)
+
+    def __call__(self, local_labels: torch.Tensor | None = None, cm_local: torch.Tensor | None = None):
+        """-> (label map of the whole scene u8 [scene_rows*cols], confusion matrix i64 [K, K] summed over ranks).
+        Pass the band's labels / counts, or nothing when they were produced in place (local_labels / local_cm)."""
+        if local_labels is not None and local_labels.data_ptr() != self.send.data_ptr():
+            self.send[: local_labels.numel()] = local_labels
+        if cm_local is not None and cm_local.data_ptr() != self.local_cm.data_ptr():
+            self.local_cm.copy_(cm_local)
+        if self.recv.is_cuda:
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        else:
+            dist.all_gather(list(self.recv.view(self.world, -1).unbind(0)), self.send, group=self.group)
+        blocks = self.recv.view(self.world, self.slot)
+        torch.cat([blocks[r, : self.per] for r in range(self.world)], out=self.labels)
+        cm = blocks[:, self.slot - self.cmb:].contiguous().view(torch.int64).view(self.world, self.K, self.K).sum(0)
+        return self.labels[: self.n], cm
+
+
 def gather_label_map(local_labels: torch.Tensor, scene_rows: int, cols: int, group=None) -> torch.Tensor:
     """all-gather the per-band uint8 labels into the raster-ordered label map [scene_rows*cols].
     Bands are padded to the common band height so one fixed-size all_gather suffices.  (Allocates its buffers;

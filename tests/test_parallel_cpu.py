@@ -77,3 +77,38 @@ def test_sharded_inference_gloo(world, R):
         p.join(timeout=240)
         assert p.exitcode == 0
     assert out.get(timeout=5) is True
+
+
+def _worker_exchange(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        R, C, K = 11, 7, 5
+        rng = np.random.default_rng(3)
+        full = torch.from_numpy(rng.integers(0, K, R * C).astype(np.uint8))
+        truth = torch.from_numpy(rng.integers(0, K, R * C))
+        r0, r1 = parallel.band_of(rank, world, R)
+        local = full[r0 * C:r1 * C]
+        cm_local = torch.from_numpy(O.confusion_matrix(local.numpy(), truth[r0 * C:r1 * C].numpy(), K))
+        ex = parallel.SceneExchange(R, C, K, torch.device("cpu"))
+        for _ in range(2):                                   # buffers are reused across calls
+            labels, cm = ex(local, cm_local)
+        if rank == 0:
+            ok = torch.equal(labels, full) and np.array_equal(cm.numpy(), O.confusion_matrix(full.numpy(), truth.numpy(), K))
+            out.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_scene_exchange_single_collective(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_exchange, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
