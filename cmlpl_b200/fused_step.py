@@ -60,7 +60,7 @@ class FusedMutualStep:
 
     def __init__(self, Base, Base1, bs=128, btu=128, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, temperature=0.3,
                  alpha=0.95, thr=1.0, num_epochs=20, queue_batch=17, noise=0.5, dropout=None, seed=1088,
-                 queue_size=None, use_graph=False):
+                 queue_size=None, use_graph=False, param_slots=64):
         _lib.require_device()
         self.nets = (Base, Base1)
         dev = next(Base.parameters()).device
@@ -105,9 +105,15 @@ class FusedMutualStep:
         lib = _lib.load()
         self.work = torch.zeros((lib.cmlpl_train_workspace_bytes(bs, btu, self.B, self.C, self.queue),),
                                 dtype=torch.uint8, device=dev)
-        self.prm_host = torch.zeros((ctypes.sizeof(TrainParams),), dtype=torch.uint8).pin_memory()
-        self.prm_dev = torch.zeros((ctypes.sizeof(TrainParams),), dtype=torch.uint8, device=dev)
-        self.prm = TrainParams.from_address(self.prm_host.data_ptr())
+        # per-step scalars: a ring of pinned host blocks -- the H2D copy of step k is asynchronous and the host runs many
+        # steps ahead of the device, so a block is only rewritten after the copy that read it has completed (its event)
+        self._nslots = max(2, int(param_slots))
+        psz = ctypes.sizeof(TrainParams)
+        self.prm_ring = torch.zeros((self._nslots, psz), dtype=torch.uint8).pin_memory()
+        self._prm_events = [None] * self._nslots
+        self._slot = 0
+        self.prm_dev = torch.zeros((psz,), dtype=torch.uint8, device=dev)
+        self.prm = TrainParams.from_address(self.prm_ring[0].data_ptr())
         # static input buffers (CUDA-graph replays read the same addresses)
         self.pix = torch.zeros((self.nb,), dtype=torch.int64, device=dev)
         self.labels = torch.zeros((bs,), dtype=torch.int64, device=dev)
@@ -154,7 +160,11 @@ class FusedMutualStep:
         return io
 
     def _set_params(self, epoch, batch_index, phases):
-        p = self.prm
+        slot = self._slot
+        self._slot = (slot + 1) % self._nslots
+        if self._prm_events[slot] is not None:
+            self._prm_events[slot].synchronize()             # the copy issued _nslots steps ago has read this block
+        p = self.prm = TrainParams.from_address(self.prm_ring[slot].data_ptr())
         nb = self.cur[0] + self.cur[1]
         p.noise_scale, p.dropout_p, p.temperature, p.alpha = self.noise, self.dropout, self.T, self.alpha
         p.adap_thr = self.thr * math.exp(-0.5 * ((epoch / self.num_epochs) ** 2))          # train.py:147-148,221
@@ -169,7 +179,10 @@ class FusedMutualStep:
             # train.py:232 would raise on the shape mismatch of the slice assignment
             raise RuntimeError("memory-bank write [%d, %d) exceeds the queue of %d rows (train.py:232-237)"
                                % (max(self.queue_ptr, self.queue_ptr1), max(self.queue_ptr, self.queue_ptr1) + nb, self.queue))
-        self.prm_dev.copy_(self.prm_host, non_blocking=True)
+        self.prm_dev.copy_(self.prm_ring[slot], non_blocking=True)
+        if self._prm_events[slot] is None:
+            self._prm_events[slot] = torch.cuda.Event()
+        self._prm_events[slot].record()
         if phases & 2:
             self.queue_ptr = (self.queue_ptr + 256) % self.queue                            # train.py:234 (literal 256)
             self.queue_ptr1 = (self.queue_ptr + 256) % self.queue                           # train.py:237 (sic: reads queue_ptr)

@@ -258,13 +258,18 @@ def test_fused_step_cube_mode_philox_and_graph(dev, golden_dir):
     nets = [BaseNet2(103, 0.8, 9).to(dev) for _ in range(2)]
     sd0 = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in nets]
 
-    def run(noise, graph, steps=1, seed=1088):
+    def run(noise, graph, steps=1, seed=1088, light=False, sync=False):
         for n, s in zip(nets, sd0):
             n.load_state_dict(s)
         fs = FusedMutualStep(nets[0], nets[1], noise=noise, seed=seed, use_graph=graph, thr=0.5)
         out = []
+        pix_d = pix.to(dev)
         for it in range(steps):
-            fs.step(labels, 1, it, cube=cube, pix=pix.to(dev), spectra=spectra)
+            fs.step(labels, 1, it, cube=cube, pix=pix_d, spectra=spectra)
+            if sync:
+                torch.cuda.synchronize()
+            if light:
+                continue
             lay = fs.workspace_layout()
             out.append(dict(x16=planes_to_nchw(fs.work[lay["x16"]:], 512, 400, 20).clone(), logits=fs.logits.clone(),
                             hist=fs.hist.clone(),
@@ -301,6 +306,23 @@ def test_fused_step_cube_mode_philox_and_graph(dev, golden_dir):
     for a, b in zip(eager[2]["w"], graph[2]["w"]):
         assert rel(a, b) < 1e-4
     assert fsg.launches() == 15 and np.isfinite(graph[2]["hist"].cpu().numpy()).all()
+    # the host runs many steps ahead of the device: the per-step scalars (Adam bias corrections, bank pointers, Philox
+    # offsets) every step READS must be the ones written for that step (ring of pinned blocks, here only 3 deep)
+    from cmlpl_b200.fused_step import TrainParams
+    for n, s in zip(nets, sd0):
+        n.load_state_dict(s)
+    fr = FusedMutualStep(nets[0], nets[1], noise=0.5, use_graph=True, thr=0.5, param_slots=3)
+    snaps, pix_d = [], pix.to(dev)
+    for it in range(40):
+        fr.step(labels, 1, it, cube=cube, pix=pix_d, spectra=spectra)
+        snaps.append(fr.prm_dev.clone())                      # stream-ordered: what this step's kernels saw
+    torch.cuda.synchronize()
+    qp = 0
+    for it, sn in enumerate(snaps):
+        prm = TrainParams.from_buffer_copy(bytes(sn.cpu().numpy()))
+        assert prm.offset == it and abs(prm.bc1 - (1 - 0.9 ** (it + 1))) < 1e-6, it
+        assert prm.queue_ptr[0] == qp, (it, prm.queue_ptr[0], qp)
+        qp = (qp + 256) % 1280
 
 
 def test_packed_weights_follow_the_optimizers(dev):
