@@ -78,3 +78,28 @@ def test_synthetic_generator_is_the_oracles(gold):
         a, ga = synth.synth_scene(*shape, seed=1088)
         b, gb = O.synth_cube(*shape, seed=1088)
         assert np.array_equal(a, b) and np.array_equal(ga, gb) and a.dtype == b.dtype == np.uint16
+
+
+def test_sample_generation_cli_writes_the_reference_file_contract(gold, tmp_path, monkeypatch):
+    """python -m cmlpl_b200.sample_generation on the scene the reference's sample_generation.main was run on
+    (oracle/make_golden.py::gold_loader): X.npy / Y.npy / the three index arrays equal the reference's files, XPCA.npy is
+    the float32 PCA cube the reference materialises patches from, and no XP.npy is written unless asked for."""
+    from cmlpl_b200 import sample_generation as SG, synth
+    z, ti = gold
+    monkeypatch.setitem(synth.SHAPES, "paviau", (40, 36, 103, 9))
+    root = str(tmp_path) + "/"
+    d = SG.main(SG.build_parser().parse_args(["--dataID", "1", "--root", root, "--synthetic"]))
+    assert sorted(os.listdir(d)) == ["X.npy", "XPCA.npy", "Y.npy", "meta.npy", "test_array.npy", "train_array.npy",
+                                     "unlabel_array.npy"]
+    X = np.load(d + "X.npy")
+    assert X.dtype == np.float64 and X.shape == z["X"].shape                      # hsi_loader.py:21 reads float64
+    assert np.abs(X - z["X"]).max() <= 1e-12 * np.abs(z["X"]).max()
+    Y = np.load(d + "Y.npy")
+    assert Y.dtype == z["Y"].dtype and np.array_equal(Y, z["Y"])
+    for f in ("train_array", "test_array", "unlabel_array"):
+        a = np.load(d + f + ".npy")
+        assert a.dtype == z[f].dtype and np.array_equal(a, z[f]), f
+    cube = np.load(d + "XPCA.npy")
+    assert cube.dtype == np.float32 and cube.shape == (40, 36, 60)
+    assert np.abs(cube - ti["cube_pca"]).max() <= 1e-5 * np.abs(ti["cube_pca"]).max()
+    assert np.array_equal(np.load(d + "meta.npy"), np.array([20, 40, 36]))
