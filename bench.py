@@ -601,7 +601,7 @@ def main():
     ppos = (nbr + W - 1) * (C + W - 1)
     exec_flop = {"conv0_map": ppos * 2 * 60 * 64, "spectral_logits": band.n * (2 * B * 1024 + 2 * 1024 * 16),
                  "conv1_pool": ppos * 9 * 2 * 64 * 64, "conv2_scene": qpos * 169 * 2 * 64 * 64,
-                 "pool2_cls": qpos * 4 * 25 * 16 * 64 * 2, "head_sum": band.n * 29 * 16}
+                 "pool2_cls": qpos * 1024 * 64 * 2, "head_sum": band.n * 29 * 16}
     achieved = exec_flop["conv2_scene"] / (cnn_ms / 1e3) / 1e12
     traffic, stage_dram = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")

@@ -15,8 +15,13 @@
 //     -> conv2_scene_kernel: 25 variants per position, 169 tap products instead of 900 per pixel;
 //   * pool + classifier are linear after the ReLU:  logit_conv(r,c) = sum_{I,J} L[I][J][r'+2I, c'+2J] with
 //       L[I][J][y',x'] = sum_{u,v in {0,1}} (Wc[I,J]/4) . Y[rho(2I+u)][kap(2J+v)][y'+u, x'+v]
-//     -> pool2_cls_kernel: the 2x2 pool is four accumulating tcgen05.mma whose A descriptors are shifted
-//        by (u,v) inside the tile; 25 maps of 16 class partials per position;
+//     The border halves of that 2x2 pool pair two DIFFERENT variants at neighbouring positions (rho 0 with rho 1 one row
+//     down, rho 3 with rho 4, and the same for kap), so conv2_scene_kernel's epilogue adds them before anything is
+//     stored (the partner sits in the same TMEM lane because the accumulator frames are shifted accordingly) and writes
+//     9 half-pooled maps  YP[Al][Be]  (Al, Be = border / middle / border) instead of 25 variants: 1 152 B per position
+//     through HBM instead of 3 200;
+//     -> pool2_cls_kernel: the remaining pool of the middle classes is accumulating tcgen05.mma whose A descriptors are
+//        shifted by (u,v) inside the tile; 25 maps of 16 class partials per position;
 //   * the head (head_sm100.cu) adds the 25 gathered partials of a pixel to its spectral logits.
 //
 // Identical math up to fp32 summation order; per PaviaU scene conv2 executes 0.32 TFLOP instead of 1.53.
@@ -97,6 +102,13 @@ __global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC,
 // rho3+rho4, so the epilogue (bias + residual + ReLU -> fp16) of one class overlaps the MMAs of the next groups
 // and the single 320-column accumulator set is reused by the next column class as its blocks drain.  Rows
 // y < rho of class rho are never produced -- no pixel reads them (pooled row i >= rho for that class).
+// HALF POOL IN THE EPILOGUE.  The frames put Y[rho0](y) and Y[rho1](y+1) -- the two rows of pooled cell I = 0 -- in the
+// same TMEM lane, likewise rho3 / rho4 (I = 4), so an epilogue thread adds them in registers.  Columns work the same way
+// in time: the frame of kap = 0 is shifted one entry LEFT and that of kap = 4 one entry RIGHT (an A-descriptor offset;
+// the taps the patch border cuts off are exactly the ones that would leave the tile), the row-pooled result of kap = 0
+// (kap = 3) is parked as fp32 in the 192 TMEM columns the accumulators leave free (tcgen05.st) and added when
+// kap = 1 (kap = 4) drains.  Per position the kernel stores 9 maps  YP[Al*3+Be]  (Al: rho {0+1 | 2 | 3+4}, Be alike),
+// each the AVERAGE of its pre-pooled partners; the classifier block weights carry the matching factor (pack.cu).
 namespace c2s {
 constexpr int TH = 4, TP = 32, TW = 30;
 constexpr int CH = (TH + 2) * TP * 16;               // 3 072: one chunk plane of a tile, dense (written by TMA)
@@ -110,7 +122,8 @@ constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
 // one full / empty mbarrier per resident class tile (slab X or M x row class a), so the next tile's loads start as each
 // tile is released (top tiles after the PA group of the last column class that reads them, ...) instead of after the
 // whole slab; DF/DE: accumulator block of row class rho full / drained
-enum { XF0 = 0, MF0 = 3, XE0 = 6, ME0 = 9, DF0 = 12, DE0 = 17, W_FULL = 22 };
+enum { XF0 = 0, MF0 = 3, XE0 = 6, ME0 = 9, DF0 = 12, DE0 = 17, W_FULL = 22, SF0 = 23, SE0 = 26 };   // SF/SE: parked item full / read
+constexpr int kPark = 320;                           // first TMEM column of the three parked 64-column items
 static_assert(SMEM <= 232448, "conv2_scene: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "conv2_scene: TMA destinations must be 128-byte aligned");
 // first tile row (relative to Y0 - 1) held by the tile of PM row class a: top rows +1.., mid +2.., bot +5..
@@ -127,6 +140,7 @@ __device__ __forceinline__ void issue_group(uint32_t t_lo, uint32_t w_lo) {
   constexpr int N = (G == 0 || G == 4) ? 128 : 192;
   constexpr int brow = G == 0 ? 64 : 0;
   constexpr int dx_first = rep_of(KAP) == 0 ? 1 : 0;
+  constexpr int xs = KAP == 0 ? -1 : (KAP == 4 ? 1 : 0);          // frame shift of the border column classes (entries)
 #pragma unroll
   for (int dx = 0; dx < 3; ++dx) {
     const int j2 = rep_of(KAP) + dx - 1;
@@ -134,7 +148,7 @@ __device__ __forceinline__ void issue_group(uint32_t t_lo, uint32_t w_lo) {
     const int tile = (cls_of(j2) == 1 ? 3 : 0) + a;               // slab M holds the mid column class
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t aa = t_lo + uint32_t((tile * TBYTES + ((o - tile_r0(a)) * TP + dx) * 16 + ks * 2 * CH) / 16);
+      const uint32_t aa = t_lo + uint32_t((tile * TBYTES + ((o - tile_r0(a)) * TP + dx + xs) * 16 + ks * 2 * CH) / 16);
       const uint32_t bb = w_lo + uint32_t((dx * kWDx + ks * 2 * kWLbo) / 16) + uint32_t(brow);
       const bool first = dx == dx_first && ks == 0;
       if (first && G >= 1 && G <= 3) {
@@ -149,7 +163,7 @@ __device__ __forceinline__ void issue_group(uint32_t t_lo, uint32_t w_lo) {
 }
 }  // namespace c2s
 
-// pmq f16 [9][4][8][PR2][PC2][8];  yq f16 [25 = rho*5+kap][4][8][PR2][PC2][8]
+// pmq f16 [9][4][8][PR2][PC2][8];  yq f16 [9 = Al*3+Be half-pooled maps][4][8][PR2][PC2][8]
 __global__ void __launch_bounds__(c2s::kThreads, 1)
 conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __restrict__ pmq, int PR2, int PC2,
                    const unsigned char* __restrict__ w2p, const float* __restrict__ b2g, __half* __restrict__ yq) {
@@ -181,6 +195,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
       mbar_init(bars + 8 * (XE0 + a), cnt); mbar_init(bars + 8 * (ME0 + a), cnt);
     }
     for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi / 2); }
+    for (int s = 0; s < 3; ++s) { mbar_init(bars + 8 * (SF0 + s), kEpi / 2); mbar_init(bars + 8 * (SE0 + s), kEpi / 2); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
@@ -264,64 +279,108 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
 #undef C2S_GROUP
   } else {
     // ================================================================ epilogue (warps 0-7)
-    // two groups of four warps take alternate variants, so the residual loads / TMEM reads / stores of one variant
-    // overlap the other group's; a thread owns one position (TMEM lane) and all 64 channels of it
+    // Work items = (column class kap, row item it): it 0 = rho 0 + rho 1, it 1 = rho 2, it 2 = rho 3 + rho 4.  Two groups of
+    // four warps take alternate items, so the residual loads / TMEM reads / stores of one item overlap the other group's;
+    // a thread owns one position (TMEM lane) and all 64 channels of it.
     const int L = (warp & 3) * 32 + lane, grp = warp >> 2;
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
     const int ty = L >> 5, tx = L & 31;
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t nv = uint32_t(my_tiles) * 25;
+    const uint32_t nv = uint32_t(my_tiles) * 15;
 #pragma unroll 1
     for (uint32_t vc = uint32_t(grp); vc < nv; vc += 2) {
-      // variant vc of this CTA -> tile, column class, row class
-      const uint32_t tl = vc / 25, r = vc - tl * 25;
-      const int kap = int(r / 5), rho = int(r - uint32_t(kap) * 5);
+      const uint32_t tl = vc / 15, r = vc - tl * 15;
+      const int kap = int(r / 3), it = int(r - uint32_t(kap) * 3);
+      const int rho0 = it == 0 ? 0 : it + 1, nrho = it == 1 ? 1 : 2;
+      const int xs = kap == 0 ? -1 : (kap == 4 ? 1 : 0);       // frame shift of this column class (entries)
       const int t = blockIdx.x + int(tl) * gridDim.x;
       const int pl = t / tiles_p, tt = t - pl * tiles_p, tr = tt / tiles_c, tc = tt - tr * tiles_c;
-      const int y = tr * TH + ty + rho, x = tc * TW + tx - 1;   // the accumulator of class rho lives rho rows further down
-      const bool valid = tx >= 1 && tx <= TW && y < PR2 && x < PC2;
+      // pooled cell (y, x) = the position of the item's first row class (its frame lives rho0 rows further down) and of the
+      // LEFT column of the pair: kap 1 holds column x+1 of the cell whose column x was parked by kap 0
+      const int y = tr * TH + ty + rho0, x = tc * TW + tx - 1 - (kap == 1 ? 1 : 0);
+      const bool valid = tx >= 1 && tx <= TW && y < PR2 && x >= 0 && x < PC2;
       const int64_t pos = valid ? int64_t(y) * PC2 + x : 0;
-      const uint32_t kc = vc / 5;                              // column-class stage (phase of the DF barriers)
-      mbar_wait(bars + 8 * (DF0 + rho), kc & 1, 64);
+      const uint32_t kc = vc / 3;                              // column-class stage (phase of the DF barriers)
+      const uint32_t pk = tl * 2 + (kap >= 3 ? 1 : 0);         // use count of the parking columns
+      const bool park = kap == 0 || kap == 3, unpark = kap == 1 || kap == 4;
+      mbar_wait(bars + 8 * (DF0 + rho0), kc & 1, 64);
+      if (nrho == 2) mbar_wait(bars + 8 * (DF0 + rho0 + 1), kc & 1, 64);
       tc_fence_after();
-      // residual = centre cell PM[A(rho)][B(kap)][y,x] = the (dy=1,dx=1) operand of this variant, still in its slab:
-      // tile row ty + rho + 1 - r0(A), entry tx (the slab is only released once every epilogue thread has read its share)
-      uint4 res[8];
-      {
-        const int a = cls_of(rep_of(rho)), b = cls_of(rep_of(kap));
-        const unsigned char* rp = smem + S_T + ((b == 1 ? 3 : 0) + a) * TBYTES + ((ty + rho + 1 - tile_r0(a)) * TP + tx) * 16;
+      // residual of row class rho = centre cell PM[A(rho)][B(kap)] = the (dy=1,dx=1) operand of that variant, still in its
+      // slab: tile row ty + rho + 1 - r0(A), entry tx + xs (the slab is only released once every epilogue thread has read
+      // its share)
+      const int bsl = cls_of(rep_of(kap)) == 1 ? 3 : 0;
+      const unsigned char* rp[2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) res[k] = *reinterpret_cast<const uint4*>(rp + k * CH);
+      for (int p = 0; p < 2; ++p) {
+        const int rho = rho0 + (p < nrho ? p : 0), a = cls_of(rep_of(rho));
+        rp[p] = smem + S_T + (bsl + a) * TBYTES + ((ty + rho + 1 - tile_r0(a)) * TP + tx + xs) * 16;
       }
-      // this thread's last residual read of a slab releases its share of all three class tiles (r = kap*5 + rho; a thread
-      // sees one parity of r per tile): left tiles are read by kap = 0 only, mid tiles by kap = 1..3, right tiles by kap = 4
-      if (r == 3 || r == 4 || r == 23 || r == 24) { mbar_arrive(bars + 8 * (XE0 + 0)); mbar_arrive(bars + 8 * (XE0 + 1)); mbar_arrive(bars + 8 * (XE0 + 2)); }
-      else if (r == 18 || r == 19) { mbar_arrive(bars + 8 * (ME0 + 0)); mbar_arrive(bars + 8 * (ME0 + 1)); mbar_arrive(bars + 8 * (ME0 + 2)); }
-      __half* dst = yq + (int64_t((rho * 5 + kap) * 4 + pl) * 8 * psz + pos) * 8;
+      const int Be = kap <= 1 ? 0 : (kap == 2 ? 1 : 2);
+      __half* dst = yq + (int64_t((it * 3 + Be) * 4 + pl) * 8 * psz + pos) * 8;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {                         // 32 channels at a time
-        float v0[16], v1[16];
-        tmem_ld16(lane_addr + rho * 64 + hf * 32, v0);
-        tmem_ld16(lane_addr + rho * 64 + hf * 32 + 16, v1);
-        tmem_ld_wait();
-        if (hf == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (DE0 + rho)); }
-        if (valid) {
-          const float* bb = sbias + hf * 32;
+        float acc[32];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const __half2* hr = reinterpret_cast<const __half2*>(&res[hf * 4 + k]);
-            const float* v = k < 2 ? v0 + k * 8 : v1 + (k - 2) * 8;
-            __half2 h[4];
+        for (int p = 0; p < 2; ++p) {
+          if (p < nrho) {
+            const int rho = rho0 + p;
+            float v[32];
+            tmem_ld16(lane_addr + rho * 64 + hf * 32, v);
+            tmem_ld16(lane_addr + rho * 64 + hf * 32 + 16, v + 16);
+            uint4 res[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(hr[e]);
-              h[e] = __floats2half2_rn(fmaxf(v[2 * e] + (f.x + bb[k * 8 + 2 * e]), 0.f),
-                                       fmaxf(v[2 * e + 1] + (f.y + bb[k * 8 + 2 * e + 1]), 0.f));
+            for (int k = 0; k < 4; ++k) res[k] = *reinterpret_cast<const uint4*>(rp[p] + (hf * 4 + k) * CH);
+            tmem_ld_wait();
+            if (hf == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (DE0 + rho)); }
+            const float* bb = sbias + hf * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __half2* hr = reinterpret_cast<const __half2*>(&res[k]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(hr[e]);
+                const float y0 = fmaxf(v[k * 8 + 2 * e] + (f.x + bb[k * 8 + 2 * e]), 0.f);
+                const float y1 = fmaxf(v[k * 8 + 2 * e + 1] + (f.y + bb[k * 8 + 2 * e + 1]), 0.f);
+                if (p == 0) { acc[k * 8 + 2 * e] = y0; acc[k * 8 + 2 * e + 1] = y1; }
+                else { acc[k * 8 + 2 * e] = (acc[k * 8 + 2 * e] + y0) * 0.5f; acc[k * 8 + 2 * e + 1] = (acc[k * 8 + 2 * e + 1] + y1) * 0.5f; }
+              }
             }
-            *reinterpret_cast<uint4*>(dst + int64_t(hf * 4 + k) * psz * 8) = *reinterpret_cast<uint4*>(h);
+          }
+        }
+        const uint32_t pcol = lane_addr + uint32_t(kPark + it * 64 + hf * 32);
+        if (park) {
+          // wait until the previous use of these columns has been read back (by the other group, one column class later)
+          if (hf == 0) { mbar_wait(bars + 8 * (SE0 + it), (pk & 1) ^ 1, 65); tc_fence_after(); }
+          tmem_st16(pcol, acc);
+          tmem_st16(pcol + 16, acc + 16);
+          if (hf == 1) { tmem_st_wait(); tc_fence_before(); mbar_arrive(bars + 8 * (SF0 + it)); }
+        } else {
+          if (unpark) {
+            if (hf == 0) { mbar_wait(bars + 8 * (SF0 + it), pk & 1, 66); tc_fence_after(); }
+            float s[32];
+            tmem_ld16(pcol, s);
+            tmem_ld16(pcol + 16, s + 16);
+            tmem_ld_wait();
+            if (hf == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (SE0 + it)); }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = (acc[c] + s[c]) * 0.5f;
+          }
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __half2 h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[k * 8 + 2 * e], acc[k * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(dst + int64_t(hf * 4 + k) * psz * 8) = *reinterpret_cast<uint4*>(h);
+            }
           }
         }
       }
+      // this thread's last residual read of a slab releases its share of all three class tiles (a thread sees one parity of
+      // r = kap*3 + it per tile): left tiles are read by kap = 0 only, mid tiles by kap = 1..3, right tiles by kap = 4
+      if (r == 1 || r == 2 || r == 13 || r == 14) { mbar_arrive(bars + 8 * (XE0 + 0)); mbar_arrive(bars + 8 * (XE0 + 1)); mbar_arrive(bars + 8 * (XE0 + 2)); }
+      else if (r == 10 || r == 11) { mbar_arrive(bars + 8 * (ME0 + 0)); mbar_arrive(bars + 8 * (ME0 + 1)); mbar_arrive(bars + 8 * (ME0 + 2)); }
     }
   }
   tc_fence_before();
@@ -332,9 +391,11 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
 // =================================================================================================
 // pool2_cls_kernel: L[m][y',x'][cls] = sum_{u,v} (Wc[I,J]/4) . Y[rho(2I+u)][kap(2J+v)][y'+u, x'+v]
 // The 25 (I,J) maps are grouped in 9 blocks by the pooled border class (Alpha, Beta) of (I, J)
-// (Alpha = 0: I=0, 1: I=1..3, 2: I=4): all maps of a block read the same <= 4 Y variants, so a block is
-// 4 (u,v) x 4 k-steps tcgen05.mma with M = 128 positions, N = 16 classes x maps of the block (16/48/144),
-// accumulating into the block's TMEM columns; the (u,v) shift is an A-descriptor offset in the tile.
+// (Alpha = 0: I=0, 1: I=1..3, 2: I=4): all maps of a block read the same half-pooled map YP[Alpha][Beta] -- border
+// classes already averaged over their two variants by conv2_scene_kernel, the middle class still per position -- so a
+// block is (Alpha==1 ? 2 : 1) x (Beta==1 ? 2 : 1) shifts x 4 k-steps tcgen05.mma with M = 128 positions, N = 16 classes
+// x maps of the block (16/48/144), accumulating into the block's TMEM columns; the (u,v) shift is an A-descriptor
+// offset in the tile and the block's weights carry 1/4, 1/2 or 1 (pack.cu).
 namespace p2c {
 constexpr int TH = 4, TP = 32, TW = 31;              // outputs valid for tx = 0..30 (tx+1 must be in the tile)
 constexpr int CH = (TH + 1) * TP * 16;               // 2 560: one chunk plane of a tile, dense (written by TMA)
@@ -350,11 +411,11 @@ static_assert(SMEM <= 232448, "pool2_cls: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "pool2_cls: TMA destinations must be 128-byte aligned");
 }  // namespace p2c
 
-// yq f16 [25][4][8][PR2][PC2][8];  wcq f16 per block [8 kchunks][N rows = map*16 + cls][8];
+// yq f16 [9][4][8][PR2][PC2][8];  wcq f16 per block [8 kchunks][N rows = map*16 + cls][8];
 // lmap f32 [4][25][4][PR2][PC2][4]
-// The kernel streams 3.2 KB of Y per position once: every Y variant tile ((TH+1) rows x 32 entries x 8 chunks,
+// The kernel streams 1 152 B of YP per position once: every map tile ((TH+1) rows x 32 entries x 8 chunks,
 // 20 KB) is ONE cp.async.bulk.tensor (TMA, 4-D tile mode, zero fill outside the plane) into a ring of 8 slots,
-// each with its own full / empty mbarrier, so a single loader thread runs up to 8 variants ahead of the MMAs.
+// each with its own full / empty mbarrier, so a single loader thread runs up to 8 maps ahead of the MMAs.
 __global__ void __launch_bounds__(p2c::kThreads, 1)
 pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int nq, const unsigned char* __restrict__ wcq,
                  float* __restrict__ lmap) {
@@ -395,18 +456,11 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
         const int pl = t / tiles_p, tt = t - pl * tiles_p;
         const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
 #pragma unroll 1
-        for (int b = 0; b < 9; ++b) {
-          const int Al = b / 3, Be = b - Al * 3;
-          const int nr = Al == 1 ? 1 : 2, nk = Be == 1 ? 1 : 2;
-#pragma unroll 1
-          for (int q = 0; q < nr * nk; ++q) {
-            const int su = q / nk, sv = q - su * nk;
-            const int var = ycls(Al, su) * 5 + ycls(Be, sv);
-            mbar_wait(bars + 8 * (E0 + slot), ph ^ 1, 71);
-            mbar_arrive_expect_tx(bars + 8 * (F0 + slot), TBYTES);
-            tma_load_tile(sbase + S_T + slot * TBYTES, &tm_y, tc * TW, tr * TH, var * 4 + pl, bars + 8 * (F0 + slot));
-            if (++slot == NSLOT) { slot = 0; ph ^= 1; }
-          }
+        for (int b = 0; b < 9; ++b) {                          // block b = (Al, Be) reads the half-pooled map YP[b] only
+          mbar_wait(bars + 8 * (E0 + slot), ph ^ 1, 71);
+          mbar_arrive_expect_tx(bars + 8 * (F0 + slot), TBYTES);
+          tma_load_tile(sbase + S_T + slot * TBYTES, &tm_y, tc * TW, tr * TH, b * 4 + pl, bars + 8 * (F0 + slot));
+          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         }
       }
     }
@@ -423,37 +477,30 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
       for (int b = 0; b < 9; ++b) {
         const int Al = b / 3, Be = b % 3;
         const int N = blk_n(Al) * blk_n(Be) * 16;
-        const int nr = Al == 1 ? 1 : 2, nk = Be == 1 ? 1 : 2;
+        const int nu = Al == 1 ? 2 : 1, nv = Be == 1 ? 2 : 1;   // border classes arrive pooled from conv2_scene_kernel
         const uint32_t idesc = make_idesc_f16(128, N);
         const uint32_t w_lo = ((sbase + S_W + blk_start(b) * 16 * 128) >> 4) | (uint32_t((N * 16) >> 4) << 16);
+        mbar_wait(bars + 8 * (F0 + slot), ph, 73);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t t_lo = ((sbase + S_T + slot * TBYTES) >> 4) | (uint32_t(CH >> 4) << 16);
 #pragma unroll
-        for (int q = 0; q < nr * nk; ++q) {
-          const int su = q / nk, sv = q % nk;
-          mbar_wait(bars + 8 * (F0 + slot), ph, 73);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t t_lo = ((sbase + S_T + slot * TBYTES) >> 4) | (uint32_t(CH >> 4) << 16);
+          for (int u = 0; u < nu; ++u) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              if (Al != 1 && u != su) continue;                // a border row class has one variant per u
+            for (int v = 0; v < nv; ++v) {
 #pragma unroll
-              for (int v = 0; v < 2; ++v) {
-                if (Be != 1 && v != sv) continue;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint32_t a = t_lo + uint32_t(((u * TP + v) * 16 + ks * 2 * CH) / 16);
-                  const uint32_t bw = w_lo + uint32_t((ks * 2 * N * 16) / 16);
-                  const bool first = q == 0 && ks == 0 && u == (Al != 1 ? su : 0) && v == (Be != 1 ? sv : 0);
-                  umma_f16(uint32_t(blk_start(b) * 16), kHi | uint64_t(a), kHi | uint64_t(bw), idesc, first ? 0u : 1u);
-                }
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t a = t_lo + uint32_t(((u * TP + v) * 16 + ks * 2 * CH) / 16);
+                const uint32_t bw = w_lo + uint32_t((ks * 2 * N * 16) / 16);
+                umma_f16(uint32_t(blk_start(b) * 16), kHi | uint64_t(a), kHi | uint64_t(bw), idesc, (u | v | ks) ? 1u : 0u);
               }
             }
-            umma_commit(bars + 8 * (E0 + slot));
-            if (b == 8 && q == nr * nk - 1) umma_commit(bars + 8 * DFULL);
           }
-          __syncwarp();
-          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+          umma_commit(bars + 8 * (E0 + slot));
+          if (b == 8) umma_commit(bars + 8 * DFULL);
         }
+        __syncwarp();
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
       }
     }
   } else {
@@ -541,7 +588,7 @@ extern "C" int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_row
   const int ntiles = 4 * ((PR2 + p2c::TH - 1) / p2c::TH) * ((PC2 + p2c::TW - 1) / p2c::TW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
   CUtensorMap tm_y;
-  const int trc = make_scene_tmap(&tm_y, yq, 100, PR2, PC2, p2c::TH + 1, p2c::TP);
+  const int trc = make_scene_tmap(&tm_y, yq, 36, PR2, PC2, p2c::TH + 1, p2c::TP);
   if (trc != CMLPL_OK) return trc;
   pool2_cls_kernel<<<grid, p2c::kThreads, p2c::SMEM, static_cast<cudaStream_t>(stream)>>>(tm_y, PR2, PC2, (num_classes + 3) / 4,
                                                                                           pk + L.wcq, lmap);

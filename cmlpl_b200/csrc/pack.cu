@@ -85,7 +85,9 @@ __global__ void pack_kernel(PackArgs a) {
         d[i] = __float2half_rn(v);
       }
     } break;
-    case 8: {  // dense-path classifier: per block [8 kc][N][8], row = map*16 + cls, value = Wc[cls][ch,I,J] / 4
+    case 8: {  // dense-path classifier: per block [8 kc][N][8], row = map*16 + cls, value = Wc[cls][ch,I,J] / 4 for the
+               // middle classes; a border class arrives averaged over its two variants (conv2_scene_kernel), so its factor
+               // doubles per border direction
       if (a.P != 25) break;
       __half* d = reinterpret_cast<__half*>(o + a.L.wcq);
       const int in_f = 64 * 25 + 1024;
@@ -97,7 +99,8 @@ __global__ void pack_kernel(PackArgs a) {
         const int e = int(li & 7), row = int((li >> 3) % N), kc = int((li >> 3) / N);
         const int mi = row >> 4, cls = row & 15, ch = kc * 8 + e;
         const int I = blk_first(Al) + mi / blk_n(Be), J = blk_first(Be) + mi % blk_n(Be);
-        d[i] = __float2half_rn(cls < a.C ? 0.25f * a.cw[int64_t(cls) * in_f + ch * 25 + I * 5 + J] : 0.f);
+        const float sc = 0.25f * (Al != 1 ? 2.f : 1.f) * (Be != 1 ? 2.f : 1.f);
+        d[i] = __float2half_rn(cls < a.C ? sc * a.cw[int64_t(cls) * in_f + ch * 25 + I * 5 + J] : 0.f);
       }
     } break;
   }

@@ -6,8 +6,8 @@
 //   2. spectral_head relu(feat_spe(x)) (models.py:142-143) and its classifier columns
 //   3. conv1_scene   conv1 + residual + ReLU once per scene position in 9 patch-border classes and the
 //                    pooled maps as parity planes (conv1_scene_sm100.cu); conv2_scene: conv2 + residual +
-//                    ReLU once per position in 25 classes; pool2_cls: avg-pool + conv columns of the
-//                    classifier -> 25 class-partial maps (conv2_scene_sm100.cu)
+//                    ReLU once per position in 25 classes, border classes pooled in its epilogue; pool2_cls: rest of
+//                    the avg-pool + conv columns of the classifier -> 25 class-partial maps (conv2_scene_sm100.cu)
 //   4. head          spectral columns of the classifier (models.py:150) + the pixel's 25 gathered conv
 //                    partials + bias, argmax (hyper_tools.py:426, first index wins ties)
 //   (> 16 classes / > 224 bands: the all-per-pixel patch_cnn_sm100.cu kernel + CUDA-core classify instead)
@@ -227,7 +227,7 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
     const size_t qpos = size_t(4) * ((band_rows + w) / 2) * ((cols + w) / 2);     // positions of the 4 parity planes
     s.g = o;                                               // (fp32 conv1 variants: not materialised any more)
     s.pm = o; o = align256(o + qpos * 9 * 64 * 2);         // pooled variants, f16 parity planes [9][4][8][PR2][PC2][8]
-    s.yq = o; o = align256(o + qpos * 25 * 64 * 2);        // conv2 variants, f16 [25][4][8][PR2][PC2][8]
+    s.yq = o; o = align256(o + qpos * 9 * 64 * 2);         // half-pooled conv2 maps, f16 [9][4][8][PR2][PC2][8]
     s.lmap = o; o = align256(o + qpos * 25 * 16 * 4);      // class partials, f32 [4][25][4][PR2][PC2][4]
   } else {
     s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);     // per-pixel pooled conv features (patch_cnn_sm100.cu)

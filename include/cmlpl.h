@@ -188,10 +188,12 @@ int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, con
  * PC2 = (cols+w)/2; "planes" = the 4 parity planes (pr&1)*2+(pc&1) of the padded map, y' = pr>>1, x' = pc>>1.
  *   cmlpl_conv1_scene_variants_f32: g f32 [9][PR*PC][64] only (no pooling)
  *   cmlpl_conv1_scene_planes_f16  : + pooled maps as planes   pmq f16 [9][4][8 chunks][PR2][PC2][8]
- *   cmlpl_conv2_scene_f16         : conv2+bias+residual+ReLU in 25 border classes (rho*5+kap)
- *                                   yq f16 [25][4][8][PR2][PC2][8]
- *   cmlpl_pool2_cls_f16           : 2x2 avg-pool + conv columns of the classifier per pooled cell (I,J)
- *                                   lmap f32 [4][25][4 class quads][PR2][PC2][4]
+ *   cmlpl_conv2_scene_f16         : conv2+bias+residual+ReLU in 25 border classes (rho, kap in {i=0, 1, 2..7, 8, 9}); the
+ *                                   border halves of the 2x2 pool (rho 0 + rho 1 one row down, rho 3 + rho 4, same for
+ *                                   kap) are averaged in the epilogue:  yq f16 [9 = Al*3+Be][4][8][PR2][PC2][8],
+ *                                   yq[Al][Be][y',x'] = mean over the border partners of Y[rho][kap][y'+u, x'+v]
+ *   cmlpl_pool2_cls_f16           : rest of the 2x2 avg-pool (middle classes) + conv columns of the classifier per
+ *                                   pooled cell (I,J):  lmap f32 [4][25][4 class quads][PR2][PC2][4]
  *   cmlpl_head_lmap_tc            : spectral classifier columns (h16 tiles) + the 25 gathered partials of each
  *                                   pixel + bias, argmax -> labels u8 [band_rows*cols] (and logits) */
 int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
