@@ -110,6 +110,16 @@ __global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC,
 // kap = 1 (kap = 4) drains.  Per position the kernel stores 9 maps  YP[Al*3+Be]  (Al: rho {0+1 | 2 | 3+4}, Be alike),
 // each the AVERAGE of its pre-pooled partners; the classifier block weights carry the matching factor (pack.cu).
 namespace c2s {
+#ifdef CMLPL_C2S_TRACE
+// debugging aid (scripts/trace_conv2_scene.py builds a second library with this flag): clock64 stamps of one CTA
+__device__ unsigned long long g_trace[4][4096];
+__device__ __forceinline__ void trace_stamp(int role, uint32_t& n, uint32_t tag) {
+  if (blockIdx.x == 5 && n < 2047) { g_trace[role][2 * n] = clock64(); g_trace[role][2 * n + 1] = tag; ++n; }
+}
+#define C2S_TR(role, n, tag) trace_stamp(role, n, tag)
+#else
+#define C2S_TR(role, n, tag) ((void)0)
+#endif
 constexpr int TH = 4, TP = 32, TW = 30;
 constexpr int CH = (TH + 2) * TP * 16;               // 3 072: one chunk plane of a tile, dense (written by TMA)
 constexpr int TBYTES = 8 * CH;                       // 24 576: one PM variant tile (6 rows)
@@ -122,7 +132,7 @@ constexpr int kWLbo = 192 * 16, kWDx = 8 * kWLbo;
 // one full / empty mbarrier per resident class tile (slab X or M x row class a), so the next tile's loads start as each
 // tile is released (top tiles after the PA group of the last column class that reads them, ...) instead of after the
 // whole slab; DF/DE: accumulator block of row class rho full / drained
-enum { XF0 = 0, MF0 = 3, XE0 = 6, ME0 = 9, DF0 = 12, DE0 = 17, W_FULL = 22, SF0 = 23, SE0 = 26 };   // SF/SE: parked item full / read
+enum { XF0 = 0, MF0 = 3, XE0 = 6, ME0 = 9, DF0 = 12, DE0 = 17, W_FULL = 22 };
 constexpr int kPark = 320;                           // first TMEM column of the three parked 64-column items
 static_assert(SMEM <= 232448, "conv2_scene: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "conv2_scene: TMA destinations must be 128-byte aligned");
@@ -188,14 +198,11 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
     bulk_weights_g2s(sbase + S_W, w2p, WBYTES, bars + 8 * W_FULL);
     for (int a = 0; a < 3; ++a) {
       mbar_init(bars + 8 * (XF0 + a), 1); mbar_init(bars + 8 * (MF0 + a), 1);
-      // released by the MMA commit after the last group that reads this class tile + EVERY epilogue thread once it has
-      // done its last residual read of the whole slab (a finer per-tile accounting of the epilogue reads was ~3 %
-      // faster but produced one differing run in ~400 under scripts/stress_determinism.py)
-      const uint32_t cnt = 1 + kEpi;
-      mbar_init(bars + 8 * (XE0 + a), cnt); mbar_init(bars + 8 * (ME0 + a), cnt);
+      // released by the MMA commit after the last group that reads this class tile (the epilogue takes its residuals
+      // from global memory, so nothing else reads the tiles)
+      mbar_init(bars + 8 * (XE0 + a), 1); mbar_init(bars + 8 * (ME0 + a), 1);
     }
-    for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi / 2); }
-    for (int s = 0; s < 3; ++s) { mbar_init(bars + 8 * (SF0 + s), kEpi / 2); mbar_init(bars + 8 * (SE0 + s), kEpi / 2); }
+    for (int s = 0; s < 5; ++s) { mbar_init(bars + 8 * (DF0 + s), 1); mbar_init(bars + 8 * (DE0 + s), kEpi); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
@@ -210,6 +217,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
     if (lane == 0) {
       tma_prefetch_desc(&tm_pm);
       uint32_t fx[3] = {0, 0, 0}, fm[3] = {0, 0, 0};           // fills of each class tile of slab X / slab M so far
+      [[maybe_unused]] uint32_t ntr = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int pl = t / tiles_p, tt = t - pl * tiles_p;
         const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
@@ -223,6 +231,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
           const uint32_t full = bars + 8 * ((slab ? MF0 : XF0) + a);
           mbar_wait(bars + 8 * ((slab ? ME0 : XE0) + a), (k & 1) ^ 1, 61);
           mbar_arrive_expect_tx(full, TBYTES);
+          C2S_TR(3, ntr, uint32_t(i));
           tma_load_tile(sbase + S_T + (slab * 3 + a) * TBYTES, &tm_pm, x0, y0 + tile_r0(a), (a * 3 + bcls) * 4 + pl, full);
           if (slab) ++fm[a]; else ++fx[a];
         }
@@ -234,11 +243,14 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
     const uint32_t t_lo = ((sbase + S_T - 16) >> 4) | (uint32_t(CH >> 4) << 16);
     const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
     uint32_t cx[3] = {0, 0, 0}, cm[3] = {0, 0, 0}, kc = 0;     // class-tile fills consumed, column-class stages issued
+    [[maybe_unused]] uint32_t ntr = 0;
 #define C2S_GROUP(KAP, G, ...)                                                       \
     do {                                                                             \
       tc_fence_after();                                                              \
+      if (lane == 0) C2S_TR(0, ntr, KAP * 16 + G * 2);                               \
       if (elect_one_sync()) { issue_group<KAP, G>(t_lo, w_lo); __VA_ARGS__; }        \
       __syncwarp();                                                                  \
+      if (lane == 0) C2S_TR(0, ntr, KAP * 16 + G * 2 + 1);                           \
     } while (0)
     // WX / WM: this column class is the first to read a fresh fill of slab X / M (wait per class tile, just before the
     // first group that reads it); RX / RM: it is the last to read the resident fill (release per class tile)
@@ -279,108 +291,115 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
 #undef C2S_GROUP
   } else {
     // ================================================================ epilogue (warps 0-7)
-    // Work items = (column class kap, row item it): it 0 = rho 0 + rho 1, it 1 = rho 2, it 2 = rho 3 + rho 4.  Two groups of
-    // four warps take alternate items, so the residual loads / TMEM reads / stores of one item overlap the other group's;
-    // a thread owns one position (TMEM lane) and all 64 channels of it.
-    const int L = (warp & 3) * 32 + lane, grp = warp >> 2;
+    // Work items = (column class kap, row item it): it 0 = rho 0 + rho 1, it 1 = rho 2, it 2 = rho 3 + rho 4.  A thread owns
+    // one position (TMEM lane) and 32 of its 64 channels: warps 0-3 take channels 0..31 of every item, warps 4-7 channels
+    // 32..63, so an accumulator block is back with the MMA issuer one TMEM load after it completes.
+    const int L = (warp & 3) * 32 + lane, hf = warp >> 2;
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
     const int ty = L >> 5, tx = L & 31;
-    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t nv = uint32_t(my_tiles) * 15;
+    const float* bb = sbias + hf * 32;
+    const int64_t cstep = psz * 8;                             // halves between the chunk planes of one map
+    [[maybe_unused]] uint32_t ntr = 0;
+    uint32_t kc = 0;                                           // column-class stage (phase of the DF barriers)
 #pragma unroll 1
-    for (uint32_t vc = uint32_t(grp); vc < nv; vc += 2) {
-      const uint32_t tl = vc / 15, r = vc - tl * 15;
-      const int kap = int(r / 3), it = int(r - uint32_t(kap) * 3);
-      const int rho0 = it == 0 ? 0 : it + 1, nrho = it == 1 ? 1 : 2;
-      const int xs = kap == 0 ? -1 : (kap == 4 ? 1 : 0);       // frame shift of this column class (entries)
-      const int t = blockIdx.x + int(tl) * gridDim.x;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int pl = t / tiles_p, tt = t - pl * tiles_p, tr = tt / tiles_c, tc = tt - tr * tiles_c;
-      // pooled cell (y, x) = the position of the item's first row class (its frame lives rho0 rows further down) and of the
-      // LEFT column of the pair: kap 1 holds column x+1 of the cell whose column x was parked by kap 0
-      const int y = tr * TH + ty + rho0, x = tc * TW + tx - 1 - (kap == 1 ? 1 : 0);
-      const bool valid = tx >= 1 && tx <= TW && y < PR2 && x >= 0 && x < PC2;
-      const int64_t pos = valid ? int64_t(y) * PC2 + x : 0;
-      const uint32_t kc = vc / 3;                              // column-class stage (phase of the DF barriers)
-      const uint32_t pk = tl * 2 + (kap >= 3 ? 1 : 0);         // use count of the parking columns
-      const bool park = kap == 0 || kap == 3, unpark = kap == 1 || kap == 4;
-      mbar_wait(bars + 8 * (DF0 + rho0), kc & 1, 64);
-      if (nrho == 2) mbar_wait(bars + 8 * (DF0 + rho0 + 1), kc & 1, 64);
-      tc_fence_after();
-      // residual of row class rho = centre cell PM[A(rho)][B(kap)] = the (dy=1,dx=1) operand of that variant, still in its
-      // slab: tile row ty + rho + 1 - r0(A), entry tx + xs (the slab is only released once every epilogue thread has read
-      // its share)
-      const int bsl = cls_of(rep_of(kap)) == 1 ? 3 : 0;
-      const unsigned char* rp[2];
+      const int yb = tr * TH + ty, xb = tc * TW + tx - 1;      // plane position of this lane in an unshifted frame
+      const __half* pm_t = pmq + (int64_t(pl) * 8 + hf * 4) * cstep;
+      __half* yq_t = yq + (int64_t(pl) * 8 + hf * 4) * cstep;
+#pragma unroll 1
+      for (int kap = 0; kap < 5; ++kap, ++kc) {
+        const int xs = kap == 0 ? -1 : (kap == 4 ? 1 : 0);     // frame shift of this column class (entries)
+        const int bcl = kap == 0 ? 0 : (kap == 4 ? 2 : 1);     // PM column class of the centre tap
+        const int Be = kap <= 1 ? 0 : (kap == 2 ? 1 : 2);
+        const bool park = kap == 0 || kap == 3, unpark = kap == 1 || kap == 4;
+        // pooled cell column = the LEFT column of the pair: kap 1 holds column x+1 of the cell whose column x kap 0 parked
+        const int xo = xb + xs, x = xb - (kap == 1 ? 1 : 0);
+        const bool xok = xo >= 0 && xo < PC2, xval = tx >= 1 && tx <= TW && x >= 0 && x < PC2;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int rho = rho0 + (p < nrho ? p : 0), a = cls_of(rep_of(rho));
-        rp[p] = smem + S_T + (bsl + a) * TBYTES + ((ty + rho + 1 - tile_r0(a)) * TP + tx + xs) * 16;
-      }
-      const int Be = kap <= 1 ? 0 : (kap == 2 ? 1 : 2);
-      __half* dst = yq + (int64_t((it * 3 + Be) * 4 + pl) * 8 * psz + pos) * 8;
+        for (int it = 0; it < 3; ++it) {
+          constexpr int kRho0[3] = {0, 2, 3};
+          const int rho0 = kRho0[it], nrho = it == 1 ? 1 : 2;
+          // residual of row class rho = centre cell PM[A(rho)][B(kap)] at the variant's own position.  It is read from
+          // GLOBAL memory (L2: the loader has just pulled the same tiles) rather than from the class tiles in shared
+          // memory, and before the accumulator wait: the load latency disappears behind the MMAs and the tiles are free
+          // for the next loads as soon as the MMAs have read them.
+          uint4 res[2][4];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {                         // 32 channels at a time
-        float acc[32];
+          for (int p = 0; p < 2; ++p) {
+            if (p < nrho) {
+              const int rho = rho0 + p, a = cls_of(rep_of(rho));
+              const int yo = yb + rho;
+              const bool rok = xok && yo < PR2;                // outside the plane the tile holds TMA zero fill
+              const uint4* rg = reinterpret_cast<const uint4*>(
+                  pm_t + int64_t((a * 3 + bcl) * 32) * cstep + (rok ? int64_t(yo) * PC2 + xo : 0) * 8);
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          if (p < nrho) {
-            const int rho = rho0 + p;
-            float v[32];
-            tmem_ld16(lane_addr + rho * 64 + hf * 32, v);
-            tmem_ld16(lane_addr + rho * 64 + hf * 32 + 16, v + 16);
-            uint4 res[4];
+              for (int k = 0; k < 4; ++k) res[p][k] = rok ? __ldg(rg + int64_t(k) * psz) : make_uint4(0, 0, 0, 0);
+            }
+          }
+          tmem_st_wait();                                      // a value parked by the previous item has landed by now
+          if ((warp & 3) == 0 && lane == 0) C2S_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4);
+          mbar_wait(bars + 8 * (DF0 + rho0), kc & 1, 64);
+          if (nrho == 2) mbar_wait(bars + 8 * (DF0 + rho0 + 1), kc & 1, 64);
+          tc_fence_after();
+          if ((warp & 3) == 0 && lane == 0) C2S_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4 + 1);
+          float v[2][32], s[32];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) res[k] = *reinterpret_cast<const uint4*>(rp[p] + (hf * 4 + k) * CH);
-            tmem_ld_wait();
-            if (hf == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (DE0 + rho)); }
-            const float* bb = sbias + hf * 32;
+          for (int p = 0; p < 2; ++p) {
+            if (p < nrho) {
+              tmem_ld16(lane_addr + uint32_t((rho0 + p) * 64 + hf * 32), v[p]);
+              tmem_ld16(lane_addr + uint32_t((rho0 + p) * 64 + hf * 32 + 16), v[p] + 16);
+            }
+          }
+          // column pairs: kap 0 (kap 3) parks its row-pooled 32 channels in this thread's own scratch columns; the same
+          // thread picks them up when kap 1 (kap 4) has drained -- program order, no barrier
+          const uint32_t pcol = lane_addr + uint32_t(kPark + it * 64 + hf * 32);
+          if (unpark) { tmem_ld16(pcol, s); tmem_ld16(pcol + 16, s + 16); }
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bars + 8 * (DE0 + rho0));
+          if (nrho == 2) mbar_arrive(bars + 8 * (DE0 + rho0 + 1));
+          float acc[32];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const __half2* hr = reinterpret_cast<const __half2*>(&res[k]);
+          for (int p = 0; p < 2; ++p) {
+            if (p < nrho) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(hr[e]);
-                const float y0 = fmaxf(v[k * 8 + 2 * e] + (f.x + bb[k * 8 + 2 * e]), 0.f);
-                const float y1 = fmaxf(v[k * 8 + 2 * e + 1] + (f.y + bb[k * 8 + 2 * e + 1]), 0.f);
-                if (p == 0) { acc[k * 8 + 2 * e] = y0; acc[k * 8 + 2 * e + 1] = y1; }
-                else { acc[k * 8 + 2 * e] = (acc[k * 8 + 2 * e] + y0) * 0.5f; acc[k * 8 + 2 * e + 1] = (acc[k * 8 + 2 * e + 1] + y1) * 0.5f; }
+              for (int k = 0; k < 4; ++k) {
+                const __half2* hr = reinterpret_cast<const __half2*>(&res[p][k]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(hr[e]);
+                  const float y0 = fmaxf(v[p][k * 8 + 2 * e] + (f.x + bb[k * 8 + 2 * e]), 0.f);
+                  const float y1 = fmaxf(v[p][k * 8 + 2 * e + 1] + (f.y + bb[k * 8 + 2 * e + 1]), 0.f);
+                  if (p == 0) { acc[k * 8 + 2 * e] = y0; acc[k * 8 + 2 * e + 1] = y1; }
+                  else { acc[k * 8 + 2 * e] = (acc[k * 8 + 2 * e] + y0) * 0.5f; acc[k * 8 + 2 * e + 1] = (acc[k * 8 + 2 * e + 1] + y1) * 0.5f; }
+                }
               }
             }
           }
-        }
-        const uint32_t pcol = lane_addr + uint32_t(kPark + it * 64 + hf * 32);
-        if (park) {
-          // wait until the previous use of these columns has been read back (by the other group, one column class later)
-          if (hf == 0) { mbar_wait(bars + 8 * (SE0 + it), (pk & 1) ^ 1, 65); tc_fence_after(); }
-          tmem_st16(pcol, acc);
-          tmem_st16(pcol + 16, acc + 16);
-          if (hf == 1) { tmem_st_wait(); tc_fence_before(); mbar_arrive(bars + 8 * (SF0 + it)); }
-        } else {
-          if (unpark) {
-            if (hf == 0) { mbar_wait(bars + 8 * (SF0 + it), pk & 1, 66); tc_fence_after(); }
-            float s[32];
-            tmem_ld16(pcol, s);
-            tmem_ld16(pcol + 16, s + 16);
-            tmem_ld_wait();
-            if (hf == 1) { tc_fence_before(); mbar_arrive(bars + 8 * (SE0 + it)); }
+          if (park) {
+            tmem_st16(pcol, acc);
+            tmem_st16(pcol + 16, acc + 16);
+          } else {
+            if (unpark) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc[c] = (acc[c] + s[c]) * 0.5f;
-          }
-          if (valid) {
+              for (int c = 0; c < 32; ++c) acc[c] = (acc[c] + s[c]) * 0.5f;
+            }
+            const int y = yb + rho0;                           // the item's frame lives rho0 rows further down
+            if (xval && y < PR2) {
+              __half* dst = yq_t + int64_t((it * 3 + Be) * 32) * cstep + (int64_t(y) * PC2 + x) * 8;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              __half2 h[4];
+              for (int k = 0; k < 4; ++k) {
+                __half2 h[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[k * 8 + 2 * e], acc[k * 8 + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(dst + int64_t(hf * 4 + k) * psz * 8) = *reinterpret_cast<uint4*>(h);
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[k * 8 + 2 * e], acc[k * 8 + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(dst + int64_t(k) * cstep) = *reinterpret_cast<uint4*>(h);
+              }
             }
           }
+          if ((warp & 3) == 0 && lane == 0) C2S_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4 + 2);
         }
       }
-      // this thread's last residual read of a slab releases its share of all three class tiles (a thread sees one parity of
-      // r = kap*3 + it per tile): left tiles are read by kap = 0 only, mid tiles by kap = 1..3, right tiles by kap = 4
-      if (r == 1 || r == 2 || r == 13 || r == 14) { mbar_arrive(bars + 8 * (XE0 + 0)); mbar_arrive(bars + 8 * (XE0 + 1)); mbar_arrive(bars + 8 * (XE0 + 2)); }
-      else if (r == 10 || r == 11) { mbar_arrive(bars + 8 * (ME0 + 0)); mbar_arrive(bars + 8 * (ME0 + 1)); mbar_arrive(bars + 8 * (ME0 + 2)); }
     }
   }
   tc_fence_before();
@@ -555,6 +574,12 @@ extern "C" int cmlpl_conv1_scene_planes_f16(const void* f0pad, int cols, int w, 
   CMLPL_CHECK_LAUNCH("pool1q_scene");
   return CMLPL_OK;
 }
+
+#ifdef CMLPL_C2S_TRACE
+extern "C" int cmlpl_debug_c2s_trace(unsigned long long* host) {
+  return cudaMemcpyFromSymbol(host, c2s::g_trace, sizeof(c2s::g_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_rows, const void* packed, void* yq,
                                      cmlpl_stream_t stream) {
