@@ -109,7 +109,7 @@ struct PackedLayout {
   size_t w1s;     // f16 [4 n-tiles][KC][256][8]  feat_spe weight, UMMA B operand tiles (K padded to 16)
   size_t wc16;    // f16 [(P*8 + 128) k-chunks][16 classes][8]  classifier over [conv(pos,ch) | spectral]
   size_t wcq;     // f16 per (Alpha,Beta) block [8 k-chunks][N = maps*16 rows = map*16+cls][8]: 0.25 * conv classifier
-                  //     columns of pooled cell (I,J), maps in lmap_index order (w = 20 only; pool2_cls_kernel)
+                  //     columns of pooled cell (I,J), per border block (Al,Be), rows J-major (w = 20 only; pool2_cls_kernel)
   size_t total;
   int conv_pos;   // P = (w/4)^2 pooled positions
   int kc_spe_in;  // KC = ceil(B/16)*2: 16-byte K-chunks of the spectral input

@@ -408,33 +408,38 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
 }
 
 // =================================================================================================
-// pool2_cls_kernel: L[m][y',x'][cls] = sum_{u,v} (Wc[I,J]/4) . Y[rho(2I+u)][kap(2J+v)][y'+u, x'+v]
-// The 25 (I,J) maps are grouped in 9 blocks by the pooled border class (Alpha, Beta) of (I, J)
-// (Alpha = 0: I=0, 1: I=1..3, 2: I=4): all maps of a block read the same half-pooled map YP[Alpha][Beta] -- border
-// classes already averaged over their two variants by conv2_scene_kernel, the middle class still per position -- so a
-// block is (Alpha==1 ? 2 : 1) x (Beta==1 ? 2 : 1) shifts x 4 k-steps tcgen05.mma with M = 128 positions, N = 16 classes
-// x maps of the block (16/48/144), accumulating into the block's TMEM columns; the (u,v) shift is an A-descriptor
-// offset in the tile and the block's weights carry 1/4, 1/2 or 1 (pack.cu).
+// pool2_cls_kernel:  M[I][y',x'][cls] = sum_J L[I][J][y', x'+2J],
+//                    L[I][J][y',x'][cls] = sum_{u,v} (Wc[I,J]/4) . Y[rho(2I+u)][kap(2J+v)][y'+u, x'+v]
+// A pixel's conv logits are sum_{I,J} L[I][J][r'+2I, c'+2J]; the sum over J is taken here, so that 5 row maps leave the
+// kernel instead of 25 cell maps and the head gathers 5 vectors per pixel.  Inputs are the 9 half-pooled maps YP[Al][Be]
+// of conv2_scene_kernel (border classes already averaged over their two variants, the middle class per position).  For a
+// pooled row class Al and a pooled column J the tile of YP[Al][Be(J)] is loaded with its origin 2J columns to the right
+// (the column shift of the J-sum is a TMA coordinate), the remaining 2x2 pool of the middle classes is an A-descriptor
+// offset (u,v) inside the tile, and the maps I of the row class share the operand: (Al==1 ? 2 : 1) x (Be==1 ? 2 : 1)
+// shifts x 4 k-steps tcgen05.mma with M = 128 positions, N = 16 classes x (1 or 3) maps, all J accumulating into the
+// same TMEM columns.  The block weights carry 1/4, 1/2 or 1 (pack.cu).  Two accumulator stages: the MMAs of the next
+// tile run under the read-out of this one.
 namespace p2c {
 constexpr int TH = 4, TP = 32, TW = 31;              // outputs valid for tx = 0..30 (tx+1 must be in the tile)
 constexpr int CH = (TH + 1) * TP * 16;               // 2 560: one chunk plane of a tile, dense (written by TMA)
-constexpr int TBYTES = 8 * CH;                       // 20 480: one Y variant tile
-constexpr int NSLOT = 8;                             // ring of variant tiles (164 KB in flight per SM)
+constexpr int TBYTES = 8 * CH;                       // 20 480: one map tile
+constexpr int NSLOT = 8;                             // ring of map tiles (164 KB in flight per SM)
 constexpr int WBYTES = 400 * 128;                    // 25 maps x 16 classes x 64 channels, f16
 constexpr int S_W = 0, S_T = WBYTES, S_BAR = S_T + NSLOT * TBYTES + 128, S_TMEM = S_BAR + 256;   // +128: shifted A rows of the last slot
 constexpr int SMEM = (S_TMEM + 16 + 127) / 128 * 128;
 constexpr int kEpi = 256, kThreads = kEpi + 64;      // warps 0-7 epilogue, warp 8 loader, warp 9 MMA issuer
 constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1;
-enum { F0 = 0, E0 = NSLOT, DFULL = 2 * NSLOT, DEMPTY, W_FULL };
+enum { F0 = 0, E0 = NSLOT, DFULL0 = 2 * NSLOT, DEMPTY0 = 2 * NSLOT + 2, W_FULL = 2 * NSLOT + 4 };
 static_assert(SMEM <= 232448, "pool2_cls: shared memory over the 227 KB limit");
 static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "pool2_cls: TMA destinations must be 128-byte aligned");
 }  // namespace p2c
 
-// yq f16 [9][4][8][PR2][PC2][8];  wcq f16 per block [8 kchunks][N rows = map*16 + cls][8];
-// lmap f32 [4][25][4][PR2][PC2][4]
-// The kernel streams 1 152 B of YP per position once: every map tile ((TH+1) rows x 32 entries x 8 chunks,
-// 20 KB) is ONE cp.async.bulk.tensor (TMA, 4-D tile mode, zero fill outside the plane) into a ring of 8 slots,
-// each with its own full / empty mbarrier, so a single loader thread runs up to 8 maps ahead of the MMAs.
+// yq f16 [9][4][8][PR2][PC2][8];  wcq f16 per block (Al,Be) [8 kchunks][N rows = ((J-J0)*nI + I-I0)*16 + cls][8];
+// lmap f32 [4 planes][5 = I][4 class quads][PR2][PC2][4]
+// Every map tile ((TH+1) rows x 32 entries x 8 chunks, 20 KB) is ONE cp.async.bulk.tensor (TMA, 4-D tile mode, zero
+// fill outside the plane) into a ring of 8 slots, each with its own full / empty mbarrier, so a single loader thread
+// runs up to 8 tiles ahead of the MMAs; 15 loads per output tile (the three middle columns re-read their map at
+// three origins, from L2).
 __global__ void __launch_bounds__(p2c::kThreads, 1)
 pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int nq, const unsigned char* __restrict__ wcq,
                  float* __restrict__ lmap) {
@@ -456,10 +461,10 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
     fence_barrier_init();
     bulk_weights_g2s(sbase + S_W, wcq, WBYTES, bars + 8 * W_FULL);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(bars + 8 * (F0 + s), 1); mbar_init(bars + 8 * (E0 + s), 1); }
-    mbar_init(bars + 8 * DFULL, 1); mbar_init(bars + 8 * DEMPTY, kEpi);
+    for (int s = 0; s < 2; ++s) { mbar_init(bars + 8 * (DFULL0 + s), 1); mbar_init(bars + 8 * (DEMPTY0 + s), kEpi); }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 512);
+  if (warp == kMmaWarp) tmem_alloc(sbase + S_TMEM, 256);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -467,7 +472,7 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
 
   if (warp == kLoadWarp) {
-    // ================================================================ loader: one TMA per variant tile
+    // ================================================================ loader: one TMA per (row class, pooled column)
     if (lane == 0) {
       tma_prefetch_desc(&tm_y);
       uint32_t slot = 0, ph = 0;
@@ -475,86 +480,99 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
         const int pl = t / tiles_p, tt = t - pl * tiles_p;
         const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
 #pragma unroll 1
-        for (int b = 0; b < 9; ++b) {                          // block b = (Al, Be) reads the half-pooled map YP[b] only
+        for (int q = 0; q < 15; ++q) {
+          const int Al = q / 5, J = q - Al * 5, Be = J == 0 ? 0 : (J == 4 ? 2 : 1);
           mbar_wait(bars + 8 * (E0 + slot), ph ^ 1, 71);
           mbar_arrive_expect_tx(bars + 8 * (F0 + slot), TBYTES);
-          tma_load_tile(sbase + S_T + slot * TBYTES, &tm_y, tc * TW, tr * TH, b * 4 + pl, bars + 8 * (F0 + slot));
+          tma_load_tile(sbase + S_T + slot * TBYTES, &tm_y, tc * TW + 2 * J, tr * TH, (Al * 3 + Be) * 4 + pl, bars + 8 * (F0 + slot));
           if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
-    if (tmem != 0) { printf("pool2_cls: unexpected TMEM base %u\n", tmem); __trap(); }
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
     uint32_t slot = 0, ph = 0, tj = 0;
     mbar_wait(bars + 8 * p2c::W_FULL, 0, 70);                  // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tj) {
-      mbar_wait(bars + 8 * DEMPTY, (tj & 1) ^ 1, 72);          // epilogue of the previous tile has drained TMEM
+      const uint32_t st = tj & 1;
+      mbar_wait(bars + 8 * (DEMPTY0 + st), ((tj >> 1) & 1) ^ 1, 72);   // this stage's previous tile has been read out
       tc_fence_after();
 #pragma unroll
-      for (int b = 0; b < 9; ++b) {
-        const int Al = b / 3, Be = b % 3;
-        const int N = blk_n(Al) * blk_n(Be) * 16;
-        const int nu = Al == 1 ? 2 : 1, nv = Be == 1 ? 2 : 1;   // border classes arrive pooled from conv2_scene_kernel
+      for (int Al = 0; Al < 3; ++Al) {
+        constexpr int dummy = 0; (void)dummy;
+        const int nI = blk_n(Al), N = nI * 16, nu = Al == 1 ? 2 : 1;
         const uint32_t idesc = make_idesc_f16(128, N);
-        const uint32_t w_lo = ((sbase + S_W + blk_start(b) * 16 * 128) >> 4) | (uint32_t((N * 16) >> 4) << 16);
-        mbar_wait(bars + 8 * (F0 + slot), ph, 73);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t t_lo = ((sbase + S_T + slot * TBYTES) >> 4) | (uint32_t(CH >> 4) << 16);
+        const uint32_t dcol = tmem + st * 128 + uint32_t(blk_first(Al) * 16);
 #pragma unroll
-          for (int u = 0; u < nu; ++u) {
+        for (int J = 0; J < 5; ++J) {
+          const int Be = J == 0 ? 0 : (J == 4 ? 2 : 1), nv = Be == 1 ? 2 : 1;
+          const int Nb = nI * blk_n(Be) * 16;                  // rows of the block (Al, Be): its k-chunk stride
+          const uint32_t w_lo = ((sbase + S_W + blk_start(Al * 3 + Be) * 16 * 128 + (J - blk_first(Be)) * N * 16) >> 4) |
+                                (uint32_t((Nb * 16) >> 4) << 16);
+          mbar_wait(bars + 8 * (F0 + slot), ph, 73);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t t_lo = ((sbase + S_T + slot * TBYTES) >> 4) | (uint32_t(CH >> 4) << 16);
 #pragma unroll
-            for (int v = 0; v < nv; ++v) {
+            for (int u = 0; u < nu; ++u) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t a = t_lo + uint32_t(((u * TP + v) * 16 + ks * 2 * CH) / 16);
-                const uint32_t bw = w_lo + uint32_t((ks * 2 * N * 16) / 16);
-                umma_f16(uint32_t(blk_start(b) * 16), kHi | uint64_t(a), kHi | uint64_t(bw), idesc, (u | v | ks) ? 1u : 0u);
+              for (int v = 0; v < nv; ++v) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint32_t a = t_lo + uint32_t(((u * TP + v) * 16 + ks * 2 * CH) / 16);
+                  const uint32_t bw = w_lo + uint32_t((ks * 2 * Nb * 16) / 16);
+                  umma_f16(dcol, kHi | uint64_t(a), kHi | uint64_t(bw), idesc, (J | u | v | ks) ? 1u : 0u);
+                }
               }
             }
+            umma_commit(bars + 8 * (E0 + slot));
+            if (Al == 2 && J == 4) umma_commit(bars + 8 * (DFULL0 + st));
           }
-          umma_commit(bars + 8 * (E0 + slot));
-          if (b == 8) umma_commit(bars + 8 * DFULL);
+          __syncwarp();
+          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
       }
     }
   } else {
-    // ================================================================ epilogue (warps 0-7)
+    // ================================================================ epilogue (warps 0-7): warps 0-3 read out I = 0..2, warps 4-7 I = 3, 4
     const int L = (warp & 3) * 32 + lane, half = warp >> 2;
-    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t lane_addr = tmem + (uint32_t((warp & 3) * 32) << 16);
     const int ty = L >> 5, tx = L & 31;
-    const int m0 = half ? 13 : 0, m1 = half ? 25 : 13;
+    const int m0 = half ? 3 : 0, m1 = half ? 5 : 3;
     uint32_t tj = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tj) {
       const int pl = t / tiles_p, tt = t - pl * tiles_p;
       const int tr = tt / tiles_c, tc = tt - tr * tiles_c;
       const int y = tr * TH + ty, x = tc * TW + tx;
       const bool valid = tx < TW && y < PR2 && x < PC2;
-      // lmap f32 [4 planes][25 maps][4 class quads][PR2][PC2][4]: a warp's store of one (map, quad) is 512 contiguous bytes
-      float4* dst = reinterpret_cast<float4*>(lmap) + int64_t(pl) * 100 * psz + (valid ? int64_t(y) * PC2 + x : 0);
-      mbar_wait(bars + 8 * DFULL, tj & 1, 74);
+      const uint32_t st = tj & 1;
+      // lmap f32 [4 planes][5 maps][4 class quads][PR2][PC2][4]: a warp's store of one (map, quad) is 512 contiguous bytes
+      float4* dst = reinterpret_cast<float4*>(lmap) + int64_t(pl) * 20 * psz + (valid ? int64_t(y) * PC2 + x : 0);
+      mbar_wait(bars + 8 * (DFULL0 + st), (tj >> 1) & 1, 74);
       tc_fence_after();
-#pragma unroll 1
-      for (int m = m0; m < m1; ++m) {
-        float v[16];
-        tmem_ld16(lane_addr + m * 16, v);
-        tmem_ld_wait();
-        if (m == m1 - 1) { tc_fence_before(); mbar_arrive(bars + 8 * DEMPTY); }
-        if (valid) {
+      float v[3][16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)                         // class quads beyond the real classes are never read (head_sum_kernel)
-            if (q < nq) dst[int64_t(m * 4 + q) * psz] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int m = 0; m < 3; ++m)
+        if (m0 + m < m1) tmem_ld16(lane_addr + st * 128 + uint32_t((m0 + m) * 16), v[m]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bars + 8 * (DEMPTY0 + st));
+      if (valid) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          if (m0 + m < m1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)                         // class quads beyond the real classes are never read (head_sum_kernel)
+              if (q < nq) dst[int64_t((m0 + m) * 4 + q) * psz] = make_float4(v[m][4 * q], v[m][4 * q + 1], v[m][4 * q + 2], v[m][4 * q + 3]);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 }  // namespace cmlpl

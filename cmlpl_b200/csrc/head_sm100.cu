@@ -253,22 +253,19 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
       const int64_t p = mt * 128 + L;
       if (p < n) {
         if (lmap) {
-          // conv part of the classifier from the dense path: 25 gathered class-partial vectors
-          // L[I][J][r'+2I, c'+2J] of this pixel's parity plane (conv2_scene_sm100.cu), fixed summation order
+          // conv part of the classifier from the dense path: 5 gathered row-map vectors M[I][r'+2I, c'] of this pixel's
+          // parity plane (pool2_cls_kernel has already summed the pooled columns J), fixed summation order
           const int r = int(p / cols), c = int(p - int64_t(r) * cols);
           const int64_t psz = int64_t(PR2) * PC2;
-          const float4* base = reinterpret_cast<const float4*>(lmap) + int64_t((r & 1) * 2 + (c & 1)) * 100 * psz +
+          const float4* base = reinterpret_cast<const float4*>(lmap) + int64_t((r & 1) * 2 + (c & 1)) * 20 * psz +
                                int64_t(r >> 1) * PC2 + (c >> 1);
 #pragma unroll
           for (int I = 0; I < 5; ++I) {
+            const float4* q = base + int64_t(I * 4) * psz + (2 * I) * PC2;
 #pragma unroll
-            for (int J = 0; J < 5; ++J) {
-              const float4* q = base + int64_t(lmap_index(I, J) * 4) * psz + (2 * I) * PC2 + 2 * J;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float4 t = __ldg(q + int64_t(k) * psz);
-                v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
-              }
+            for (int k = 0; k < 4; ++k) {
+              const float4 t = __ldg(q + int64_t(k) * psz);
+              v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
             }
           }
         }
@@ -480,8 +477,8 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
 }
 
 // ------------------------------------------------------------------ head of the dense path: sums + argmax
-// logits(p) = bc + sum over the 4 hidden quarters of part[q][p] + the 25 gathered conv partials of pixel p
-// (class-partial maps of pool2_cls_kernel); first index wins ties (hyper_tools.py:426).  One thread per pixel:
+// logits(p) = bc + sum over the 4 hidden quarters of part[q][p] + the 5 gathered conv partials M[I][r'+2I, c'] of pixel p
+// (row maps of pool2_cls_kernel); first index wins ties (hyper_tools.py:426).  One thread per pixel:
 // adjacent lanes read adjacent 16-byte quads of the two parity planes of a row.
 __global__ void __launch_bounds__(256)
 head_sum_kernel(const float* __restrict__ part, int64_t mtiles, const float* __restrict__ lmap, int cols, int PR2, int PC2,
@@ -494,19 +491,16 @@ head_sum_kernel(const float* __restrict__ part, int64_t mtiles, const float* __r
   for (int c = 0; c < 16; ++c) v[c] = 0.f;
   const int r = int(p / cols), c0 = int(p - int64_t(r) * cols);
   const int64_t psz = int64_t(PR2) * PC2;
-  const float4* base = reinterpret_cast<const float4*>(lmap) + int64_t((r & 1) * 2 + (c0 & 1)) * 100 * psz +
+  const float4* base = reinterpret_cast<const float4*>(lmap) + int64_t((r & 1) * 2 + (c0 & 1)) * 20 * psz +
                        int64_t(r >> 1) * PC2 + (c0 >> 1);
 #pragma unroll
   for (int I = 0; I < 5; ++I) {
+    const float4* q = base + int64_t(I * 4) * psz + (2 * I) * PC2;
 #pragma unroll
-    for (int J = 0; J < 5; ++J) {
-      const float4* q = base + int64_t(lmap_index(I, J) * 4) * psz + (2 * I) * PC2 + 2 * J;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < nq) {
-          const float4 t = __ldg(q + int64_t(k) * psz);
-          v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
-        }
+    for (int k = 0; k < 4; ++k) {
+      if (k < nq) {
+        const float4 t = __ldg(q + int64_t(k) * psz);
+        v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
       }
     }
   }

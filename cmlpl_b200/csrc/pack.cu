@@ -85,7 +85,7 @@ __global__ void pack_kernel(PackArgs a) {
         d[i] = __float2half_rn(v);
       }
     } break;
-    case 8: {  // dense-path classifier: per block [8 kc][N][8], row = map*16 + cls, value = Wc[cls][ch,I,J] / 4 for the
+    case 8: {  // dense-path classifier: per block [8 kc][N][8], row = ((J-J0)*nI + (I-I0))*16 + cls, value = Wc[cls][ch,I,J] / 4 for the
                // middle classes; a border class arrives averaged over its two variants (conv2_scene_kernel), so its factor
                // doubles per border direction
       if (a.P != 25) break;
@@ -97,8 +97,9 @@ __global__ void pack_kernel(PackArgs a) {
         const int Al = b / 3, Be = b % 3, N = blk_n(Al) * blk_n(Be) * 16;
         const int64_t li = i - int64_t(blk_start(b)) * 16 * 64;
         const int e = int(li & 7), row = int((li >> 3) % N), kc = int((li >> 3) / N);
-        const int mi = row >> 4, cls = row & 15, ch = kc * 8 + e;
-        const int I = blk_first(Al) + mi / blk_n(Be), J = blk_first(Be) + mi % blk_n(Be);
+        // rows J-major: the maps of one pooled column J (all I of the block) are one contiguous B operand
+        const int nI = blk_n(Al), cls = row & 15, ch = kc * 8 + e;
+        const int I = blk_first(Al) + (row >> 4) % nI, J = blk_first(Be) + (row >> 4) / nI;
         const float sc = 0.25f * (Al != 1 ? 2.f : 1.f) * (Be != 1 ? 2.f : 1.f);
         d[i] = __float2half_rn(cls < a.C ? sc * a.cw[int64_t(cls) * in_f + ch * 25 + I * 5 + J] : 0.f);
       }

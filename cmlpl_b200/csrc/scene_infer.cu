@@ -228,7 +228,7 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
     s.g = o;                                               // (fp32 conv1 variants: not materialised any more)
     s.pm = o; o = align256(o + qpos * 9 * 64 * 2);         // pooled variants, f16 parity planes [9][4][8][PR2][PC2][8]
     s.yq = o; o = align256(o + qpos * 9 * 64 * 2);         // half-pooled conv2 maps, f16 [9][4][8][PR2][PC2][8]
-    s.lmap = o; o = align256(o + qpos * 25 * 16 * 4);      // class partials, f32 [4][25][4][PR2][PC2][4]
+    s.lmap = o; o = align256(o + qpos * 5 * 16 * 4);       // class partials per pooled row, f32 [4][5][4][PR2][PC2][4]
   } else {
     s.p2 = o; o = align256(o + size_t(n) * P * 64 * 2);     // per-pixel pooled conv features (patch_cnn_sm100.cu)
     if (!s.tc) {

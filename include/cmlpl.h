@@ -193,9 +193,12 @@ int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, con
  *                                   kap) are averaged in the epilogue:  yq f16 [9 = Al*3+Be][4][8][PR2][PC2][8],
  *                                   yq[Al][Be][y',x'] = mean over the border partners of Y[rho][kap][y'+u, x'+v]
  *   cmlpl_pool2_cls_f16           : rest of the 2x2 avg-pool (middle classes) + conv columns of the classifier per
- *                                   pooled cell (I,J):  lmap f32 [4][25][4 class quads][PR2][PC2][4]
- *   cmlpl_head_lmap_tc            : spectral classifier columns (h16 tiles) + the 25 gathered partials of each
- *                                   pixel + bias, argmax -> labels u8 [band_rows*cols] (and logits) */
+ *                                   pooled cell (I,J), summed over the pooled columns J of a pooled row I:
+ *                                   lmap f32 [4][5 = I][4 class quads][PR2][PC2][4],
+ *                                   lmap[I][y',x'] = sum_J L[I][J][y', x'+2J]
+ *   cmlpl_head_lmap_tc            : spectral classifier columns (h16 tiles) + the 5 gathered partials
+ *                                   lmap[I][r'+2I, c'] of each pixel + bias, argmax -> labels u8 [band_rows*cols]
+ *                                   (and logits) */
 int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
                                    cmlpl_stream_t stream);
 int cmlpl_conv1_scene_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
@@ -212,7 +215,7 @@ int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_rows, int num_
  *   cmlpl_spectral_logits_tc     : part f32 [4 hidden quarters][ceil(n/128)*128][16] = Wc_spe . relu(Wspe . x + b) per
  *                                  quarter of the 1024 hidden features (tools/models.py:142-143,150), <= 224 bands
  *   cmlpl_spectral_logits_raw_tc : the same from the raw cube (z-score folded into the fp16 conversion)
- *   cmlpl_head_sum_lmap          : 4 quarter partials + the 25 gathered conv partials + bias, argmax */
+ *   cmlpl_head_sum_lmap          : 4 quarter partials + the 5 gathered conv partials + bias, argmax */
 int cmlpl_spectral_logits_tc(const float* spectra, int64_t n, int num_features, int num_classes, int w,
                              const void* packed, void* x16, float* part, cmlpl_stream_t stream);
 int cmlpl_spectral_logits_raw_tc(const void* raw, int dtype, int64_t n, int num_features, int num_classes, int w,
