@@ -110,16 +110,6 @@ __global__ void pool1q_scene_kernel(const float* __restrict__ g, int PR, int PC,
 // kap = 1 (kap = 4) drains.  Per position the kernel stores 9 maps  YP[Al*3+Be]  (Al: rho {0+1 | 2 | 3+4}, Be alike),
 // each the AVERAGE of its pre-pooled partners; the classifier block weights carry the matching factor (pack.cu).
 namespace c2s {
-#ifdef CMLPL_C2S_TRACE
-// debugging aid (scripts/trace_conv2_scene.py builds a second library with this flag): clock64 stamps of one CTA
-__device__ unsigned long long g_trace[4][4096];
-__device__ __forceinline__ void trace_stamp(int role, uint32_t& n, uint32_t tag) {
-  if (blockIdx.x == 5 && n < 2047) { g_trace[role][2 * n] = clock64(); g_trace[role][2 * n + 1] = tag; ++n; }
-}
-#define C2S_TR(role, n, tag) trace_stamp(role, n, tag)
-#else
-#define C2S_TR(role, n, tag) ((void)0)
-#endif
 constexpr int TH = 4, TP = 32, TW = 30;
 constexpr int CH = (TH + 2) * TP * 16;               // 3 072: one chunk plane of a tile, dense (written by TMA)
 constexpr int TBYTES = 8 * CH;                       // 24 576: one PM variant tile (6 rows)
@@ -231,7 +221,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
           const uint32_t full = bars + 8 * ((slab ? MF0 : XF0) + a);
           mbar_wait(bars + 8 * ((slab ? ME0 : XE0) + a), (k & 1) ^ 1, 61);
           mbar_arrive_expect_tx(full, TBYTES);
-          C2S_TR(3, ntr, uint32_t(i));
+          CMLPL_TR(3, ntr, uint32_t(i));
           tma_load_tile(sbase + S_T + (slab * 3 + a) * TBYTES, &tm_pm, x0, y0 + tile_r0(a), (a * 3 + bcls) * 4 + pl, full);
           if (slab) ++fm[a]; else ++fx[a];
         }
@@ -247,10 +237,10 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
 #define C2S_GROUP(KAP, G, ...)                                                       \
     do {                                                                             \
       tc_fence_after();                                                              \
-      if (lane == 0) C2S_TR(0, ntr, KAP * 16 + G * 2);                               \
+      if (lane == 0) CMLPL_TR(0, ntr, KAP * 16 + G * 2);                               \
       if (elect_one_sync()) { issue_group<KAP, G>(t_lo, w_lo); __VA_ARGS__; }        \
       __syncwarp();                                                                  \
-      if (lane == 0) C2S_TR(0, ntr, KAP * 16 + G * 2 + 1);                           \
+      if (lane == 0) CMLPL_TR(0, ntr, KAP * 16 + G * 2 + 1);                           \
     } while (0)
     // WX / WM: this column class is the first to read a fresh fill of slab X / M (wait per class tile, just before the
     // first group that reads it); RX / RM: it is the last to read the resident fill (release per class tile)
@@ -338,11 +328,11 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
             }
           }
           tmem_st_wait();                                      // a value parked by the previous item has landed by now
-          if ((warp & 3) == 0 && lane == 0) C2S_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4);
+          if ((warp & 3) == 0 && lane == 0) CMLPL_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4);
           mbar_wait(bars + 8 * (DF0 + rho0), kc & 1, 64);
           if (nrho == 2) mbar_wait(bars + 8 * (DF0 + rho0 + 1), kc & 1, 64);
           tc_fence_after();
-          if ((warp & 3) == 0 && lane == 0) C2S_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4 + 1);
+          if ((warp & 3) == 0 && lane == 0) CMLPL_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4 + 1);
           float v[2][32], s[32];
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
@@ -397,7 +387,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
               }
             }
           }
-          if ((warp & 3) == 0 && lane == 0) C2S_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4 + 2);
+          if ((warp & 3) == 0 && lane == 0) CMLPL_TR(1 + hf, ntr, uint32_t(kap * 3 + it) * 4 + 2);
         }
       }
     }
@@ -593,11 +583,7 @@ extern "C" int cmlpl_conv1_scene_planes_f16(const void* f0pad, int cols, int w, 
   return CMLPL_OK;
 }
 
-#ifdef CMLPL_C2S_TRACE
-extern "C" int cmlpl_debug_c2s_trace(unsigned long long* host) {
-  return cudaMemcpyFromSymbol(host, c2s::g_trace, sizeof(c2s::g_trace)) == cudaSuccess ? 0 : 1;
-}
-#endif
+CMLPL_TRACE_EXPORT(cmlpl_debug_c2s_trace)
 
 extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_rows, const void* packed, void* yq,
                                      cmlpl_stream_t stream) {

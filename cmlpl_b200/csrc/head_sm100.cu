@@ -352,9 +352,11 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
   if (warp == kLoadWarp) {
     // ================================================================ loader: one bulk copy per pixel tile
     if (lane == 0) {
+      [[maybe_unused]] uint32_t ntr = 0;
       for (uint32_t j = 0; j < uint32_t(my_tiles); ++j) {
         const uint32_t s = j % uint32_t(nA), ph = (j / uint32_t(nA)) & 1;
         mbar_wait(bars + 8 * (A_EMPTY0 + s), ph ^ 1, 91);
+        CMLPL_TR(4, ntr, j);
         mbar_arrive_expect_tx(bars + 8 * (A_FULL0 + s), abytes);
         // one bulk copy moves ~6-7 GB/s however large it is: the tile goes as KC/2 copies of 4 KB in flight together
         const __half* src = x16 + (mt0 + int64_t(j) * mstep) * int64_t(KC) * 1024;
@@ -370,11 +372,15 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     // MMA1 only: gated by the input tile and a drained accumulator slot, never by the epilogue -> MMA2 hand-over, so it
     // really runs the full ring (3 units) ahead; MMA2 is issued by its own warp below
     mbar_wait(bars + 8 * W_FULL, 0, 90);                 // weights have landed
+    [[maybe_unused]] uint32_t ntr = 0;
     for (uint32_t u = 0; u < U; ++u) {
       const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, s = ti % uint32_t(nA);
+      if (lane == 0) CMLPL_TR(0, ntr, u * 4);
       if (hh == 0) mbar_wait(bars + 8 * (A_FULL0 + s), (ti / uint32_t(nA)) & 1, 92);
+      if (lane == 0) CMLPL_TR(0, ntr, u * 4 + 1);
       mbar_wait(bars + 8 * (D1_EMPTY0 + d), ((u / 3) & 1) ^ 1, 93);
       tc_fence_after();
+      if (lane == 0) CMLPL_TR(0, ntr, u * 4 + 2);
       if (elect_one_sync()) {
         uint32_t a_lo = ((sbase + S_A + s * abytes) >> 4) | (uint32_t(2048 >> 4) << 16);
         uint32_t b_lo = ((sbase + S_W + hh * 2048) >> 4) | (uint32_t(4096 >> 4) << 16);
@@ -386,17 +392,21 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
         if (hh == 1) umma_commit(bars + 8 * (A_EMPTY0 + s));
       }
       __syncwarp();
+      if (lane == 0) CMLPL_TR(0, ntr, u * 4 + 3);
     }
   } else if (warp == kMma2Warp) {
     // ================================================================ MMA2 issuer: classifier columns over the hidden half-tiles
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
     constexpr uint32_t idesc2 = make_idesc_f16(128, 16);
     mbar_wait(bars + 8 * W_FULL, 0, 90);
+    [[maybe_unused]] uint32_t ntr = 0;
     for (uint32_t u = 0; u < U; ++u) {
       const uint32_t ti = u >> 1, hh = u & 1, hs = u % uint32_t(nH), ls = ti & 3;
+      if (lane == 0) CMLPL_TR(1, ntr, u * 4);
       mbar_wait(bars + 8 * (H_FULL0 + hs), (u / uint32_t(nH)) & 1, 94);
       if (hh == 0) mbar_wait(bars + 8 * (L_EMPTY0 + ls), ((ti >> 2) & 1) ^ 1, 95);
       tc_fence_after();
+      if (lane == 0) CMLPL_TR(1, ntr, u * 4 + 2);
       if (elect_one_sync()) {
         uint32_t a_lo = ((sbase + S_H + hs * HBYTES) >> 4) | (uint32_t(2048 >> 4) << 16);
         uint32_t b_lo = ((sbase + S_WC + hh * 16 * 256) >> 4) | (uint32_t(256 >> 4) << 16);
@@ -410,6 +420,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
         if (hh == 1) umma_commit(bars + 8 * (L_FULL0 + ls));
       }
       __syncwarp();
+      if (lane == 0) CMLPL_TR(1, ntr, u * 4 + 3);
     }
   } else {
     // ================================================================ epilogue (warps 0-15)
@@ -437,12 +448,17 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
 #pragma unroll
       for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     };
+    [[maybe_unused]] uint32_t ntr = 0;
+    const bool tracer = (warp & 7) == 0 && lane == 0;
     for (uint32_t u = uint32_t(grp); u < U; u += uint32_t(G)) {
       const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, hs = u % uint32_t(nH);
       if (hh == 1 && ch == 0 && ti > 1) readout(ti - 2);      // deferred by two tiles (4 logits stages): its MMA2 has long completed
+      if (tracer) CMLPL_TR(2 + grp, ntr, u * 4);
       mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
+      if (tracer) CMLPL_TR(2 + grp, ntr, u * 4 + 1);
       mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
       tc_fence_after();
+      if (tracer) CMLPL_TR(2 + grp, ntr, u * 4 + 2);
       unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * (cpt / 8)) * 2048 + L * 16;
       const float* bb = sb + hh * 128 + ch * cpt;
 #pragma unroll 1
@@ -465,6 +481,7 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       }
       fence_proxy_async();                             // generic-proxy writes of H -> visible to the tensor core
       mbar_arrive(bars + 8 * (H_FULL0 + hs));
+      if (tracer) CMLPL_TR(2 + grp, ntr, u * 4 + 3);
     }
     if ((G == 1 || grp == 1) && ch == 0) {
       if (my_tiles > 1) readout(uint32_t(my_tiles - 2));
@@ -530,6 +547,8 @@ head_sum_kernel(const float* __restrict__ part, int64_t mtiles, const float* __r
 }  // namespace cmlpl
 
 using namespace cmlpl;
+
+CMLPL_TRACE_EXPORT(cmlpl_debug_spl_trace)
 
 // shared-memory plan of spectral_logits_kernel for KC input k-chunks: prefers 3 input stages + 2 hidden half-tiles
 static bool spectral_logits_plan(int KC, int* nA, int* nH, size_t* smem) {

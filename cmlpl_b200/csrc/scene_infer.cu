@@ -11,6 +11,8 @@
 //   4. head          spectral columns of the classifier (models.py:150) + the pixel's 25 gathered conv
 //                    partials + bias, argmax (hyper_tools.py:426, first index wins ties)
 //   (> 16 classes / > 224 bands: the all-per-pixel patch_cnn_sm100.cu kernel + CUDA-core classify instead)
+#include <mutex>
+
 #include "common.cuh"
 #include "gemm_core.cuh"
 
@@ -259,10 +261,29 @@ extern "C" int cmlpl_scene_workspace_layout(int band_rows, int cols, int num_fea
   return CMLPL_OK;
 }
 
+// The spectral branch (fp16 tiles of the spectra + the two spectral GEMMs) does not depend on the conv tower until the
+// head: it runs on a side stream forked off the caller's, so that its conversion kernel shares the SMs with conv0 and
+// its tail with the head of conv1_pool; the head waits for both.  One side stream and two events per device; host threads
+// that drive the same device from several streams take turns (the launches are microseconds).
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; std::mutex mu; };   // mu: one fork/join sequence at a time
+static SideStream* side_stream() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& x = per_dev[dev];
+  if (!x.s) {
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &x;
+}
+
 // conv1 (9 border classes) -> pooled parity planes -> conv2 (25 classes) -> pool + conv classifier columns ->
 // spectral classifier columns + gathered conv partials + argmax: everything after conv0 / the spectral GEMM
 static int dense_tail(unsigned char* wsb, const SceneWs& ws, int cols, int w, int band_rows, int num_features,
-                      int num_classes, const void* packed, uint8_t* labels, float* logits, cmlpl_stream_t stream) {
+                      int num_classes, const void* packed, uint8_t* labels, float* logits, cmlpl_stream_t stream,
+                      cudaEvent_t spectral_done = nullptr) {
   int rc = cmlpl_conv1_pool_planes_f16(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.pm, stream);
   if (rc != CMLPL_OK) return rc;
   rc = cmlpl_conv2_scene_f16(wsb + ws.pm, cols, w, band_rows, packed, wsb + ws.yq, stream);
@@ -270,6 +291,7 @@ static int dense_tail(unsigned char* wsb, const SceneWs& ws, int cols, int w, in
   rc = cmlpl_pool2_cls_f16(wsb + ws.yq, cols, w, band_rows, num_features, num_classes, packed,
                            reinterpret_cast<float*>(wsb + ws.lmap), stream);
   if (rc != CMLPL_OK) return rc;
+  if (spectral_done) CMLPL_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), spectral_done, 0));
   return cmlpl_head_sum_lmap(reinterpret_cast<const float*>(wsb + ws.h16), reinterpret_cast<const float*>(wsb + ws.lmap), cols,
                              band_rows, num_features, num_classes, w, packed, labels, logits, stream);
 }
@@ -384,14 +406,29 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
   CMLPL_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "scene_infer: workspace must be 256-byte aligned");
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   const int64_t n = int64_t(band_rows) * cols;
-  int rc = cmlpl_conv0_map_f16(cube, scene_rows, cols, slab_row0, slab_rows, w, band_row0, band_rows, packed,
-                               wsb + ws.f0pad, stream);
+  int rc = CMLPL_OK;
+  if (ws.tc && ws.dense) {
+    SideStream* sd = side_stream();
+    CMLPL_CHECK_ARG(sd, "scene_infer: cannot create the side stream");
+    std::lock_guard<std::mutex> lock(sd->mu);
+    cudaStream_t ms = static_cast<cudaStream_t>(stream);
+    CMLPL_CUDA(cudaEventRecord(sd->fork, ms));
+    CMLPL_CUDA(cudaStreamWaitEvent(sd->s, sd->fork, 0));
+    rc = cmlpl_spectral_logits_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16,
+                                  reinterpret_cast<float*>(wsb + ws.h16), sd->s);
+    if (rc != CMLPL_OK) return rc;
+    CMLPL_CUDA(cudaEventRecord(sd->join, sd->s));
+    rc = cmlpl_conv0_map_f16(cube, scene_rows, cols, slab_row0, slab_rows, w, band_row0, band_rows, packed, wsb + ws.f0pad, stream);
+    if (rc != CMLPL_OK) return rc;
+    return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream, sd->join);
+  }
+  rc = cmlpl_conv0_map_f16(cube, scene_rows, cols, slab_row0, slab_rows, w, band_row0, band_rows, packed,
+                           wsb + ws.f0pad, stream);
   if (rc != CMLPL_OK) return rc;
   if (ws.tc) {
     rc = cmlpl_spectral_logits_tc(spectra, n, num_features, num_classes, w, packed, wsb + ws.x16,
                                   reinterpret_cast<float*>(wsb + ws.h16), stream);
     if (rc != CMLPL_OK) return rc;
-    if (ws.dense) return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
     rc = cmlpl_patch_cnn_f16(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.p2, stream);
     if (rc != CMLPL_OK) return rc;
     return classify_launch(wsb + ws.p2, nullptr, reinterpret_cast<const float*>(wsb + ws.h16), ((n + 127) / 128) * 128, n,
@@ -439,21 +476,36 @@ extern "C" int cmlpl_scene_infer_raw(const void* raw, int dtype, int scene_rows,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t n = int64_t(band_rows) * cols;
   const int prow_n = band_rows + w - 1, pcol_n = cols + w - 1;
-  {
+  auto conv0_raw = [&]() {
     __half* f0 = reinterpret_cast<__half*>(wsb + ws.f0pad);
-    const int rc0 = dtype == 0
+    return dtype == 0
         ? launch_conv0_tc<uint16_t, false, true>(static_cast<const uint16_t*>(raw), num_features, scene_rows, cols, slab_row0, w,
                                                  band_row0, prow_n, pcol_n, wf, bf, mu, inv_sigma, f0, s)
         : launch_conv0_tc<float, false, true>(static_cast<const float*>(raw), num_features, scene_rows, cols, slab_row0, w,
                                               band_row0, prow_n, pcol_n, wf, bf, mu, inv_sigma, f0, s);
-    if (rc0 != CMLPL_OK) return rc0;
-  }
+  };
   const size_t esz = dtype == 0 ? 2 : 4;
   const void* band_raw = static_cast<const unsigned char*>(raw) + size_t(band_row0 - slab_row0) * cols * num_features * esz;
-  int rc = cmlpl_spectral_logits_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
-                                        wsb + ws.x16, reinterpret_cast<float*>(wsb + ws.h16), stream);
+  int rc = CMLPL_OK;
+  if (ws.dense) {                                          // spectral branch beside the conv tower (see side_stream())
+    SideStream* sd = side_stream();
+    CMLPL_CHECK_ARG(sd, "scene_infer_raw: cannot create the side stream");
+    std::lock_guard<std::mutex> lock(sd->mu);
+    CMLPL_CUDA(cudaEventRecord(sd->fork, s));
+    CMLPL_CUDA(cudaStreamWaitEvent(sd->s, sd->fork, 0));
+    rc = cmlpl_spectral_logits_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
+                                      wsb + ws.x16, reinterpret_cast<float*>(wsb + ws.h16), sd->s);
+    if (rc != CMLPL_OK) return rc;
+    CMLPL_CUDA(cudaEventRecord(sd->join, sd->s));
+    rc = conv0_raw();
+    if (rc != CMLPL_OK) return rc;
+    return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream, sd->join);
+  }
+  rc = conv0_raw();
   if (rc != CMLPL_OK) return rc;
-  if (ws.dense) return dense_tail(wsb, ws, cols, w, band_rows, num_features, num_classes, packed, labels, logits, stream);
+  rc = cmlpl_spectral_logits_raw_tc(band_raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed,
+                                    wsb + ws.x16, reinterpret_cast<float*>(wsb + ws.h16), stream);
+  if (rc != CMLPL_OK) return rc;
   rc = cmlpl_patch_cnn_f16(wsb + ws.f0pad, cols, w, band_rows, packed, wsb + ws.p2, stream);
   if (rc != CMLPL_OK) return rc;
   return classify_launch(wsb + ws.p2, nullptr, reinterpret_cast<const float*>(wsb + ws.h16), ((n + 127) / 128) * 128, n,

@@ -5,6 +5,25 @@
 
 namespace cmlpl {
 
+// ------------------------------------------------------------------ timeline tracing (debugging aid)
+// `make trace` builds a second library (scripts/_trace/, never loaded by the package) with -DCMLPL_TRACE: CMLPL_TR stamps
+// clock64 + a tag into a per-translation-unit device array for ONE CTA, CMLPL_TRACE_EXPORT(name) exports the function
+// that copies it out (scripts/trace_kernel.py).  In the product build both expand to nothing.
+#ifdef CMLPL_TRACE
+static __device__ unsigned long long g_trace[6][4096];
+__device__ __forceinline__ void trace_stamp(int role, uint32_t& n, uint32_t tag) {
+  if (blockIdx.x == 5 && n < 2047) { g_trace[role][2 * n] = clock64(); g_trace[role][2 * n + 1] = tag; ++n; }
+}
+#define CMLPL_TR(role, n, tag) ::cmlpl::trace_stamp(role, n, tag)
+#define CMLPL_TRACE_EXPORT(name)                                                                          \
+  extern "C" int name(unsigned long long* host) {                                                         \
+    return cudaMemcpyFromSymbol(host, ::cmlpl::g_trace, sizeof(::cmlpl::g_trace)) == cudaSuccess ? 0 : 1;  \
+  }
+#else
+#define CMLPL_TR(role, n, tag) ((void)0)
+#define CMLPL_TRACE_EXPORT(name)
+#endif
+
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
