@@ -267,14 +267,42 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
       C2S_GROUP(KAP, 4, (umma_commit(bars + 8 * (DF0 + 3)), umma_commit(bars + 8 * (DF0 + 4)), C2S_REL(2, RX, RM)));   \
       ++kc;                                                                          \
     } while (0)
+    // Column classes whose class tiles are resident (or landed long ago) issue their five groups in two runs, PA + T1 and
+    // T2 + T3 + PB: every barrier poll between two groups is a few hundred cycles in which the issue queue runs dry.
+#define C2S_COLUMN2(KAP, WX, RX, RM)                                                 \
+    do {                                                                             \
+      const uint32_t ep = (kc & 1) ^ 1;                                              \
+      if (WX) { C2S_FILL(0, true, false); C2S_FILL(1, true, false); C2S_FILL(2, true, false); }              \
+      mbar_wait(bars + 8 * (DE0 + 0), ep, 63); mbar_wait(bars + 8 * (DE0 + 1), ep, 63); mbar_wait(bars + 8 * (DE0 + 2), ep, 63);   \
+      tc_fence_after();                                                              \
+      if (lane == 0) CMLPL_TR(0, ntr, KAP * 16 + 0);                                 \
+      if (elect_one_sync()) {                                                        \
+        issue_group<KAP, 0>(t_lo, w_lo); C2S_REL(0, RX, RM);                         \
+        issue_group<KAP, 1>(t_lo, w_lo); umma_commit(bars + 8 * (DF0 + 0));          \
+      }                                                                              \
+      __syncwarp();                                                                  \
+      if (lane == 0) CMLPL_TR(0, ntr, KAP * 16 + 3);                                 \
+      mbar_wait(bars + 8 * (DE0 + 3), ep, 63); mbar_wait(bars + 8 * (DE0 + 4), ep, 63);                       \
+      tc_fence_after();                                                              \
+      if (lane == 0) CMLPL_TR(0, ntr, KAP * 16 + 4);                                 \
+      if (elect_one_sync()) {                                                        \
+        issue_group<KAP, 2>(t_lo, w_lo); umma_commit(bars + 8 * (DF0 + 1));          \
+        issue_group<KAP, 3>(t_lo, w_lo); umma_commit(bars + 8 * (DF0 + 2)); C2S_REL(1, RX, RM);              \
+        issue_group<KAP, 4>(t_lo, w_lo); umma_commit(bars + 8 * (DF0 + 3)); umma_commit(bars + 8 * (DF0 + 4)); C2S_REL(2, RX, RM);   \
+      }                                                                              \
+      __syncwarp();                                                                  \
+      if (lane == 0) CMLPL_TR(0, ntr, KAP * 16 + 9);                                 \
+      ++kc;                                                                          \
+    } while (0)
     mbar_wait(bars + 8 * c2s::W_FULL, 0, 60);                  // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      C2S_COLUMN(0, true, true, false, false);                 // left + mid arrive
-      C2S_COLUMN(1, false, false, true, false);                // last reader of the left tiles
-      C2S_COLUMN(2, false, false, false, false);
-      C2S_COLUMN(3, true, false, false, false);                // right tiles arrive
-      C2S_COLUMN(4, false, false, true, true);                 // last reader of the right and mid tiles
+      C2S_COLUMN(0, true, true, false, false);                 // left + mid arrive: group by group, as the tiles land
+      C2S_COLUMN2(1, false, true, false);                      // last reader of the left tiles
+      C2S_COLUMN2(2, false, false, false);
+      C2S_COLUMN2(3, true, false, false);                      // right tiles (loaded during the first two classes)
+      C2S_COLUMN2(4, false, true, true);                       // last reader of the right and mid tiles
     }
+#undef C2S_COLUMN2
 #undef C2S_COLUMN
 #undef C2S_REL
 #undef C2S_FILL
