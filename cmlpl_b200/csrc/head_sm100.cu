@@ -291,22 +291,25 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
 // ------------------------------------------------------------------ spectral logits: Wc_spe . relu(Wspe . x + b), hidden never in HBM
 // spectral_logits_kernel fuses the two GEMMs of the spectral branch (models.py:142-143 and the spectral columns of
 // models.py:150): a CTA owns one quarter (256) of the 1024 hidden features and walks pixel tiles of 128.
-//   MMA1 (M=128, N=128, K=B)  hidden half-tile -> TMEM (ring of 3)
-//   epilogue                   bias + ReLU -> fp16 -> shared memory in the UMMA K-major layout (ring of nH half-tiles)
-//   MMA2 (M=128, N=16, K=128)  classifier columns of those hidden features, accumulated over both halves -> TMEM
+//   MMA1 (M=128, N=128, K=B)  hidden half-tile -> TMEM (ring of 3 accumulator slots)
+//   epilogue                   bias + ReLU -> fp16, written back IN PLACE into the slot it came from (tcgen05.st): a thread
+//                              packs the 64 fp32 columns it has read into the first 32 of them, i.e. the half-tile sits in
+//                              columns [0,32) and [64,96) of the slot as a K-major A operand
+//   MMA2 (M=128, N=16, K=128)  classifier columns of those hidden features, A operand FROM TENSOR MEMORY, accumulated over
+//                              both halves -> TMEM; its commit hands the slot back to MMA1
 //   readout                    part[quarter][pixel][16] f32: the head adds the 4 quarter partials (53 MB instead of the
 //                              425 MB hidden tensor written and read back)
+// The hidden features touch neither HBM nor shared memory, whose space goes to the input-tile ring.
 namespace spl {
 constexpr int kEpi = 512, kThreads = kEpi + 96;      // warps 0-15 epilogue, warp 16 loader, warp 17 MMA1 issuer (+ TMEM), warp 18 MMA2 issuer
 constexpr int kLoadWarp = kEpi / 32, kMmaWarp = kLoadWarp + 1, kMma2Warp = kLoadWarp + 2;
-constexpr int HBYTES = 16 * 2048;                    // one hidden half-tile: 16 k-chunks x 128 rows x 16 B
 constexpr int WCBYTES = 32 * 256;                    // classifier columns of this quarter: 32 k-chunks x 16 classes x 16 B
 constexpr int D2COL = 384;                           // TMEM: MMA1 ring at 0/128/256, 4 stages x 2 logits accumulators at 384..511
-enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, H_EMPTY0 = 17, L_FULL0 = 20, L_EMPTY0 = 24, W_FULL = 28 };   // nA <= 4, nH <= 3, 4 logits stages
+enum { A_FULL0 = 0, A_EMPTY0 = 4, D1_FULL0 = 8, D1_EMPTY0 = 11, H_FULL0 = 14, L_FULL0 = 20, L_EMPTY0 = 24, W_FULL = 28 };   // nA <= 4, 4 logits stages
 }  // namespace spl
 
 __global__ void __launch_bounds__(spl::kThreads, 1)
-spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, int nA, int nH,
+spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, int nA,
                        const __half* __restrict__ w1t, const float* __restrict__ bspe,
                        const __half* __restrict__ wc_spe16, float* __restrict__ part) {
   using namespace spl;
@@ -314,8 +317,8 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t wbytes = uint32_t(KC) * 4096, abytes = uint32_t(KC) * 2048;
-  const uint32_t S_W = 0, S_A = wbytes, S_H = S_A + uint32_t(nA) * abytes, S_WC = S_H + uint32_t(nH) * HBYTES,
-                 S_BIAS = S_WC + WCBYTES, S_BAR = S_BIAS + 1024, S_TMEM = S_BAR + 256;
+  const uint32_t S_W = 0, S_A = wbytes, S_WC = S_A + uint32_t(nA) * abytes, S_BIAS = S_WC + WCBYTES, S_BAR = S_BIAS + 1024,
+                 S_TMEM = S_BAR + 256;
   const uint32_t bars = sbase + S_BAR;
   const int ntile = blockIdx.x & 3;
   const int64_t mt0 = blockIdx.x >> 2, mstep = gridDim.x >> 2;
@@ -334,11 +337,10 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     for (uint32_t o = 0; o < wbytes; o += 8192) bulk_g2s(sbase + S_W + o, gw + o, wbytes - o < 8192 ? wbytes - o : 8192, bars + 8 * W_FULL);
     bulk_g2s(sbase + S_WC, reinterpret_cast<const unsigned char*>(wc_spe16) + size_t(ntile) * WCBYTES, WCBYTES, bars + 8 * W_FULL);
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (A_FULL0 + i), 1); mbar_init(bars + 8 * (A_EMPTY0 + i), 1); }
-    // one or two epilogue groups (two as soon as there are >= 2 hidden half-tile slots); a unit's barriers see the
-    // threads of the group that owns it only
-    const int ng = nH >= 2 ? 2 : 1;
-    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), kEpi / ng); }
-    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (H_FULL0 + i), kEpi / ng); mbar_init(bars + 8 * (H_EMPTY0 + i), 1); }
+    // two epilogue groups of eight warps take alternate units; a slot goes MMA1 -> (D1_FULL) -> epilogue group ->
+    // (H_FULL) -> MMA2 -> (D1_EMPTY) -> MMA1
+    for (int i = 0; i < 3; ++i) { mbar_init(bars + 8 * (D1_FULL0 + i), 1); mbar_init(bars + 8 * (D1_EMPTY0 + i), 1); }
+    for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * (H_FULL0 + i), kEpi / 2);
     for (int i = 0; i < 4; ++i) { mbar_init(bars + 8 * (L_FULL0 + i), 1); mbar_init(bars + 8 * (L_EMPTY0 + i), 128); }
     fence_barrier_init();
   }
@@ -365,12 +367,11 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================================================================ MMA issuer
+    // ================================================================ MMA1 issuer
     if (tmem != 0) { printf("spectral_logits: unexpected TMEM base %u\n", tmem); __trap(); }
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
     constexpr uint32_t idesc1 = make_idesc_f16(128, 128);
-    // MMA1 only: gated by the input tile and a drained accumulator slot, never by the epilogue -> MMA2 hand-over, so it
-    // really runs the full ring (3 units) ahead; MMA2 is issued by its own warp below
+    // gated by the input tile and by the slot's previous MMA2; runs up to the full ring (3 units) ahead
     mbar_wait(bars + 8 * W_FULL, 0, 90);                 // weights have landed
     [[maybe_unused]] uint32_t ntr = 0;
     for (uint32_t u = 0; u < U; ++u) {
@@ -395,28 +396,29 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
       if (lane == 0) CMLPL_TR(0, ntr, u * 4 + 3);
     }
   } else if (warp == kMma2Warp) {
-    // ================================================================ MMA2 issuer: classifier columns over the hidden half-tiles
+    // ================================================================ MMA2 issuer: classifier columns over the hidden half-tiles (A from TMEM)
     constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;
     constexpr uint32_t idesc2 = make_idesc_f16(128, 16);
     mbar_wait(bars + 8 * W_FULL, 0, 90);
     [[maybe_unused]] uint32_t ntr = 0;
     for (uint32_t u = 0; u < U; ++u) {
-      const uint32_t ti = u >> 1, hh = u & 1, hs = u % uint32_t(nH), ls = ti & 3;
+      const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, ls = ti & 3;
       if (lane == 0) CMLPL_TR(1, ntr, u * 4);
-      mbar_wait(bars + 8 * (H_FULL0 + hs), (u / uint32_t(nH)) & 1, 94);
+      mbar_wait(bars + 8 * (H_FULL0 + d), (u / 3) & 1, 94);
       if (hh == 0) mbar_wait(bars + 8 * (L_EMPTY0 + ls), ((ti >> 2) & 1) ^ 1, 95);
       tc_fence_after();
       if (lane == 0) CMLPL_TR(1, ntr, u * 4 + 2);
       if (elect_one_sync()) {
-        uint32_t a_lo = ((sbase + S_H + hs * HBYTES) >> 4) | (uint32_t(2048 >> 4) << 16);
         uint32_t b_lo = ((sbase + S_WC + hh * 16 * 256) >> 4) | (uint32_t(256 >> 4) << 16);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          // two independent accumulators (even / odd k-steps); the readout adds them
-          umma_f16(D2COL + ls * 32 + (ks & 1) * 16, kHi | a_lo, kHi | b_lo, idesc2, (hh | (ks >> 1)) ? 1u : 0u);
-          a_lo += 4096 >> 4; b_lo += 512 >> 4;
+          // k-step ks = hidden features 16 ks .. 16 ks + 15 of the half-tile = 8 packed columns; two independent
+          // accumulators (even / odd k-steps), the readout adds them
+          umma_f16_ta(D2COL + ls * 32 + (ks & 1) * 16, d * 128 + (ks >> 2) * 64 + (ks & 3) * 8, kHi | b_lo, idesc2,
+                      (hh | (ks >> 1)) ? 1u : 0u);
+          b_lo += 512 >> 4;
         }
-        umma_commit(bars + 8 * (H_EMPTY0 + hs));
+        umma_commit(bars + 8 * (D1_EMPTY0 + d));
         if (hh == 1) umma_commit(bars + 8 * (L_FULL0 + ls));
       }
       __syncwarp();
@@ -424,12 +426,9 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     }
   } else {
     // ================================================================ epilogue (warps 0-15)
-    // nH >= 2: two groups of eight warps, group 0 takes the first hidden halves (even units), group 1 the second halves;
-    // unit u writes half-tile slot u % nH, so with three slots a group never waits for the MMA2 of its own previous unit.
-    // A thread owns one pixel row x 64 columns.  nH = 1 (wide spectra leave room for one slot): one group of sixteen
-    // warps on every unit, 32 columns per thread -- two groups on ONE slot could run two barrier phases apart.
-    const int G = nH >= 2 ? 2 : 1, grp = G == 2 ? warp >> 3 : 0, q = warp & 3, ch = G == 2 ? (warp >> 2) & 1 : warp >> 2, L = q * 32 + lane;
-    const int cpt = 128 / (4 / G);                                // columns per thread: 64 or 32
+    // two groups of eight warps, group 0 takes the first hidden halves (even units), group 1 the second halves; a thread
+    // owns one pixel row x 64 columns of the slot
+    const int grp = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1, L = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const float* sb = reinterpret_cast<const float*>(smem + S_BIAS);
     auto readout = [&](uint32_t ti) {                  // partial logits of tile ti (four warps: one lane quarter each)
@@ -450,40 +449,38 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
     };
     [[maybe_unused]] uint32_t ntr = 0;
     const bool tracer = (warp & 7) == 0 && lane == 0;
-    for (uint32_t u = uint32_t(grp); u < U; u += uint32_t(G)) {
-      const uint32_t ti = u >> 1, hh = u & 1, d = u % 3, hs = u % uint32_t(nH);
+    for (uint32_t u = uint32_t(grp); u < U; u += 2) {
+      const uint32_t ti = u >> 1, hh = u & 1, d = u % 3;
       if (hh == 1 && ch == 0 && ti > 1) readout(ti - 2);      // deferred by two tiles (4 logits stages): its MMA2 has long completed
       if (tracer) CMLPL_TR(2 + grp, ntr, u * 4);
       mbar_wait(bars + 8 * (D1_FULL0 + d), (u / 3) & 1, 97);
-      if (tracer) CMLPL_TR(2 + grp, ntr, u * 4 + 1);
-      mbar_wait(bars + 8 * (H_EMPTY0 + hs), ((u / uint32_t(nH)) & 1) ^ 1, 98);
       tc_fence_after();
-      if (tracer) CMLPL_TR(2 + grp, ntr, u * 4 + 2);
-      unsigned char* hdst = smem + S_H + hs * HBYTES + (ch * (cpt / 8)) * 2048 + L * 16;
-      const float* bb = sb + hh * 128 + ch * cpt;
-#pragma unroll 1
-      for (int g = 0; g < cpt / 32; ++g) {
+      if (tracer) CMLPL_TR(2 + grp, ntr, u * 4 + 1);
+      const float* bb = sb + hh * 128 + ch * 64;
+      const uint32_t col0 = lane_addr + d * 128 + ch * 64;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
         float v0[16], v1[16];
-        tmem_ld16(lane_addr + d * 128 + ch * cpt + g * 32, v0);
-        tmem_ld16(lane_addr + d * 128 + ch * cpt + g * 32 + 16, v1);
+        tmem_ld16(col0 + g * 32, v0);
+        tmem_ld16(col0 + g * 32 + 16, v1);
         tmem_ld_wait();
-        if (g == cpt / 32 - 1) { tc_fence_before(); mbar_arrive(bars + 8 * (D1_EMPTY0 + d)); }
-        __half2 h[16];
+        uint32_t h[16];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          h[e] = __floats2half2_rn(fmaxf(v0[2 * e] + bb[g * 32 + 2 * e], 0.f), fmaxf(v0[2 * e + 1] + bb[g * 32 + 2 * e + 1], 0.f));
-          h[8 + e] = __floats2half2_rn(fmaxf(v1[2 * e] + bb[g * 32 + 16 + 2 * e], 0.f),
-                                        fmaxf(v1[2 * e + 1] + bb[g * 32 + 16 + 2 * e + 1], 0.f));
+          const __half2 a = __floats2half2_rn(fmaxf(v0[2 * e] + bb[g * 32 + 2 * e], 0.f), fmaxf(v0[2 * e + 1] + bb[g * 32 + 2 * e + 1], 0.f));
+          const __half2 b = __floats2half2_rn(fmaxf(v1[2 * e] + bb[g * 32 + 16 + 2 * e], 0.f),
+                                              fmaxf(v1[2 * e + 1] + bb[g * 32 + 16 + 2 * e + 1], 0.f));
+          h[e] = *reinterpret_cast<const uint32_t*>(&a);
+          h[8 + e] = *reinterpret_cast<const uint32_t*>(&b);
         }
-        const uint4* hv = reinterpret_cast<const uint4*>(h);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(hdst + (g * 4 + k) * 2048) = hv[k];
+        tmem_st16u(col0 + g * 16, h);                    // packed pair c of the chunk -> column c: trails this thread's own reads
       }
-      fence_proxy_async();                             // generic-proxy writes of H -> visible to the tensor core
-      mbar_arrive(bars + 8 * (H_FULL0 + hs));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bars + 8 * (H_FULL0 + d));
       if (tracer) CMLPL_TR(2 + grp, ntr, u * 4 + 3);
     }
-    if ((G == 1 || grp == 1) && ch == 0) {
+    if (grp == 1 && ch == 0) {
       if (my_tiles > 1) readout(uint32_t(my_tiles - 2));
       if (my_tiles > 0) readout(uint32_t(my_tiles - 1));
     }
@@ -550,13 +547,11 @@ using namespace cmlpl;
 
 CMLPL_TRACE_EXPORT(cmlpl_debug_spl_trace)
 
-// shared-memory plan of spectral_logits_kernel for KC input k-chunks: prefers 3 input stages + 2 hidden half-tiles
-static bool spectral_logits_plan(int KC, int* nA, int* nH, size_t* smem) {
-  const int opts[6][2] = {{2, 3}, {3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 1}};   // hidden half-tile slots first, then input tiles in flight
-  for (int i = 0; i < 6; ++i) {
-    const size_t b = size_t(KC) * 4096 + size_t(opts[i][0]) * KC * 2048 + size_t(opts[i][1]) * spl::HBYTES + spl::WCBYTES +
-                     1024 + 256 + 64;
-    if (b <= 232448) { *nA = opts[i][0]; *nH = opts[i][1]; *smem = b; return true; }
+// shared-memory plan of spectral_logits_kernel for KC input k-chunks: as many input tiles in flight as fit (<= 4)
+static bool spectral_logits_plan(int KC, int* nA, size_t* smem) {
+  for (int a = 4; a >= 1; --a) {
+    const size_t b = size_t(KC) * 4096 + size_t(a) * KC * 2048 + spl::WCBYTES + 1024 + 256 + 64;
+    if (b <= 232448) { *nA = a; *smem = b; return true; }
   }
   return false;
 }
@@ -581,15 +576,15 @@ static int spectral_hidden_impl(const void* x, int dtype /* -1 = preprocessed f3
     x16_tile_raw_kernel<float><<<int(g), 256, 0, s>>>(static_cast<const float*>(x), n, num_features, KC, total, mu, inv_sigma, static_cast<__half*>(x16));
   CMLPL_CHECK_LAUNCH("x16_tile");
   if (fused_logits) {
-    int nA = 0, nH = 0; size_t fsmem = 0;
-    CMLPL_CHECK_ARG(spectral_logits_plan(KC, &nA, &nH, &fsmem), "spectral_logits_tc: %d bands do not fit shared memory", num_features);
+    int nA = 0; size_t fsmem = 0;
+    CMLPL_CHECK_ARG(spectral_logits_plan(KC, &nA, &fsmem), "spectral_logits_tc: %d bands do not fit shared memory", num_features);
     CMLPL_CHECK_ARG(num_classes <= 16, "spectral_logits_tc: needs <= 16 classes, got %d", num_classes);
     CMLPL_MAX_DYN_SMEM(spectral_logits_kernel, int(fsmem));
     int fgrid = sm_count() / 4 * 4;
     if (fgrid > mtiles * 4) fgrid = int(mtiles * 4);
     const unsigned char* fpk = static_cast<const unsigned char*>(packed);
     spectral_logits_kernel<<<fgrid, spl::kThreads, fsmem, s>>>(
-        static_cast<const __half*>(x16), mtiles, KC, nA, nH, reinterpret_cast<const __half*>(fpk + L.w1s),
+        static_cast<const __half*>(x16), mtiles, KC, nA, reinterpret_cast<const __half*>(fpk + L.w1s),
         reinterpret_cast<const float*>(fpk + L.bspe),
         reinterpret_cast<const __half*>(fpk + L.wc16 + size_t(L.conv_pos) * 8 * 256), static_cast<float*>(h16));
     CMLPL_CHECK_LAUNCH("spectral_logits");
