@@ -309,10 +309,12 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
     if (lane == 0) {
       tma_prefetch_desc(&tm_f0);
       uint32_t j = 0;
+      [[maybe_unused]] uint32_t ntr = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
         const uint32_t buf = j & 1, ph = (j >> 1) & 1;
         const int tr = t / tiles_c, tc = t - tr * tiles_c;
         mbar_wait(bars + 8 * (A_EMPTY0 + buf), ph ^ 1, 81);
+        CMLPL_TR(4, ntr, j);
         mbar_arrive_expect_tx(bars + 8 * (A_FULL0 + buf), ABYTES);
         tma_load_tile(sbase + S_A + buf * ABYTES, &tm_f0, tc * OW - 1, tr * OH - 1, 0, bars + 8 * (A_FULL0 + buf));
       }
@@ -324,6 +326,7 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
     constexpr uint32_t kI32 = make_idesc_f16(128, 32);
     const uint32_t w_lo = ((sbase + S_W) >> 4) | (uint32_t(kWLbo >> 4) << 16);
     uint32_t j = 0, slot = 0, sph = 0;
+    [[maybe_unused]] uint32_t ntr = 0;
     mbar_wait(bars + 8 * W_FULL, 0, 80);                       // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const uint32_t buf = j & 1, ph = (j >> 1) & 1;
@@ -333,8 +336,10 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
 #pragma unroll 1
       for (int hd = 0; hd < 6; ++hd) {                         // sub-stage = (channel half h, tap row dy)
         const int h = hd / 3, dy = hd - h * 3;
+        if (lane == 0) CMLPL_TR(0, ntr, (j * 6 + hd) * 4);
         mbar_wait(bars + 8 * (S_EMPTY0 + slot), sph ^ 1, 83);
         tc_fence_after();
+        if (lane == 0) CMLPL_TR(0, ntr, (j * 6 + hd) * 4 + 1);
         if (elect_one_sync()) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
@@ -350,6 +355,7 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
           if (hd == 5) umma_commit(bars + 8 * (A_EMPTY0 + buf));
         }
         __syncwarp();
+        if (lane == 0) CMLPL_TR(0, ntr, (j * 6 + hd) * 4 + 2);
         if (++slot == NSUB) { slot = 0; sph ^= 1; }
       }
     }
@@ -359,6 +365,8 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
     const uint32_t lane_addr = uint32_t(ty * 32) << 16;
     const int nb = ty < 3 ? tid + 32 : tid;                   // exchange slot of the position one row below
     uint32_t j = 0, slot = 0, sph = 0, xpar = 0;
+    [[maybe_unused]] uint32_t ntr = 0;
+    const bool tracer = (warp == 0 || warp == 4) && lane == 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const uint32_t buf = j & 1;
       const int tr = t / tiles_c, tc = t - tr * tiles_c;
@@ -370,6 +378,7 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         uint32_t sl[3];
+        if (tracer) CMLPL_TR(1 + chsel, ntr, (j * 4 + h * 2) * 8);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           sl[k] = slot;
@@ -377,6 +386,7 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
           if (++slot == NSUB) { slot = 0; sph ^= 1; }
         }
         tc_fence_after();
+        if (tracer) CMLPL_TR(1 + chsel, ntr, (j * 4 + h * 2) * 8 + 1);
 #pragma unroll 1
         for (int pp = 0; pp < 2; ++pp, xpar ^= 1) {
           const int chunk = h * 4 + pp * 2 + chsel;
@@ -388,6 +398,7 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) tmem_ld8_x2(lane_addr + sl[dy] * SUBCOLS + dx * 32 + col, T[dy][dx]);
           tmem_ld_wait();
+          if (tracer) CMLPL_TR(1 + chsel, ntr, (j * 4 + h * 2 + pp) * 8 + 2);
           if (pp == 1) {
             tc_fence_before();
 #pragma unroll
@@ -430,7 +441,9 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
 #pragma unroll
               for (int q = 0; q < 2; ++q)
                 xb[(((a - 1) * 3 + b) * 2 + q) * kEpi + tid] = make_ulonglong2(G[a][b][2 * q], G[a][b][2 * q + 1]);
+          if (tracer) CMLPL_TR(1 + chsel, ntr, (j * 4 + h * 2 + pp) * 8 + 3);
           named_bar_sync(1, kEpi);
+          if (tracer) CMLPL_TR(1 + chsel, ntr, (j * 4 + h * 2 + pp) * 8 + 4);
           f2 V[3][3][4];                                       // [A][b]
 #pragma unroll
           for (int b = 0; b < 3; ++b)
@@ -462,6 +475,7 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
               *reinterpret_cast<uint4*>(dst + int64_t(64) * psz * 8) = *reinterpret_cast<uint4*>(o2);
             }
           }
+          if (tracer) CMLPL_TR(1 + chsel, ntr, (j * 4 + h * 2 + pp) * 8 + 5);
         }
       }
       mbar_arrive(bars + 8 * (A_EMPTY0 + buf));               // residual reads (and the MMAs, by their commit) done with A
@@ -475,6 +489,8 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
 }  // namespace cmlpl
 
 using namespace cmlpl;
+
+CMLPL_TRACE_EXPORT(cmlpl_debug_c1p_trace)
 
 extern "C" int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_rows, const void* packed,
                                               float* g, cmlpl_stream_t stream) {

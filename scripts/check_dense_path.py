@@ -20,6 +20,7 @@ def rel(a, b):
 
 def run(R, C, B, K, seed, time_it=False):
     w = 20
+    res = {}
     rng = np.random.default_rng(seed)
     cube = torch.from_numpy(rng.standard_normal((R, C, 60)).astype(np.float32)).to(dev)
     spectra = torch.from_numpy(rng.standard_normal((R * C, B)).astype(np.float32)).to(dev)
@@ -48,7 +49,8 @@ def run(R, C, B, K, seed, time_it=False):
         for q in range(2):
             sub = pm4[:, p:PR - 1:2, q:PC - 1:2, :]                    # pooled cells exist for pr < PR-1, pc < PC-1
             pmq_ref[:, p * 2 + q, :, :sub.shape[1], :sub.shape[2], :] = sub.reshape(9, sub.shape[1], sub.shape[2], 8, 8).permute(0, 3, 1, 2, 4)
-    print(f"[{R}x{C}] planes vs pooled maps: equal={torch.equal(pmq, pmq_ref)} nan={int(torch.isnan(pmq.float()).sum())}")
+    res["planes_equal"] = bool(torch.equal(pmq, pmq_ref))
+    print(f"[{R}x{C}] planes vs pooled maps: equal={res['planes_equal']} nan={int(torch.isnan(pmq.float()).sum())}")
     # fused conv1+pool kernel (what scene_infer runs): same planes up to the fp32 summation order of the 2x2 pool
     pmq_f = torch.full((9, 4, 8, PR2, PC2, 8), float("nan"), dtype=torch.float16, device=dev)
     _lib.call("cmlpl_conv1_pool_planes_f16", f0.data_ptr(), C, w, R, packed.data_ptr(), pmq_f.data_ptr(), st)
@@ -99,6 +101,7 @@ def run(R, C, B, K, seed, time_it=False):
             worst = max(worst, e)
             if not e < 5e-3:
                 print("      map Al=%d Be=%d rel %.2e" % (Al, Be, e))
+    res["half_pooled_rel"], res["half_pooled_nan"] = worst, nan_y
     print(f"   half-pooled conv2 maps: worst rel err {worst:.2e} (fp16 output rounding ~5e-4) nan={nan_y}")
     # ---- stage 3: pooled classifier partial maps from the kernel's own yq
     _lib.call("cmlpl_pool2_cls_f16", yq.data_ptr(), C, w, R, B, K, packed.data_ptr(), lmap.data_ptr(), st)
@@ -122,6 +125,7 @@ def run(R, C, B, K, seed, time_it=False):
         # map I is read at y' = r' + 2I >= 2I, x' = c' <= PC2 - 11 only; compare where every input exists
         e = rel(got[:, :, 2 * I:PR2 - 1, :PC2 - 10], ref[:, :, 2 * I:PR2 - 1, :PC2 - 10])
         worst = max(worst, e)
+    res["row_maps_rel"] = worst
     print(f"   class-partial row maps: worst rel err {worst:.2e}")
     # ---- stage 4: whole path vs per-pixel path vs oracle
     labels, logits = ops.scene_infer(cube, spectra, packed, K, w, want_logits=True)
@@ -137,10 +141,12 @@ def run(R, C, B, K, seed, time_it=False):
     _lib.call("cmlpl_spectral_hidden_tc", spectra.data_ptr(), n, B, K, w, packed.data_ptr(), x16.data_ptr(), h16.data_ptr(), st)
     _lib.call("cmlpl_head_tc", p2.data_ptr(), h16.data_ptr(), n, B, K, w, packed.data_ptr(), lab2.data_ptr(), log2.data_ptr(), st)
     torch.cuda.synchronize()
-    print(f"   logits dense vs per-pixel path: rel {rel(logits, log2):.2e}, labels equal {float((labels == lab2).float().mean()):.5f}")
+    res["dense_vs_pixel_rel"], res["labels_equal"] = rel(logits, log2), float((labels == lab2).float().mean())
+    print(f"   logits dense vs per-pixel path: rel {res['dense_vs_pixel_rel']:.2e}, labels equal {res['labels_equal']:.5f}")
     if n <= 4000:
         lab_ref, log_ref = O.test_whole(sd, cube.cpu().numpy(), spectra.cpu().numpy(), w, return_logits=True)
-        print(f"   logits dense vs oracle: rel {rel(logits.cpu(), torch.from_numpy(log_ref)):.2e}; per-pixel vs oracle {rel(log2.cpu(), torch.from_numpy(log_ref)):.2e}")
+        res["dense_vs_oracle_rel"] = rel(logits.cpu(), torch.from_numpy(log_ref))
+        print(f"   logits dense vs oracle: rel {res['dense_vs_oracle_rel']:.2e}; per-pixel vs oracle {rel(log2.cpu(), torch.from_numpy(log_ref)):.2e}")
     if time_it:
         ws = ops.scene_workspace(R, C, B, K, w, dev)
         off = (ctypes.c_size_t * 12)()
@@ -173,9 +179,11 @@ def run(R, C, B, K, seed, time_it=False):
         for _ in range(10): ops.scene_infer(cube, spectra, packed, K, w, workspace=ws, labels=lab2)
         e1.record(); torch.cuda.synchronize()
         print(f"   scene_infer {e0.elapsed_time(e1) / 10:.3f} ms  ({n / (e0.elapsed_time(e1) / 10) / 1e3:.1f} M px/s)")
+    return res
 
 
-run(37, 45, 103, 9, 1)
-run(24, 75, 144, 15, 2)
-if "--big" in sys.argv:
-    run(610, 340, 103, 9, 3, time_it=True)
+if __name__ == "__main__":
+    run(37, 45, 103, 9, 1)
+    run(24, 75, 144, 15, 2)
+    if "--big" in sys.argv:
+        run(610, 340, 103, 9, 3, time_it=True)

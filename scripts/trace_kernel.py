@@ -1,7 +1,7 @@
 """Timeline of one CTA of a scene kernel (clock64 stamps of its issuer / epilogue / loader warps).
 Needs the instrumented library:  make -C cmlpl_b200/csrc trace   (-> scripts/_trace/libcmlpl_trace.so, git-ignored);
 GPU box only, debugging aid -- nothing in the product loads that library.
-usage: trace_kernel.py {conv2|spectral} [first_event] [n_events]"""
+usage: trace_kernel.py {conv2|conv1|spectral} [first_event] [n_events]"""
 import ctypes
 import os
 import sys
@@ -39,6 +39,10 @@ for _ in range(3):
         tl.cmlpl_conv2_scene_f16.argtypes = [P, I, I, I, P, P, P]
         rc = tl.cmlpl_conv2_scene_f16(base + off[4], C, w, R, packed.data_ptr(), base + off[5], st)
         names, export = ["mma", "epi0", "epi1", "load"], "cmlpl_debug_c2s_trace"
+    elif which == "conv1":
+        tl.cmlpl_conv1_pool_planes_f16.argtypes = [P, I, I, I, P, P, P]
+        rc = tl.cmlpl_conv1_pool_planes_f16(base + off[0], C, w, R, packed.data_ptr(), base + off[4], st)
+        names, export = ["mma", "epi0", "epi1", "-", "load"], "cmlpl_debug_c1p_trace"
     else:
         tl.cmlpl_spectral_logits_tc.argtypes = [P, L, I, I, I, P, P, P, P]
         rc = tl.cmlpl_spectral_logits_tc(spectra.data_ptr(), R * C, B, K, w, packed.data_ptr(), base + off[1], base + off[2], st)
@@ -70,6 +74,16 @@ if which == "conv2":
             return f"tma tile {t}"
         r = t >> 2
         return f"item kap{r // 3} it{r % 3} " + ["wait", "ready", "done"][t & 3]
+elif which == "conv1":
+    m = [c for c, n, t in ev if n == "mma" and t % 24 == 0]
+    print("cycles per tile (MMA loop):", [m[i + 1] - m[i] for i in range(5, min(17, len(m) - 1))])
+
+    def desc(n, t):
+        if n == "mma":
+            return f"tile {t // 24} sub-stage {(t // 4) % 6} " + ["loop", "slot free", "issued"][t & 3]
+        if n == "load":
+            return f"tile {t} tma issued"
+        return f"tile {t // 32} pass {(t // 8) % 4} " + ["wait T", "T full", "T in regs", "published", "past barrier", "stored"][t & 7]
 else:
     m1 = [c for c, n, t in ev if n == "mma1" and (t & 3) == 0]
     print("cycles per unit (MMA1 loop):", [m1[i + 1] - m1[i] for i in range(20, 40)])
