@@ -222,3 +222,37 @@ def test_raw_path_mid_size_matches_preprocessed_path(dev, B, K, dtype):
         parts.append(ops.scene_infer_raw(raw_in[s0 * C:s1 * C].contiguous(), folded, packed, K, C, 20, band_row0=a,
                                          band_rows=b - a, scene_rows=R, slab_row0=s0))
     assert torch.equal(torch.cat(parts), lab_b)
+
+
+def test_scene_infer_from_two_streams_interleaved(dev):
+    """cmlpl_scene_infer forks its spectral branch onto a per-device side stream (scene_infer.cu::side_stream).  Two
+    caller streams that issue scenes alternately share that side stream and its two events; every result must still be
+    the one a lone call produces (bit-identical: the kernels are deterministic), and work queued on a caller stream
+    after the call must see the labels."""
+    from cmlpl_b200 import ops
+    K, w = 9, 20
+    scenes = []
+    for i, (R, C, B) in enumerate([(61, 83, 103), (47, 120, 103)]):
+        rng = np.random.default_rng(40 + i)
+        cube = torch.from_numpy(rng.standard_normal((R, C, 60)).astype(np.float32)).to(dev)
+        spectra = torch.from_numpy(rng.standard_normal((R * C, B)).astype(np.float32)).to(dev)
+        torch.manual_seed(40 + i)
+        packed = ops.pack_basenet2({k: v.to(dev) for k, v in O.basenet2_init(B, K).items()}, B, K, w)
+        ref = ops.scene_infer(cube, spectra, packed, K, w).clone()
+        scenes.append(dict(cube=cube, spectra=spectra, packed=packed, ref=ref, R=R, C=C, B=B,
+                           ws=ops.scene_workspace(R, C, B, K, w, dev), labels=torch.empty(R * C, dtype=torch.uint8, device=dev),
+                           copy=torch.empty(R * C, dtype=torch.uint8, device=dev), stream=torch.cuda.Stream(device=dev)))
+    torch.cuda.synchronize()
+    for it in range(25):
+        for s in scenes:
+            with torch.cuda.stream(s["stream"]):
+                s["labels"].fill_(255)
+                ops.scene_infer(s["cube"], s["spectra"], s["packed"], K, w, workspace=s["ws"], labels=s["labels"])
+                s["copy"].copy_(s["labels"])                  # queued behind the call on the caller's stream
+        if it % 8 == 7:
+            torch.cuda.synchronize()
+            for s in scenes:
+                assert torch.equal(s["copy"], s["ref"]), it
+    torch.cuda.synchronize()
+    for s in scenes:
+        assert torch.equal(s["copy"], s["ref"]) and torch.equal(s["labels"], s["ref"])
