@@ -66,6 +66,7 @@ SIGNATURES = {
     "cmlpl_softmax_js_f32": (I, [P, P, L, I, F, P, P, P]),
     "cmlpl_sim_nt_tc_f32": (I, [P, P, I, I, I, P, P]),
     "cmlpl_set_loss_gemm_mode": (I, [I]),
+    "cmlpl_set_scene_path_mode": (I, [I]),
     "cmlpl_bank_smooth_f32": (I, [P, P, P, P, L, I, I, L, F, F, I, F, P, P, P, P, P]),
     "cmlpl_graph_contrast_f32": (I, [P, P, P, P, L, I, I, F, I, F, P, P, P, P]),
     "cmlpl_ntxent_f32": (I, [P, L, I, F, P, P, P, P]),

@@ -526,7 +526,7 @@ extern "C" int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int ban
 extern "C" int cmlpl_conv1_pool_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed,
                                            void* pmq, cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(f0pad && packed && pmq, "conv1_pool_planes: null pointer");
-  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "conv1_pool_planes: bad dims (w must be 20)");
+  CMLPL_CHECK_ARG((w == 20 || w == 11) && cols > 0 && band_rows > 0, "conv1_pool_planes: bad dims (w must be 20 or 11)");
   const int PR = band_rows + w - 1, PC = cols + w - 1, PR2 = (PR + 1) / 2, PC2 = (PC + 1) / 2;
   const PackedLayout L = packed_layout(1, 1, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);

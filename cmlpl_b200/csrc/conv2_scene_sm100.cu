@@ -459,8 +459,8 @@ static_assert(S_T % 128 == 0 && TBYTES % 128 == 0, "pool2_cls: TMA destinations 
 // runs up to 8 tiles ahead of the MMAs; 15 loads per output tile (the three middle columns re-read their map at
 // three origins, from L2).
 __global__ void __launch_bounds__(p2c::kThreads, 1)
-pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int nq, const unsigned char* __restrict__ wcq,
-                 float* __restrict__ lmap) {
+pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int nq, int ncell /* pooled cells per side: 5 (w = 20) or 2 (w = 11) */,
+                 const unsigned char* __restrict__ wcq, float* __restrict__ lmap) {
   using namespace p2c;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -469,6 +469,9 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
   const int tiles_c = (PC2 + TW - 1) / TW, tiles_r = (PR2 + TH - 1) / TH;
   const int tiles_p = tiles_r * tiles_c, ntiles = 4 * tiles_p;
   const int64_t psz = int64_t(PR2) * PC2;
+  // w = 11: pooled cells I, J in {0, 1} only -> row classes Al = 0, 1 and pooled columns J = 0, 1 (the weights of every
+  // other cell are zero in wcq, their maps are neither loaded nor multiplied)
+  const int nAl = ncell >= 5 ? 3 : 2, nJ = ncell >= 5 ? 5 : 2;
 
   {
     uint4* z = reinterpret_cast<uint4*>(smem + S_T);
@@ -500,6 +503,7 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
 #pragma unroll 1
         for (int q = 0; q < 15; ++q) {
           const int Al = q / 5, J = q - Al * 5, Be = J == 0 ? 0 : (J == 4 ? 2 : 1);
+          if (Al >= nAl || J >= nJ) continue;
           mbar_wait(bars + 8 * (E0 + slot), ph ^ 1, 71);
           mbar_arrive_expect_tx(bars + 8 * (F0 + slot), TBYTES);
           tma_load_tile(sbase + S_T + slot * TBYTES, &tm_y, tc * TW + 2 * J, tr * TH, (Al * 3 + Be) * 4 + pl, bars + 8 * (F0 + slot));
@@ -522,8 +526,10 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
         const int nI = blk_n(Al), N = nI * 16, nu = Al == 1 ? 2 : 1;
         const uint32_t idesc = make_idesc_f16(128, N);
         const uint32_t dcol = tmem + st * 128 + uint32_t(blk_first(Al) * 16);
+        if (Al >= nAl) continue;
 #pragma unroll
         for (int J = 0; J < 5; ++J) {
+          if (J >= nJ) continue;
           const int Be = J == 0 ? 0 : (J == 4 ? 2 : 1), nv = Be == 1 ? 2 : 1;
           const int Nb = nI * blk_n(Be) * 16;                  // rows of the block (Al, Be): its k-chunk stride
           const uint32_t w_lo = ((sbase + S_W + blk_start(Al * 3 + Be) * 16 * 128 + (J - blk_first(Be)) * N * 16) >> 4) |
@@ -545,7 +551,7 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
               }
             }
             umma_commit(bars + 8 * (E0 + slot));
-            if (Al == 2 && J == 4) umma_commit(bars + 8 * (DFULL0 + st));
+            if (Al == nAl - 1 && J == nJ - 1) umma_commit(bars + 8 * (DFULL0 + st));
           }
           __syncwarp();
           if (++slot == NSLOT) { slot = 0; ph ^= 1; }
@@ -579,7 +585,7 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
       if (valid) {
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
-          if (m0 + m < m1) {
+          if (m0 + m < m1 && m0 + m < ncell) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)                         // class quads beyond the real classes are never read (head_sum_kernel)
               if (q < nq) dst[int64_t((m0 + m) * 4 + q) * psz] = make_float4(v[m][4 * q], v[m][4 * q + 1], v[m][4 * q + 2], v[m][4 * q + 3]);
@@ -616,7 +622,7 @@ CMLPL_TRACE_EXPORT(cmlpl_debug_c2s_trace)
 extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_rows, const void* packed, void* yq,
                                      cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(pmq && packed && yq, "conv2_scene: null pointer");
-  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "conv2_scene: bad dims (w must be 20)");
+  CMLPL_CHECK_ARG((w == 20 || w == 11) && cols > 0 && band_rows > 0, "conv2_scene: bad dims (w must be 20 or 11)");
   const int PR2 = (band_rows + w) / 2, PC2 = (cols + w) / 2;
   const PackedLayout L = packed_layout(1, 1, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
@@ -636,8 +642,8 @@ extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_
 extern "C" int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_rows, int num_features, int num_classes,
                                    const void* packed, float* lmap, cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(yq && packed && lmap, "pool2_cls: null pointer");
-  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0 && num_classes > 0 && num_classes <= 16,
-                  "pool2_cls: bad dims (w must be 20, <= 16 classes)");
+  CMLPL_CHECK_ARG((w == 20 || w == 11) && cols > 0 && band_rows > 0 && num_classes > 0 && num_classes <= 16,
+                  "pool2_cls: bad dims (w must be 20 or 11, <= 16 classes)");
   const int PR2 = (band_rows + w) / 2, PC2 = (cols + w) / 2;
   const PackedLayout L = packed_layout(num_features, num_classes, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
@@ -648,7 +654,7 @@ extern "C" int cmlpl_pool2_cls_f16(const void* yq, int cols, int w, int band_row
   const int trc = make_scene_tmap(&tm_y, yq, 36, PR2, PC2, p2c::TH + 1, p2c::TP);
   if (trc != CMLPL_OK) return trc;
   pool2_cls_kernel<<<grid, p2c::kThreads, p2c::SMEM, static_cast<cudaStream_t>(stream)>>>(tm_y, PR2, PC2, (num_classes + 3) / 4,
-                                                                                          pk + L.wcq, lmap);
+                                                                                          w == 20 ? 5 : 2, pk + L.wcq, lmap);
   CMLPL_CHECK_LAUNCH("pool2_cls");
   return CMLPL_OK;
 }

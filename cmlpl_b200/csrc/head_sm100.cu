@@ -496,7 +496,8 @@ spectral_logits_kernel(const __half* __restrict__ x16, int64_t mtiles, int KC, i
 // adjacent lanes read adjacent 16-byte quads of the two parity planes of a row.
 __global__ void __launch_bounds__(256)
 head_sum_kernel(const float* __restrict__ part, int64_t mtiles, const float* __restrict__ lmap, int cols, int PR2, int PC2,
-                int64_t n, int C, const float* __restrict__ bc, uint8_t* __restrict__ labels, float* __restrict__ logits) {
+                int64_t n, int C, int ncell /* pooled rows: 5 (w = 20) or 2 (w = 11) */, const float* __restrict__ bc,
+                uint8_t* __restrict__ labels, float* __restrict__ logits) {
   const int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (p >= n) return;
   const int nq = (C + 3) >> 2;                         // class quads that hold real classes
@@ -509,6 +510,7 @@ head_sum_kernel(const float* __restrict__ part, int64_t mtiles, const float* __r
                        int64_t(r >> 1) * PC2 + (c0 >> 1);
 #pragma unroll
   for (int I = 0; I < 5; ++I) {
+    if (I >= ncell) break;
     const float4* q = base + int64_t(I * 4) * psz + (2 * I) * PC2;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -683,13 +685,13 @@ extern "C" int cmlpl_head_sum_lmap(const float* part, const float* lmap, int col
                                    int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
                                    cmlpl_stream_t stream) {
   CMLPL_CHECK_ARG(part && lmap && packed && labels, "head_sum_lmap: null pointer");
-  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "head_sum_lmap: bad dims (w must be 20)");
+  CMLPL_CHECK_ARG((w == 20 || w == 11) && cols > 0 && band_rows > 0, "head_sum_lmap: bad dims (w must be 20 or 11)");
   CMLPL_CHECK_ARG(num_classes > 0 && num_classes <= 16, "head_sum_lmap: needs 1..16 classes, got %d", num_classes);
   const PackedLayout L = packed_layout(num_features, num_classes, w);
   const int64_t n = int64_t(band_rows) * cols, mtiles = (n + 127) / 128;
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
   head_sum_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      part, mtiles, lmap, cols, (band_rows + w) / 2, (cols + w) / 2, n, num_classes,
+      part, mtiles, lmap, cols, (band_rows + w) / 2, (cols + w) / 2, n, num_classes, w == 20 ? 5 : 2,
       reinterpret_cast<const float*>(pk + L.bc), labels, logits);
   CMLPL_CHECK_LAUNCH("head_sum");
   return CMLPL_OK;

@@ -88,9 +88,11 @@ __global__ void pack_kernel(PackArgs a) {
     case 8: {  // dense-path classifier: per block [8 kc][N][8], row = ((J-J0)*nI + (I-I0))*16 + cls, value = Wc[cls][ch,I,J] / 4 for the
                // middle classes; a border class arrives averaged over its two variants (conv2_scene_kernel), so its factor
                // doubles per border direction
-      if (a.P != 25) break;
+      // w = 20: 5x5 pooled cells.  w = 11: 2x2 cells (I, J in {0, 1}) at the same border classes, every other map zero
+      if (a.P != 25 && a.P != 4) break;
       __half* d = reinterpret_cast<__half*>(o + a.L.wcq);
-      const int in_f = 64 * 25 + 1024;
+      const int pw = a.P == 25 ? 5 : 2;                         // pooled cells per side
+      const int in_f = 64 * a.P + 1024;
       for (int64_t i = t0; i < 400 * 64; i += step) {
         int b = 0;
         while (b < 8 && i >= int64_t(blk_start(b + 1)) * 16 * 64) ++b;
@@ -101,7 +103,7 @@ __global__ void pack_kernel(PackArgs a) {
         const int nI = blk_n(Al), cls = row & 15, ch = kc * 8 + e;
         const int I = blk_first(Al) + (row >> 4) % nI, J = blk_first(Be) + (row >> 4) / nI;
         const float sc = 0.25f * (Al != 1 ? 2.f : 1.f) * (Be != 1 ? 2.f : 1.f);
-        d[i] = __float2half_rn(cls < a.C ? sc * a.cw[int64_t(cls) * in_f + ch * 25 + I * 5 + J] : 0.f);
+        d[i] = __float2half_rn(cls < a.C && I < pw && J < pw ? sc * a.cw[int64_t(cls) * in_f + ch * a.P + I * pw + J] : 0.f);
       }
     } break;
   }

@@ -202,6 +202,10 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int64_t n, int C
 // CUDA-core spectral_head + classify kernels above run (same C ABI, same results contract).
 static bool use_tc_head(int B, int C) { return C <= 16 && ((B + 15) / 16) * 2 <= 28; }   // <= 224 bands (spectral_logits_kernel)
 
+// 1 (default): the exact-compute-sharing kernels where they apply; 0: the per-pixel tensor-core kernels everywhere (the
+// independent implementation the tests compare against).  Per host thread; the workspace layout follows the mode.
+static thread_local int g_scene_path_mode = 1;
+
 struct SceneWs {
   size_t f0pad, p2, spe, hidden, x16, h16, g, pm, yq, lmap, total;
   int64_t chunk;
@@ -216,7 +220,9 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
   const int64_t mtiles = (n + 127) / 128;
   const int P = ((w / 2) / 2) * ((w / 2) / 2);
   s.tc = use_tc_head(B, C);
-  s.dense = s.tc && w == 20;                               // the exact-compute-sharing kernels are specialised to w = 20
+  // the exact-compute-sharing kernels: w = 20 (9 / 25 border classes) and w = 11, whose 4 / 9 classes and 2x2 pooled cells
+  // are a subset of them (conv1 rows 0..9 and conv2 rows 0..3 of an 11-window are top / mid class only)
+  s.dense = s.tc && (w == 20 || w == 11) && g_scene_path_mode == 1;
   size_t o = 0;
   s.f0pad = o; o = align256(o + size_t(band_rows + w - 1) * (cols + w - 1) * 64 * 2);
   s.p2 = s.spe = s.hidden = s.x16 = s.h16 = s.g = s.pm = s.yq = s.lmap = 0;
@@ -245,6 +251,12 @@ static SceneWs scene_ws(int band_rows, int cols, int B, int C, int w) {
 }  // namespace cmlpl
 
 using namespace cmlpl;
+
+extern "C" int cmlpl_set_scene_path_mode(int mode) {
+  CMLPL_CHECK_ARG(mode == 0 || mode == 1, "set_scene_path_mode: 0 (per-pixel kernels) or 1 (exact compute sharing, default)");
+  g_scene_path_mode = mode;
+  return CMLPL_OK;
+}
 
 extern "C" size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w) {
   if (band_rows <= 0 || cols <= 0 || num_classes <= 0 || num_features <= 0 || w < 4) return 0;

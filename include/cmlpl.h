@@ -119,6 +119,12 @@ int cmlpl_pack_basenet2(const float* conv0_w, const float* conv0_b,
                         int num_features, int num_classes, int w,
                         void* packed, cmlpl_stream_t stream);
 
+/* Which kernels cmlpl_scene_infer / cmlpl_scene_infer_raw run on the tensor-core path (<= 16 classes, <= 224 bands), per
+ * calling host thread: 1 (default) = the scene-level kernels with exact compute sharing (w = 20 and w = 11), 0 = the
+ * per-pixel kernels (patch_cnn_kernel<w> per pixel; the independent implementation the tests compare the default against,
+ * models.py:133-150 per patch).  The workspace size and layout follow the mode: set it before sizing the workspace. */
+int cmlpl_set_scene_path_mode(int mode);
+
 /* Workspace needed to infer `band_rows` rows of a scene with `cols` columns. */
 size_t cmlpl_scene_workspace_bytes(int band_rows, int cols, int num_features, int num_classes, int w);
 

@@ -68,3 +68,34 @@ def test_batch_forward_backward_w11(dev):
     assert rel(lo.detach().cpu(), lo_r.detach()) < 1e-5
     for k in O.LIVE_KEYS:
         assert rel(dict(net.named_parameters())[k].grad.cpu(), sd[k].grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("w,shape,B,K", [(11, (29, 37), 224, 16), (11, (18, 52), 103, 9), (20, (33, 41), 144, 15)])
+def test_compute_sharing_path_matches_per_pixel_path(dev, w, shape, B, K):
+    """cmlpl_scene_infer's default kernels (conv1 / conv2 evaluated once per scene position in border classes, pooled
+    cells as class-partial maps) against the per-pixel kernels (cmlpl_set_scene_path_mode(0): patch_cnn_kernel<w> on every
+    pixel's own window) on the same conv0 map -- two independent evaluations of tools/models.py:133-150.  For w = 11 the
+    shared kernels run with the 2x2 pooled cells of the 1280-input classifier.  Logits within 5e-4 * max, labels equal
+    wherever the per-pixel logits are not tied to within that."""
+    from cmlpl_b200 import _lib, ops
+    from cmlpl_b200.tools.models import BaseNet2
+    R, C = shape
+    rng = np.random.default_rng(w + B)
+    cube = torch.from_numpy(rng.standard_normal((R, C, 60)).astype(np.float32)).to(dev)
+    spectra = torch.from_numpy(rng.standard_normal((R * C, B)).astype(np.float32)).to(dev)
+    torch.manual_seed(w + B)
+    net = BaseNet2(B, 0, K, w=w).to(dev).eval()
+    packed = net.packed_weights(w)
+    lab_d, log_d = ops.scene_infer(cube, spectra, packed, K, w, want_logits=True)
+    _lib.call("cmlpl_set_scene_path_mode", 0)
+    try:
+        lab_p, log_p = ops.scene_infer(cube, spectra, packed, K, w, want_logits=True)
+    finally:
+        _lib.call("cmlpl_set_scene_path_mode", 1)
+    log_d, log_p = log_d.cpu().numpy(), log_p.cpu().numpy()
+    assert rel(log_d, log_p) < 5e-4
+    tol = 1e-3 * np.abs(log_p).max()
+    top2 = np.sort(log_p, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > tol
+    assert np.array_equal(lab_d.cpu().numpy()[clear], lab_p.cpu().numpy()[clear])
+    assert clear.mean() > 0.9
