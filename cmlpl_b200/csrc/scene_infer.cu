@@ -410,7 +410,8 @@ extern "C" int cmlpl_scene_infer(const float* cube, int scene_rows, int cols, in
   CMLPL_CHECK_ARG(cube && spectra && packed && workspace && labels, "scene_infer: null pointer");
   // w = 20: the reference's BaseNet2 (classifier hard-wired to 2624 inputs, tools/models.py:127).  w = 11: the odd-window
   // variant BASELINE configs[4] names (ExtractPatches_for_base windows, hyper_tools.py:300-317; pooled 5 -> 2, classifier
-  // over 64*2*2 + 1024 = 1280 inputs) -- a documented extension, evaluated per pixel by patch_cnn_kernel<11>.
+  // over 64*2*2 + 1024 = 1280 inputs) -- a documented extension; its border classes and pooled cells are a subset of the
+  // w = 20 ones, so the same scene-level kernels run; patch_cnn_kernel<11> per pixel behind path mode 0.
   CMLPL_CHECK_ARG(w == 20 || w == 11, "scene_infer: w=%d unsupported (20, or 11 for the odd-window variant)", w);
   CMLPL_CHECK_ARG(band_rows > 0 && cols > 0 && num_classes > 0 && num_classes <= 32, "scene_infer: bad dims");
   const SceneWs ws = scene_ws(band_rows, cols, num_features, num_classes, w);
