@@ -271,7 +271,7 @@ static_assert(S_A % 128 == 0 && ABYTES % 128 == 0, "conv1_pool: TMA destinations
 
 // f0: f16 chunk-planar [8][PR][PC][8];  pmq f16 [9 = A*3+B][4 planes][8 chunks][PR2][PC2][8]
 __global__ void __launch_bounds__(c1p::kThreads, 1)
-conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int PR2, int PC2,
+conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int PR2, int PC2, int ncls /* pooled classes per direction stored: 3, or 2 (top, mid) for 11x11 windows */,
                   const unsigned char* __restrict__ w1p, const float* __restrict__ b1g, __half* __restrict__ pmq) {
   using namespace c1p;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -468,11 +468,11 @@ conv1_pool_kernel(const __grid_constant__ CUtensorMap tm_f0, int PR, int PC, int
               f2_unpack(f2_mul(f2_add(V[A][1][e], n1), sc), lo, hi); o1[e] = __floats2half2_rn(lo, hi);
               f2_unpack(f2_mul(f2_add(V[A][1][e], n2), sc), lo, hi); o2[e] = __floats2half2_rn(lo, hi);
             }
-            if (inplane) {
+            if (inplane && A < ncls) {
               __half* dst = pmq + (int64_t(A * 3) * 32 * psz + opos + int64_t(chunk) * psz) * 8;
               *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(o0);
               *reinterpret_cast<uint4*>(dst + int64_t(32) * psz * 8) = *reinterpret_cast<uint4*>(o1);
-              *reinterpret_cast<uint4*>(dst + int64_t(64) * psz * 8) = *reinterpret_cast<uint4*>(o2);
+              if (ncls > 2) *reinterpret_cast<uint4*>(dst + int64_t(64) * psz * 8) = *reinterpret_cast<uint4*>(o2);
             }
           }
           if (tracer) CMLPL_TR(1 + chsel, ntr, (j * 4 + h * 2 + pp) * 8 + 5);
@@ -537,7 +537,7 @@ extern "C" int cmlpl_conv1_pool_planes_f16(const void* f0pad, int cols, int w, i
   const int trc = make_scene_tmap(&tm_f0, f0pad, 1, PR, PC, c1p::TH + 2, c1p::TP);
   if (trc != CMLPL_OK) return trc;
   conv1_pool_kernel<<<grid, c1p::kThreads, c1p::SMEM, static_cast<cudaStream_t>(stream)>>>(
-      tm_f0, PR, PC, PR2, PC2, pk + L.w1, reinterpret_cast<const float*>(pk + L.b1), static_cast<__half*>(pmq));
+      tm_f0, PR, PC, PR2, PC2, w == 11 ? 2 : 3, pk + L.w1, reinterpret_cast<const float*>(pk + L.b1), static_cast<__half*>(pmq));
   CMLPL_CHECK_LAUNCH("conv1_pool");
   return CMLPL_OK;
 }

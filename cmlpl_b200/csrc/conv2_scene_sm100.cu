@@ -131,13 +131,14 @@ __host__ __device__ constexpr int tile_r0(int a) { return a == 0 ? 1 : (a == 1 ?
 
 // group G (0 = PA, 1..3 = T1..T3, 4 = PB) of column class KAP: every dx tap x 4 k-steps.  t_lo = low descriptor word of
 // tile 0 minus 16 B (MMA row m of tap dx reads entry m + dx - 1), w_lo = weight block of dx = 0.  All offsets immediate.
-template <int KAP, int G>
+// W11 (11x11 windows): only the row classes rho = 0, 1, 2 exist, so T2 feeds [rho1|rho2] (N=128), T3 [rho2] (N=64), no PB.
+template <int KAP, int G, bool W11 = false>
 __device__ __forceinline__ void issue_group(uint32_t t_lo, uint32_t w_lo) {
   constexpr uint64_t kHi = (uint64_t(128 >> 4) | (uint64_t(1) << 14)) << 32;   // SBO = 128 B, version 1
   constexpr int a = G == 0 ? 0 : (G == 4 ? 2 : 1);
   constexpr int o = G == 0 ? 1 : (G == 4 ? 5 : G + 1);
   constexpr int d = G == 0 ? 0 : (G == 4 ? 192 : (G - 1) * 64);
-  constexpr int N = (G == 0 || G == 4) ? 128 : 192;
+  constexpr int N = W11 ? (G == 1 ? 192 : (G == 3 ? 64 : 128)) : ((G == 0 || G == 4) ? 128 : 192);
   constexpr int brow = G == 0 ? 64 : 0;
   constexpr int dx_first = rep_of(KAP) == 0 ? 1 : 0;
   constexpr int xs = KAP == 0 ? -1 : (KAP == 4 ? 1 : 0);          // frame shift of the border column classes (entries)
@@ -151,7 +152,7 @@ __device__ __forceinline__ void issue_group(uint32_t t_lo, uint32_t w_lo) {
       const uint32_t aa = t_lo + uint32_t((tile * TBYTES + ((o - tile_r0(a)) * TP + dx + xs) * 16 + ks * 2 * CH) / 16);
       const uint32_t bb = w_lo + uint32_t((dx * kWDx + ks * 2 * kWLbo) / 16) + uint32_t(brow);
       const bool first = dx == dx_first && ks == 0;
-      if (first && G >= 1 && G <= 3) {
+      if (first && G >= 1 && G <= (W11 ? 1 : 3)) {
         // the group's third accumulator starts here (overwrite); the other two already hold earlier groups
         umma_f16(uint32_t(d), kHi | uint64_t(aa), kHi | uint64_t(bb), make_idesc_f16(128, 128), 1u);
         umma_f16(uint32_t(d + 128), kHi | uint64_t(aa), kHi | uint64_t(bb + 128), make_idesc_f16(128, 64), 0u);
@@ -164,6 +165,9 @@ __device__ __forceinline__ void issue_group(uint32_t t_lo, uint32_t w_lo) {
 }  // namespace c2s
 
 // pmq f16 [9][4][8][PR2][PC2][8];  yq f16 [9 = Al*3+Be half-pooled maps][4][8][PR2][PC2][8]
+// W11: the instantiation for 11x11 windows -- column / row classes 0, 1, 2 only (64 of the 169 tap products), top and
+// mid-row tiles of the left and mid column classes only (4 of the 9 class tiles), maps Al, Be in {0, 1} written.
+template <bool W11>
 __global__ void __launch_bounds__(c2s::kThreads, 1)
 conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __restrict__ pmq, int PR2, int PC2,
                    const unsigned char* __restrict__ w2p, const float* __restrict__ b2g, __half* __restrict__ yq) {
@@ -214,7 +218,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
         const int y0 = tr * TH - 1, x0 = tc * TW - 1;          // borders zero-filled; tile of row class a starts at row y0 + tile_r0(a)
         // left and mid tiles interleaved in the order the MMA groups need them (top, mid, bottom), then the right tiles
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
+        for (int i = 0; i < (W11 ? 4 : 9); ++i) {
           const int a = i < 6 ? i >> 1 : i - 6;
           const int slab = i < 6 ? (i & 1) : 0, bcls = i < 6 ? (i & 1) : 2;
           const uint32_t k = slab ? fm[a] : fx[a];
@@ -294,14 +298,42 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
       if (lane == 0) CMLPL_TR(0, ntr, KAP * 16 + 9);                                 \
       ++kc;                                                                          \
     } while (0)
+    // 11x11 windows: three column classes, groups PA, T1, T2 (two accumulators), T3 (one); top and mid-row tiles only
+#define C2S_GROUP11(KAP, G, ...)                                                     \
+    do {                                                                             \
+      tc_fence_after();                                                              \
+      if (elect_one_sync()) { issue_group<KAP, G, true>(t_lo, w_lo); __VA_ARGS__; }  \
+      __syncwarp();                                                                  \
+    } while (0)
+#define C2S_COLUMN11(KAP, WX, WM, RX, RM)                                            \
+    do {                                                                             \
+      const uint32_t ep = (kc & 1) ^ 1;                                              \
+      C2S_FILL(0, WX, WM);                                                           \
+      mbar_wait(bars + 8 * (DE0 + 0), ep, 63); mbar_wait(bars + 8 * (DE0 + 1), ep, 63);                       \
+      C2S_GROUP11(KAP, 0, C2S_REL(0, RX, RM));                                       \
+      C2S_FILL(1, WX, WM);                                                           \
+      mbar_wait(bars + 8 * (DE0 + 2), ep, 63);                                       \
+      C2S_GROUP11(KAP, 1, (umma_commit(bars + 8 * (DF0 + 0)), (void)0));             \
+      C2S_GROUP11(KAP, 2, (umma_commit(bars + 8 * (DF0 + 1)), (void)0));             \
+      C2S_GROUP11(KAP, 3, (umma_commit(bars + 8 * (DF0 + 2)), C2S_REL(1, RX, RM)));  \
+      ++kc;                                                                          \
+    } while (0)
     mbar_wait(bars + 8 * c2s::W_FULL, 0, 60);                  // weights have landed
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      C2S_COLUMN(0, true, true, false, false);                 // left + mid arrive: group by group, as the tiles land
-      C2S_COLUMN2(1, false, true, false);                      // last reader of the left tiles
-      C2S_COLUMN2(2, false, false, false);
-      C2S_COLUMN2(3, true, false, false);                      // right tiles (loaded during the first two classes)
-      C2S_COLUMN2(4, false, true, true);                       // last reader of the right and mid tiles
+      if constexpr (W11) {
+        C2S_COLUMN11(0, true, true, false, false);             // left + mid arrive
+        C2S_COLUMN11(1, false, false, true, false);            // last reader of the left tiles
+        C2S_COLUMN11(2, false, false, false, true);            // last reader of the mid tiles
+      } else {
+        C2S_COLUMN(0, true, true, false, false);               // left + mid arrive: group by group, as the tiles land
+        C2S_COLUMN2(1, false, true, false);                    // last reader of the left tiles
+        C2S_COLUMN2(2, false, false, false);
+        C2S_COLUMN2(3, true, false, false);                    // right tiles (loaded during the first two classes)
+        C2S_COLUMN2(4, false, true, true);                     // last reader of the right and mid tiles
+      }
     }
+#undef C2S_COLUMN11
+#undef C2S_GROUP11
 #undef C2S_COLUMN2
 #undef C2S_COLUMN
 #undef C2S_REL
@@ -326,7 +358,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
       const __half* pm_t = pmq + (int64_t(pl) * 8 + hf * 4) * cstep;
       __half* yq_t = yq + (int64_t(pl) * 8 + hf * 4) * cstep;
 #pragma unroll 1
-      for (int kap = 0; kap < 5; ++kap, ++kc) {
+      for (int kap = 0; kap < (W11 ? 3 : 5); ++kap, ++kc) {
         const int xs = kap == 0 ? -1 : (kap == 4 ? 1 : 0);     // frame shift of this column class (entries)
         const int bcl = kap == 0 ? 0 : (kap == 4 ? 2 : 1);     // PM column class of the centre tap
         const int Be = kap <= 1 ? 0 : (kap == 2 ? 1 : 2);
@@ -335,7 +367,7 @@ conv2_scene_kernel(const __grid_constant__ CUtensorMap tm_pm, const __half* __re
         const int xo = xb + xs, x = xb - (kap == 1 ? 1 : 0);
         const bool xok = xo >= 0 && xo < PC2, xval = tx >= 1 && tx <= TW && x >= 0 && x < PC2;
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {
+        for (int it = 0; it < (W11 ? 2 : 3); ++it) {
           constexpr int kRho0[3] = {0, 2, 3};
           const int rho0 = kRho0[it], nrho = it == 1 ? 1 : 2;
           // residual of row class rho = centre cell PM[A(rho)][B(kap)] at the variant's own position.  It is read from
@@ -626,15 +658,22 @@ extern "C" int cmlpl_conv2_scene_f16(const void* pmq, int cols, int w, int band_
   const int PR2 = (band_rows + w) / 2, PC2 = (cols + w) / 2;
   const PackedLayout L = packed_layout(1, 1, w);
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  CMLPL_MAX_DYN_SMEM(conv2_scene_kernel, c2s::SMEM);
   const int ntiles = 4 * ((PR2 + c2s::TH - 1) / c2s::TH) * ((PC2 + c2s::TW - 1) / c2s::TW);
   int grid = sm_count(); if (grid > ntiles) grid = ntiles;
   CUtensorMap tm_pm;
   const int trc = make_scene_tmap(&tm_pm, pmq, 36, PR2, PC2, c2s::TH + 2, c2s::TP);
   if (trc != CMLPL_OK) return trc;
-  conv2_scene_kernel<<<grid, c2s::kThreads, c2s::SMEM, static_cast<cudaStream_t>(stream)>>>(
-      tm_pm, static_cast<const __half*>(pmq), PR2, PC2, pk + L.w2, reinterpret_cast<const float*>(pk + L.b2),
-      static_cast<__half*>(yq));
+  if (w == 11) {
+    CMLPL_MAX_DYN_SMEM(conv2_scene_kernel<true>, c2s::SMEM);
+    conv2_scene_kernel<true><<<grid, c2s::kThreads, c2s::SMEM, static_cast<cudaStream_t>(stream)>>>(
+        tm_pm, static_cast<const __half*>(pmq), PR2, PC2, pk + L.w2, reinterpret_cast<const float*>(pk + L.b2),
+        static_cast<__half*>(yq));
+  } else {
+    CMLPL_MAX_DYN_SMEM(conv2_scene_kernel<false>, c2s::SMEM);
+    conv2_scene_kernel<false><<<grid, c2s::kThreads, c2s::SMEM, static_cast<cudaStream_t>(stream)>>>(
+        tm_pm, static_cast<const __half*>(pmq), PR2, PC2, pk + L.w2, reinterpret_cast<const float*>(pk + L.b2),
+        static_cast<__half*>(yq));
+  }
   CMLPL_CHECK_LAUNCH("conv2_scene");
   return CMLPL_OK;
 }

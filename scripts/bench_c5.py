@@ -163,7 +163,7 @@ def main(args, cfg):
     px = R * C
     nsub = SUB * C
     qpos = 4 * ((SUB + W) // 2) * ((C + W) // 2)
-    executed = qpos * 169 * 2 * 64 * 64
+    executed = qpos * 64 * 2 * 64 * 64               # the w = 11 instantiation: 8 x 8 = 64 tap products per plane position
     achieved = executed / (cnn_ms / 1e3) / 1e12
     line = {
         "metric": "pixels/sec full-scene inference", "value": px / (ms_dev / 1e3), "unit": "pixels/s", "n_gpus": world,
@@ -176,17 +176,16 @@ def main(args, cfg):
                          "stream, preprocessing folded into conv0 / the spectral fp16 conversion; the label map stays on "
                          "the device"},
         "gpu_launches": (7 * len(subs) + (1 if world > 1 else 0)) * args.steps,
-        "roofline": {"kernel": "conv2_scene_kernel on one sub-band (tcgen05 conv2 once per scene position in 25 border classes; "
-                               "an 11x11 window uses 9 of them, i.e. 64 of the 169 tap products)",
+        "roofline": {"kernel": "conv2_scene_kernel<W11> on one sub-band (tcgen05 conv2 once per scene position in the 9 border "
+                               "classes of an 11x11 window: 64 tap products of 64x64 MACs per plane position)",
                      "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tf_burst"], "frac_burst": achieved / peaks["tf_burst"],
                      "frac_sustained": achieved / peaks["tf_sustained"], "traffic": None,
-                     "executed_flop_per_launch": executed, "useful_flop_per_launch": qpos * 64 * 2 * 64 * 64,
+                     "executed_flop_per_launch": executed,
                      "algorithmic_flop_per_launch": nsub * fl["conv2"], "kernel_ms": cnn_ms,
-                     "note": "`achieved` counts the FLOPs the kernel executes; the w = 11 classes are a subset of the w = 20 "
-                             "ones, so 105 of the 169 tap products per position are not needed by any pixel (a trimmed "
-                             "instantiation is future work); algorithmic = SURVEY 8d per-patch arithmetic for w = 11 (conv2 on "
-                             "5x5 positions per pixel)",
+                     "note": "`achieved` counts the FLOPs the kernel executes (the shortened T groups run N=128 / N=64 MMAs at "
+                             "the cost of N=128, so the array is less full than at w = 20); algorithmic = SURVEY 8d per-patch "
+                             "arithmetic for w = 11 (conv2 on 5x5 positions per pixel)",
                      "whole_step_algorithmic_tflops": (r1 - r0) * C * fl["all"] / (ms_dev / 1e3) / 1e12},
         "sub_band_rows": SUB,
     }
