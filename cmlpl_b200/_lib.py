@@ -48,7 +48,6 @@ SIGNATURES = {
     "cmlpl_conv1_pool_planes_f16": (I, [P, I, I, I, P, P, P]),
     "cmlpl_conv2_scene_f16": (I, [P, I, I, I, P, P, P]),
     "cmlpl_pool2_cls_f16": (I, [P, I, I, I, I, I, P, P, P]),
-    "cmlpl_head_lmap_tc": (I, [P, P, I, I, I, I, I, P, P, P, P]),
     "cmlpl_spectral_logits_tc": (I, [P, L, I, I, I, P, P, P, P]),
     "cmlpl_spectral_logits_raw_tc": (I, [P, I, L, I, I, I, P, P, P, P, P, P]),
     "cmlpl_head_sum_lmap": (I, [P, P, I, I, I, I, I, P, P, P, P]),

@@ -84,13 +84,6 @@ __host__ __device__ constexpr int blk_first(int cls) { return cls == 0 ? 0 : (cl
 __host__ __device__ constexpr int blk_start(int b) {
   return b == 0 ? 0 : b == 1 ? 1 : b == 2 ? 4 : b == 3 ? 5 : b == 4 ? 8 : b == 5 ? 17 : b == 6 ? 20 : b == 7 ? 21 : 24;
 }
-__host__ __device__ constexpr int ycls(int cls, int u) { return cls == 0 ? u : (cls == 1 ? 2 : 3 + u); }
-// map index of pooled cell (I, J) in the block-ordered list of 25 (shared with pack.cu / head_sm100.cu)
-__host__ __device__ constexpr int lmap_index(int I, int J) {
-  const int A = I == 0 ? 0 : (I == 4 ? 2 : 1), B = J == 0 ? 0 : (J == 4 ? 2 : 1);
-  return blk_start(A * 3 + B) + (I - blk_first(A)) * blk_n(B) + (J - blk_first(B));
-}
-
 
 // ---- packed BaseNet2 weights (layout shared by pack.cu and the scene kernels) ----
 // All offsets in bytes from the start of the packed buffer, 256-B aligned.

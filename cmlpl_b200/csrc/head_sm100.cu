@@ -169,8 +169,7 @@ constexpr int kHeadStages = 6, kHeadChunkKc = 8, kHeadChunkBytes = kHeadChunkKc 
 __global__ void __launch_bounds__(kHeadThreads, 1)
 head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restrict__ h16, int kc_spe, int64_t mtiles,
             int64_t n, int C, const __half* __restrict__ wc16, const float* __restrict__ bc,
-            uint8_t* __restrict__ labels, float* __restrict__ logits,
-            const float* __restrict__ lmap, int cols, int PR2, int PC2) {
+            uint8_t* __restrict__ labels, float* __restrict__ logits) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -252,23 +251,6 @@ head_kernel(const __half* __restrict__ p2t, int kc_conv, const __half* __restric
       mbar_arrive(bars + 8 * (14 + acc));
       const int64_t p = mt * 128 + L;
       if (p < n) {
-        if (lmap) {
-          // conv part of the classifier from the dense path: 5 gathered row-map vectors M[I][r'+2I, c'] of this pixel's
-          // parity plane (pool2_cls_kernel has already summed the pooled columns J), fixed summation order
-          const int r = int(p / cols), c = int(p - int64_t(r) * cols);
-          const int64_t psz = int64_t(PR2) * PC2;
-          const float4* base = reinterpret_cast<const float4*>(lmap) + int64_t((r & 1) * 2 + (c & 1)) * 20 * psz +
-                               int64_t(r >> 1) * PC2 + (c >> 1);
-#pragma unroll
-          for (int I = 0; I < 5; ++I) {
-            const float4* q = base + int64_t(I * 4) * psz + (2 * I) * PC2;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 t = __ldg(q + int64_t(k) * psz);
-              v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
-            }
-          }
-        }
         float best = -INFINITY; int arg = 0;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -633,35 +615,8 @@ extern "C" int cmlpl_head_tc(const void* p2t, const void* h16, int64_t n, int nu
   const unsigned char* pk = static_cast<const unsigned char*>(packed);
   head_kernel<<<grid, kHeadThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(p2t), kc_conv, static_cast<const __half*>(h16), kc_spe, mtiles, n, num_classes,
-      reinterpret_cast<const __half*>(pk + L.wc16), reinterpret_cast<const float*>(pk + L.bc), labels, logits,
-      nullptr, 0, 0, 0);
+      reinterpret_cast<const __half*>(pk + L.wc16), reinterpret_cast<const float*>(pk + L.bc), labels, logits);
   CMLPL_CHECK_LAUNCH("head");
-  return CMLPL_OK;
-}
-
-// Head of the dense path: spectral columns of the classifier on the tensor core (K = 1024) + the 25 gathered
-// conv partials per pixel from lmap (cmlpl_pool2_cls_f16) + bias, argmax.  Pixels are the band's raster order.
-extern "C" int cmlpl_head_lmap_tc(const void* h16, const float* lmap, int cols, int band_rows, int num_features,
-                                  int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
-                                  cmlpl_stream_t stream) {
-  CMLPL_CHECK_ARG(h16 && lmap && packed && labels, "head_lmap_tc: null pointer");
-  CMLPL_CHECK_ARG(w == 20 && cols > 0 && band_rows > 0, "head_lmap_tc: bad dims (w must be 20)");
-  CMLPL_CHECK_ARG(num_classes > 0 && num_classes <= 16, "head_lmap_tc: needs 1..16 classes, got %d", num_classes);
-  const PackedLayout L = packed_layout(num_features, num_classes, w);
-  const int kc_conv = L.conv_pos * 8, kc_spe = 128;
-  const size_t wbytes = size_t(kc_spe) * 256;
-  const size_t smem = (wbytes + 127) / 128 * 128 + size_t(kHeadStages) * kHeadChunkBytes + 256 + 64;
-  CMLPL_MAX_DYN_SMEM(head_kernel, int(smem));
-  const int64_t n = int64_t(band_rows) * cols;
-  const int64_t mtiles = (n + 127) / 128;
-  int grid = sm_count(); if (grid > mtiles) grid = int(mtiles);
-  const unsigned char* pk = static_cast<const unsigned char*>(packed);
-  // spectral k-chunks follow the conv k-chunks in wc16
-  head_kernel<<<grid, kHeadThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, 0, static_cast<const __half*>(h16), kc_spe, mtiles, n, num_classes,
-      reinterpret_cast<const __half*>(pk + L.wc16 + size_t(kc_conv) * 256), reinterpret_cast<const float*>(pk + L.bc),
-      labels, logits, lmap, cols, (band_rows + w) / 2, (cols + w) / 2);
-  CMLPL_CHECK_LAUNCH("head_lmap");
   return CMLPL_OK;
 }
 

@@ -23,118 +23,12 @@ namespace cmlpl {
 // the RAW cube both operands are split into fp16 hi + lo parts (3 MMAs per K-step), because folding the PCA projection
 // into conv0 makes the contraction ill-conditioned in fp16 -- the noise components of the PCA are differences of band
 // values ~10x larger than the result (measured: with single fp16 operands the B = 200 raw parity test misses the 1e-3
-// logit bar).  The fp32 CUDA-core kernel below is kept for inputs the tensor-core kernel does not take.
+// logit bar).  PCA projection, both z-scores and conv0 are per-pixel affine maps, so they fold into one
+// F0 = Wf . (x - mu) + bf with Wf = W0 . (U/s)^T [64 x B].  Output: mirrored halo baked in, chunk-planar fp16
+// [8 chunks][prow_n][pcol_n][8].
 template <typename T, bool kVec4, bool kSplit>
 int launch_conv0_tc(const T* in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0, int prow_n, int pcol_n,
                     const float* wt, const float* bias, const float* mu, const float* inv_sigma, __half* f0pad, cudaStream_t s);
-
-// conv0 (1x1) once per PADDED scene position, fp32 FFMA, register-tiled: a thread owns 4 consecutive padded
-// positions x 16 output channels (64 accumulators; per input channel 4 loaded inputs + 4 broadcast LDS.128 of
-// weights feed 64 FMAs), the 4 warps of a half-block share the same 128 positions (inputs hit L1), weights
-// [K][64] live in shared memory.  T = float with K = 60 (PCA cube) or the RAW cube (uint16 / float, K = B bands):
-// PCA projection, both z-scores and conv0 are per-pixel affine maps, so they fold into one
-// F0 = Wf . (x - mu) + bf with Wf = W0 . (U/s)^T [64 x B].  Output: mirrored halo baked in,
-// chunk-planar fp16 [8 chunks][prow_n][pcol_n][8].
-template <typename T, bool kVec4>
-__global__ void __launch_bounds__(256, 2)
-conv0_tiled_kernel(const T* __restrict__ in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0,
-                   int prow_n, int pcol_n, const float* __restrict__ wt, const float* __restrict__ bias,
-                   const float* __restrict__ mu, __half* __restrict__ f0pad) {
-  extern __shared__ __align__(16) float sm0[];              // wt [K][64] | bias [64] | mu [K]
-  float* ws = sm0; float* bs = sm0 + K * 64; float* mus = bs + 64;                 // bias right after the weights: 8-byte aligned pairs
-  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) ws[i] = wt[i];
-  for (int i = threadIdx.x; i < K; i += blockDim.x) mus[i] = mu ? mu[i] : 0.f;
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cg = warp & 3;                                  // 16 output channels = chunks 2cg, 2cg+1
-  const int lo = window_lo(w);
-  const int64_t plane = int64_t(prow_n) * pcol_n;
-  const int64_t ngroups = (plane + 3) >> 2;
-  for (int64_t g = (int64_t(blockIdx.x) * 2 + (warp >> 2)) * 32 + lane; g < ngroups; g += int64_t(gridDim.x) * 64) {
-    const T* src[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int64_t pp = g * 4 + j; if (pp >= plane) pp = plane - 1;
-      const int pr = int(pp / pcol_n), pc = int(pp - int64_t(pr) * pcol_n);
-      const int sr = mirror_index(band_row0 + pr + lo, scene_rows) - slab_row0;
-      const int sc = mirror_index(pc + lo, cols);
-      src[j] = in + (int64_t(sr) * cols + sc) * K;
-    }
-    // accumulators as packed pairs: fma.rn.f32x2 (FFMA2) does two fp32 FMAs per issue slot, each rounded exactly like fmaf
-    unsigned long long acc2[4][8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc2[j][c] = *reinterpret_cast<const unsigned long long*>(&bs[cg * 16 + 2 * c]);
-    auto fma_k = [&](int k, const float (&x)[4]) {
-      unsigned long long wv[8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(&ws[k * 64 + cg * 16 + 4 * q]);
-        wv[2 * q] = t.x; wv[2 * q + 1] = t.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        unsigned long long xx;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x[j]));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[j][c]) : "l"(xx), "l"(wv[c]));
-      }
-    };
-    if constexpr (kVec4) {                                  // float rows, 16-byte aligned, K % 4 == 0
-#pragma unroll 1
-      for (int k4 = 0; k4 < K; k4 += 4) {
-        float4 v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(src[j] + k4));
-        { const float x[4] = {v[0].x - mus[k4], v[1].x - mus[k4], v[2].x - mus[k4], v[3].x - mus[k4]}; fma_k(k4, x); }
-        { const float x[4] = {v[0].y - mus[k4 + 1], v[1].y - mus[k4 + 1], v[2].y - mus[k4 + 1], v[3].y - mus[k4 + 1]}; fma_k(k4 + 1, x); }
-        { const float x[4] = {v[0].z - mus[k4 + 2], v[1].z - mus[k4 + 2], v[2].z - mus[k4 + 2], v[3].z - mus[k4 + 2]}; fma_k(k4 + 2, x); }
-        { const float x[4] = {v[0].w - mus[k4 + 3], v[1].w - mus[k4 + 3], v[2].w - mus[k4 + 3], v[3].w - mus[k4 + 3]}; fma_k(k4 + 3, x); }
-      }
-    } else {
-#pragma unroll 2
-      for (int k = 0; k < K; ++k) {
-        const float m = mus[k];
-        const float x[4] = {float(src[0][k]) - m, float(src[1][k]) - m, float(src[2][k]) - m, float(src[3][k]) - m};
-        fma_k(k, x);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t pp = g * 4 + j;
-      if (pp < plane) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          __half2 h[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float lo_, hi_;
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo_), "=f"(hi_) : "l"(acc2[j][q * 4 + e]));
-            h[e] = __floats2half2_rn(lo_, hi_);
-          }
-          *reinterpret_cast<uint4*>(f0pad + (int64_t(cg * 2 + q) * plane + pp) * 8) = *reinterpret_cast<uint4*>(h);
-        }
-      }
-    }
-  }
-}
-
-template <typename T, bool kVec4>
-static int launch_conv0(const T* in, int K, int scene_rows, int cols, int slab_row0, int w, int band_row0, int prow_n,
-                        int pcol_n, const float* wt, const float* bias, const float* mu, __half* f0pad, cudaStream_t s) {
-  const int64_t ngroups = (int64_t(prow_n) * pcol_n + 3) / 4;
-  int64_t grid = (ngroups + 63) / 64;
-  const int64_t cap = int64_t(sm_count()) * 2;
-  if (grid > cap) grid = cap;
-  const size_t smem = sizeof(float) * (size_t(K) * 64 + K + 64);
-  CMLPL_MAX_DYN_SMEM((conv0_tiled_kernel<T, kVec4>), int(smem));
-  conv0_tiled_kernel<T, kVec4><<<int(grid), 256, smem, s>>>(in, K, scene_rows, cols, slab_row0, w, band_row0, prow_n, pcol_n, wt,
-                                                            bias, mu, f0pad);
-  CMLPL_CHECK_LAUNCH("conv0_map");
-  return CMLPL_OK;
-}
 
 // ------------------------------------------------------------------ classifier + argmax
 // one warp per pixel; lanes stride over the K = P*64 pooled features in 8-half chunks.

@@ -201,10 +201,7 @@ int cmlpl_conv1_scene_f16(const void* f0pad, int cols, int w, int band_rows, con
  *   cmlpl_pool2_cls_f16           : rest of the 2x2 avg-pool (middle classes) + conv columns of the classifier per
  *                                   pooled cell (I,J), summed over the pooled columns J of a pooled row I:
  *                                   lmap f32 [4][5 = I][4 class quads][PR2][PC2][4],
- *                                   lmap[I][y',x'] = sum_J L[I][J][y', x'+2J]
- *   cmlpl_head_lmap_tc            : spectral classifier columns (h16 tiles) + the 5 gathered partials
- *                                   lmap[I][r'+2I, c'] of each pixel + bias, argmax -> labels u8 [band_rows*cols]
- *                                   (and logits) */
+ *                                   lmap[I][y',x'] = sum_J L[I][J][y', x'+2J] */
 int cmlpl_conv1_scene_variants_f32(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
                                    cmlpl_stream_t stream);
 int cmlpl_conv1_scene_planes_f16(const void* f0pad, int cols, int w, int band_rows, const void* packed, float* g,
@@ -230,9 +227,6 @@ int cmlpl_spectral_logits_raw_tc(const void* raw, int dtype, int64_t n, int num_
 int cmlpl_head_sum_lmap(const float* part, const float* lmap, int cols, int band_rows, int num_features,
                         int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
                         cmlpl_stream_t stream);
-int cmlpl_head_lmap_tc(const void* h16, const float* lmap, int cols, int band_rows, int num_features,
-                       int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
-                       cmlpl_stream_t stream);
 /* Per-pixel conv2 stage on the pooled conv1 maps of cmlpl_conv1_scene_f16 (models.py:137-140 per patch):
  * pm f16 [9][PR][PC][64] -> p2t UMMA tiles [ceil(n/128)][(w/4)^2*8][128][8] for cmlpl_head_tc. */
 int cmlpl_patch_conv2_f16_tiled(const void* pm, int cols, int w, int band_rows, const void* packed,
