@@ -634,7 +634,7 @@ extern "C" int cmlpl_spectral_logits_raw_tc(const void* raw, int dtype, int64_t 
   return spectral_hidden_impl(raw, dtype, n, num_features, num_classes, w, mu, inv_sigma, packed, x16, part, stream, true);
 }
 
-// Head of the dense path without a GEMM: quarter partials of cmlpl_spectral_logits_tc + the 25 gathered conv partials
+// Head of the dense path without a GEMM: quarter partials of cmlpl_spectral_logits_tc + the 5 gathered conv partials
 // per pixel from lmap (cmlpl_pool2_cls_f16) + bias, argmax.  Pixels are the band's raster order.
 extern "C" int cmlpl_head_sum_lmap(const float* part, const float* lmap, int cols, int band_rows, int num_features,
                                    int num_classes, int w, const void* packed, uint8_t* labels, float* logits,
