@@ -107,3 +107,41 @@ def test_fp16_operand_range(dev, hard):
         lab_ref, log_ref = O.test_whole(sd, h["Xp"], h["Xs"], 20, rows=rows, return_logits=True)
         assert np.isfinite(lg).all() and rel(lg, log_ref) < 1e-3
         assert float(np.mean(lab.cpu().numpy() == lab_ref)) >= 0.999
+
+
+def test_paviau_size_row_band_with_the_trained_net(dev, hard):
+    """a scene of the headline size (610 x 340 x 103: the hard scene tiled 5 x 3 and cropped, so the
+    spectra stay in the distribution of the net the reference trained and the tile seams add new neighbourhoods; stored
+    preprocessing) inferred in ONE call; a 60-row band of it (20 400 pixels, across a seam) through the CPU oracle's
+    test_whole (hyper_tools.py:416-437 per pixel).  >= 99.9 % identical labels, logits 1e-3 * max|ref|, both for the
+    preprocessed entry point and for the raw-cube one."""
+    from cmlpl_b200 import ops, preprocess
+    h, z = hard, hard["z"]
+    R, C, B, K, w = 610, 340, h["B"], h["K"], 20
+    cube = np.ascontiguousarray(np.tile(h["cube"], (5, 3, 1))[:R, :C])
+    Xp, Xs = O.apply_preprocess(cube, h["pp"])
+    Xp, Xs = Xp.astype(np.float32), Xs.astype(np.float32)
+    net = make_net(h, dev)
+    packed = net.packed_weights(w)
+    r0, r1 = 275, 335                                              # 60 rows x 340 columns = 20 400 pixels
+    lab_ref, log_ref = O.test_whole(h["sd"], Xp, Xs, w, rows=(r0, r1), return_logits=True)
+    lab, logits = ops.scene_infer(torch.from_numpy(Xp).to(dev), torch.from_numpy(Xs).to(dev), packed, K, w, want_logits=True)
+    sl = slice(r0 * C, r1 * C)
+    agree = float(np.mean(lab.cpu().numpy()[sl] == lab_ref))
+    print("PaviaU-size band: label agreement %.5f over %d pixels" % (agree, (r1 - r0) * C))
+    assert len(np.unique(lab_ref)) >= 6                            # the band is not a one-class region
+    assert (r1 - r0) * C >= 20000 and agree >= 0.999
+    assert rel(logits.cpu().numpy()[sl], log_ref) < 1e-3
+    tol = 2e-3 * np.abs(log_ref).max()                             # only near-ties of the reference may flip
+    for i in np.nonzero(lab.cpu().numpy()[sl] != lab_ref)[0]:
+        assert log_ref[i].max() - log_ref[i, lab.cpu().numpy()[sl][i]] < tol
+    # the raw-cube entry point on the same scene (preprocessing folded into the first kernels)
+    pp = preprocess.Preproc(mu=h["pp"]["mu"], sigma=h["pp"]["sigma"], U=h["pp"]["U"], pca_mu=h["pp"]["pca_mu"],
+                            pca_sigma=h["pp"]["pca_sigma"])
+    folded = pp.folded_conv0(net.conv0.weight, net.conv0.bias, dev)
+    raw = torch.from_numpy(np.ascontiguousarray(cube.reshape(R * C, B))).to(dev)
+    lab_raw, log_raw = ops.scene_infer_raw(raw, folded, packed, K, C, w, want_logits=True)
+    agree_raw = float(np.mean(lab_raw.cpu().numpy()[sl] == lab_ref))
+    print("PaviaU-size band, raw entry point: label agreement %.5f" % agree_raw)
+    assert agree_raw >= 0.999
+    assert rel(log_raw.cpu().numpy()[sl], log_ref) < 1e-3
