@@ -554,7 +554,6 @@ pool2_cls_kernel(const __grid_constant__ CUtensorMap tm_y, int PR2, int PC2, int
       tc_fence_after();
 #pragma unroll
       for (int Al = 0; Al < 3; ++Al) {
-        constexpr int dummy = 0; (void)dummy;
         const int nI = blk_n(Al), N = nI * 16, nu = Al == 1 ? 2 : 1;
         const uint32_t idesc = make_idesc_f16(128, N);
         const uint32_t dcol = tmem + st * 128 + uint32_t(blk_first(Al) * 16);

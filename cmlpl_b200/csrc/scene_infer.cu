@@ -177,10 +177,11 @@ static SideStream* side_stream() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream& x = per_dev[dev];
-  if (!x.s) {
-    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(x.mu);
+  if (!x.join) {                                             // `join` is created last: set only when all three exist
+    if (!x.s && cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) { x.s = nullptr; return nullptr; }
+    if (!x.fork && cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) { x.fork = nullptr; return nullptr; }
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) { x.join = nullptr; return nullptr; }
   }
   return &x;
 }
